@@ -1,0 +1,322 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference has no tests / golden vectors of its own, so these fixtures --
+inputs, weights, explicit noise, outputs and gradients of the reference modules on seeded
+inputs, true-fp32 ('highest' matmul precision, CPU) -- are what pins ``oracle/port.py`` and,
+through it and directly, the CUDA path.  Everything is stored as float32/int64 ``.npz``.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import port  # noqa: E402
+from oracle.ref_harness import cuda_identity_shim, in_reference_cwd, load_reference  # noqa: E402
+
+ns = load_reference()
+torch.set_num_threads(1)          # deterministic reduction order in the fixtures
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: (npy(v) if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()})
+    print(f"wrote {name}.npz  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def state_arrays(module, prefix="sd."):
+    return {prefix + k: v for k, v in module.state_dict().items()}
+
+
+# ----------------------------------------------------------------------------------------
+# 1. evidence activation                                                   utils.py:46-63
+# ----------------------------------------------------------------------------------------
+def gen_activation():
+    g = torch.Generator().manual_seed(11)
+    h = torch.cat([torch.linspace(-12, 12, 97), torch.randn(927, generator=g) * 4,
+                   torch.tensor([-10.0, 10.0, 0.0, -0.0, 9.999999, -9.999999])])
+    h = h.requires_grad_()
+    e = ns.utils.activation_function(h, "exp")
+    (gr,) = torch.autograd.grad(e.sum(), h)
+    save("activation", h=h, e=e, grad=gr)
+
+
+# ----------------------------------------------------------------------------------------
+# 2. fusion rules + AvgTrustedLoss + uncertainty summaries
+#    utils.py:66-116, models/losses.py:117-248, models/evidential_probe.py:139-143
+# ----------------------------------------------------------------------------------------
+def gen_edl():
+    cfgs = {"c1": (100, 7, 10, 50), "c2": (128, 3, 3, 10), "c3scene": (100, 4, 15, 50),
+            "c3late": (100, 3, 15, 50), "c4": (64, 4, 42, 20), "ragged": (37, 2, 5, 20),
+            "single": (1, 3, 4, 20)}
+    for tag, (B, V, C, astart) in cfgs.items():
+        g = torch.Generator().manual_seed(sum(map(ord, tag)) + 5)
+        h = (torch.randn(B, V, C, generator=g) * 2.0).clamp(-10, 10)
+        evid = ns.utils.activation_function(h, "exp")
+        y = torch.randint(0, C, (B,), generator=g)
+        out = {"evid": evid, "y": y, "annealing_start": astart}
+        for agg, fn in (("cml", ns.utils.get_cml_fusion), ("avg", ns.utils.get_avg_fusion),
+                        ("joint", ns.utils.get_joint_fusion),
+                        ("disentangled", ns.utils.get_disentangled_fusion),
+                        ("dbf", ns.utils.discounted_belief_fusion)):
+            fe = fn(evid.clone())
+            out["fused_" + agg] = fe
+            alphas = fe + 1                                     # evidential_probe.py:139-143
+            denom = alphas.sum(dim=-1, keepdim=True)
+            probs = alphas / denom
+            out["u_" + agg] = (C / denom).squeeze(-1)
+            out["ale_" + agg] = -torch.sum(probs * (torch.digamma(alphas + 1) - torch.digamma(denom + 1)), dim=-1)
+            out["pred_" + agg] = fe.argmax(dim=-1)
+        out["pred_views"] = evid.argmax(dim=-1)
+        for step in (0, 7, astart + 10):
+            for fused in (1, 0):
+                crit = ns.losses.AvgTrustedLoss(num_views=V, annealing_start=astart)
+                crit.annealing_step = step
+                ev = evid.clone().requires_grad_()
+                loss = crit(ev, y, ns.utils.get_cml_fusion(ev), fused=fused)
+                (gr,) = torch.autograd.grad(loss, ev)
+                out[f"loss_s{step}_f{fused}"] = loss
+                out[f"grad_s{step}_f{fused}"] = gr
+        out["steps"] = np.array([0, 7, astart + 10])
+        save("edl_" + tag, **out)
+
+
+# ----------------------------------------------------------------------------------------
+# 3. SupConLoss / ortho_loss                                    models/losses.py:17-110
+# ----------------------------------------------------------------------------------------
+def gen_supcon():
+    for tag, (B, D, unit) in {"b64d16": (64, 16, True), "b96d64": (96, 64, True),
+                              "b33d24raw": (33, 24, False), "b2d8": (2, 8, True)}.items():
+        g = torch.Generator().manual_seed(B * 7 + D)
+        z0 = torch.randn(B, D, generator=g)
+        z1 = (0.6 * z0 + 0.8 * torch.randn(B, D, generator=g))
+        if unit:
+            z0 = z0 / z0.norm(dim=-1, keepdim=True)
+            z1 = z1 / z1.norm(dim=-1, keepdim=True)
+        else:
+            z0, z1 = 0.3 * z0, 0.3 * z1
+        z0.requires_grad_()
+        z1.requires_grad_()
+        crit = ns.losses.SupConLoss()
+        loss, lx, ly = crit(torch.stack([z0, z1], dim=1))
+        g0, g1 = torch.autograd.grad(loss, (z0, z1))
+        a = torch.randn(B, D, generator=g).requires_grad_()
+        b = torch.randn(B, D, generator=g).requires_grad_()
+        ol = ns.losses.ortho_loss(a, b)
+        ga, gb = torch.autograd.grad(ol, (a, b))
+        save("supcon_" + tag, z0=z0, z1=z1, loss=loss, loss_x=lx, loss_y=ly, g0=g0, g1=g1,
+             oa=a, ob=b, ortho=ol, goa=ga, gob=gb)
+
+
+# ----------------------------------------------------------------------------------------
+# 4. DMVAE                                                            models/dmvae.py
+# ----------------------------------------------------------------------------------------
+class _RecordRandnLike:
+    def __enter__(self):
+        self.rec = []
+        self._orig = torch.randn_like
+
+        def rl(t, *a, **k):
+            n = self._orig(t, *a, **k)
+            self.rec.append(n.clone())
+            return n
+        torch.randn_like = rl
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn_like = self._orig
+        return False
+
+
+def gen_dmvae():
+    for tag, (dims, h, e, B, a) in {"scene_small": ([20, 59, 40], 32, 8, 16, 1e-5),
+                                    "hw_small": ([240, 76, 216, 47, 64, 6], 48, 12, 10, 1e-5),
+                                    "syn_small": ([32, 32], 64, 16, 40, 1.0)}.items():
+        torch.manual_seed(3)
+        m = ns.dmvae.DMVAE(output_dim=dims, a=a, hidden_dim=h, embed_dim=e)
+        g = torch.Generator().manual_seed(17)
+        xs = [torch.rand(B, d, generator=g) for d in dims]
+        torch.manual_seed(99)
+        with _RecordRandnLike() as rr:
+            loss, logs = m(xs)
+        loss.backward()
+        out = state_arrays(m)
+        out.update({f"grad.{k}": p.grad for k, p in m.named_parameters()})
+        out.update({f"x{i}": x for i, x in enumerate(xs)})
+        out.update({f"noise{i}": n for i, n in enumerate(rr.rec)})
+        out["loss"] = loss
+        for k in ("loss_joint_recon", "loss_cross_recon", "kl_private", "kl_shared_poe", "kl_shared_uni_sum"):
+            out["log." + k] = np.float32(logs[k])
+        mu_poe, mu_p = m.get_embedding(xs)
+        out["emb_shared"] = mu_poe
+        out.update({f"emb_private{i}": t for i, t in enumerate(mu_p)})
+        out["meta"] = np.array([h, e, B], dtype=np.int64)
+        out["dims"] = np.array(dims, dtype=np.int64)
+        out["a"] = np.float64(a)
+        save("dmvae_" + tag, **out)
+
+
+# ----------------------------------------------------------------------------------------
+# 5. DisentangledSSL                                        models/disentangledssl.py
+# ----------------------------------------------------------------------------------------
+def gen_dssl():
+    for tag, (dims, h, e, B, a) in {"small": ([24, 40], 32, 16, 32, 1.0),
+                                    "wide": ([72, 64], 64, 32, 48, 0.5)}.items():
+        with cuda_identity_shim():
+            torch.manual_seed(5)
+            m = ns.disentangledssl.DisentangledSSL(output_dim=dims, hidden_dim=h, embed_dim=e, a=a,
+                                                   lmd_start_value=0.25)
+            g = torch.Generator().manual_seed(23)
+            x1, x2 = torch.randn(B, dims[0], generator=g), torch.randn(B, dims[1], generator=g)
+            v1 = x1 + 0.01 * torch.randn(B, dims[0], generator=g)
+            v2 = x2 + 0.01 * torch.randn(B, dims[1], generator=g)
+            torch.manual_seed(1234)
+            loss, logs = m(x1, x2, v1, v2)
+            loss.backward()
+            # replay the reference's draw order to obtain the explicit noise
+            torch.manual_seed(1234)
+            noise = [port.draw_vmf_noise(B, e, 1.0) for _ in range(4)]
+            emb_s, emb_p = m.get_embedding([x1, x2])
+        out = state_arrays(m)
+        out.update({f"grad.{k}": p.grad for k, p in m.named_parameters()})
+        out.update(x1=x1, x2=x2, v1=v1, v2=v2, loss=loss, emb_shared=emb_s,
+                   emb_private0=emb_p[0], emb_private1=emb_p[1])
+        for i, (w, v) in enumerate(noise):
+            out[f"noise_w{i}"] = w
+            out[f"noise_v{i}"] = v
+        for k in ("shared", "clip", "loss_x", "loss_y", "specific", "ortho", "lmd"):
+            out["log." + k] = np.float32(logs[k])
+        out["meta"] = np.array([h, e, B], dtype=np.int64)
+        out["dims"] = np.array(dims, dtype=np.int64)
+        out["a"] = np.float64(a)
+        save("dssl_" + tag, **out)
+
+
+# ----------------------------------------------------------------------------------------
+# 6. probes / LateFusion (eval mode: dropout off)
+#    models/evidential_probe.py:87-103,289-304, models/baselines.py:42-70
+# ----------------------------------------------------------------------------------------
+def gen_probes():
+    dims, h, e, B, C = [20, 59, 40], 32, 8, 24, 15
+    torch.manual_seed(3)
+    backbone = ns.dmvae.DMVAE(output_dim=dims, a=1e-5, hidden_dim=h, embed_dim=e)
+    g = torch.Generator().manual_seed(41)
+    xs = [torch.rand(B, d, generator=g) for d in dims]
+    y = torch.randint(0, C, (B,), generator=g)
+    base = state_arrays(backbone, "backbone_sd.")
+    base.update({f"x{i}": x for i, x in enumerate(xs)})
+    base["y"] = y
+    base["dims"] = np.array(dims, dtype=np.int64)
+    base["meta"] = np.array([h, e, B, C], dtype=np.int64)
+
+    for agg in ("cml", "avg", "joint", "disentangled"):
+        torch.manual_seed(8)
+        pm = ns.evidential_probe.EvidentialProbeModule(backbone, num_classes=C, input_dim=e,
+                                                       hidden_dim=(16,), dropout=0.1, annealing_start=50,
+                                                       aggregation=agg, fused=1)
+        pm.eval()
+        pm.criterion.annealing_step = 5
+        loss, ea, _, ev = pm.shared_step([*xs, y])
+        loss.backward()
+        out = dict(base)
+        out.update(state_arrays(pm))
+        out.update({f"grad.{k}": p.grad for k, p in pm.named_parameters() if p.grad is not None})
+        out.update(loss=loss, evidences_a=ea, evidences=ev, annealing_step=5, annealing_start=50)
+        save("probe_" + agg, **out)
+
+    torch.manual_seed(8)
+    dm = ns.evidential_probe.DisentangledEvidentialProbeModule(backbone, num_classes=C, input_dim=e,
+                                                               hidden_dim=(16,), dropout=0.1,
+                                                               annealing_start=50, aggregation="cml")
+    dm.eval()
+    dm.criterion.annealing_step = 60
+    loss, ea, _, ev = dm.shared_step([*xs, y])
+    loss.backward()
+    out = dict(base)
+    out.update(state_arrays(dm))
+    out.update({f"grad.{k}": p.grad for k, p in dm.named_parameters() if p.grad is not None})
+    out.update(loss=loss, evidences_a=ea, evidences=ev, annealing_step=60, annealing_start=50)
+    save("probe_dis_cml", **out)
+
+    for agg in ("dbf", "cml", "avg"):
+        torch.manual_seed(8)
+        lf = ns.baselines.LateFusion([(ns.classifiers.IdentityEncoder, {}) for _ in dims], dims, C,
+                                     dropout=0.1, aggregation=agg, annealing_start=50, hidden_dim=(16,))
+        lf.eval()
+        lf.criterion.annealing_step = 20
+        loss, ea, _, ev = lf.shared_step([*xs, y])
+        loss.backward()
+        out = {f"x{i}": x for i, x in enumerate(xs)}
+        out.update(y=y, dims=np.array(dims, dtype=np.int64), meta=np.array([0, 0, B, C], dtype=np.int64))
+        out.update(state_arrays(lf))
+        out.update({f"grad.{k}": p.grad for k, p in lf.named_parameters() if p.grad is not None})
+        out.update(loss=loss, evidences_a=ea, evidences=ev, annealing_step=20, annealing_start=50)
+        save("latefusion_" + agg, **out)
+
+
+# ----------------------------------------------------------------------------------------
+# 7. real data slice: HandWritten (6 views) first rows after the dataset's MinMax scaling
+#    datasets/dataset.py:164-221,273-279  -> LateFusion(cml) on the real features
+# ----------------------------------------------------------------------------------------
+def gen_handwritten():
+    with in_reference_cwd():
+        ds = ns.dataset.HandWritten()
+    idx = np.arange(0, 2000, 31)[:64]
+    xs = [torch.from_numpy(np.stack([ds[i][v] for i in idx])) for v in range(ds.num_views)]
+    y = torch.from_numpy(np.array([ds[i][-1] for i in idx], dtype=np.int64))
+    dims = [int(d) for d in np.squeeze(ds.dims)]
+    torch.manual_seed(8)
+    lf = ns.baselines.LateFusion([(ns.classifiers.IdentityEncoder, {}) for _ in dims], dims, ds.num_classes,
+                                 dropout=0.1, aggregation="cml", annealing_start=50, hidden_dim=(32,))
+    lf.eval()
+    lf.criterion.annealing_step = 3
+    loss, ea, _, ev = lf.shared_step([*xs, y])
+    loss.backward()
+    out = {f"x{i}": x for i, x in enumerate(xs)}
+    out.update(y=y, dims=np.array(dims, dtype=np.int64), meta=np.array([0, 0, len(idx), ds.num_classes], dtype=np.int64))
+    out.update(state_arrays(lf))
+    out.update({f"grad.{k}": p.grad for k, p in lf.named_parameters() if p.grad is not None})
+    out.update(loss=loss, evidences_a=ea, evidences=ev, annealing_step=3, annealing_start=50)
+    save("latefusion_handwritten", **out)
+
+
+# ----------------------------------------------------------------------------------------
+# 8. vMF sampler draw order                              models/classifiers.py:314-431
+# ----------------------------------------------------------------------------------------
+def gen_vmf():
+    B, D = 40, 16
+    g = torch.Generator().manual_seed(2)
+    e = torch.randn(B, D, generator=g).requires_grad_()
+    with cuda_identity_shim():
+        ph = ns.classifiers.ProbabilisticEncoder(torch.nn.Identity(), distribution="vmf", vmfkappa=1)
+        torch.manual_seed(77)
+        dist, _ = ph(e)
+        z = dist.rsample()
+    (ge,) = torch.autograd.grad((z * torch.arange(D, dtype=torch.float32)).sum(), e)
+    torch.manual_seed(77)
+    w, v = port.draw_vmf_noise(B, D, 1.0)
+    save("vmf", e=e, z=z, w=w, v=v, grad_e=ge)
+
+
+if __name__ == "__main__":
+    gen_activation()
+    gen_edl()
+    gen_supcon()
+    gen_dmvae()
+    gen_dssl()
+    gen_probes()
+    gen_handwritten()
+    gen_vmf()

@@ -1,0 +1,573 @@
+// Memory-bound row / elementwise kernels of the hot path (all fp32 math, coalesced access):
+//   row normalisation (F.normalize, models/losses.py:105-106, disentangledssl.py:139-140)
+//   vMF reparameterised sample given noise + its backward (models/classifiers.py:314-335,433-466)
+//   device-side vMF noise draw (Wood's rejection sampler)
+//   DMVAE head: chunk / reparameterise / PoE / KL and backward (models/dmvae.py:74-112,142-176)
+//   DMVAE reconstruction MSE fused with its gradient (models/dmvae.py:155,164)
+//   fused flat-buffer Adam/AdamW (torch.optim semantics; models/dmvae.py:204-210)
+//   fp32->bf16 casts / transposes feeding the tensor-core path
+#include "common.cuh"
+#include <curand_kernel.h>
+
+namespace dmf {
+
+// ------------------------------------------------------------------------------------------
+// row normalisation: one warp per row
+// ------------------------------------------------------------------------------------------
+__global__ void row_normalize_fwd_kernel(const float* __restrict__ X, long long ldx, int rows, int D, float eps,
+                                         float* __restrict__ Y, long long ldy, uint16_t* __restrict__ Yb,
+                                         long long ldyb, float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* x = X + (long long)row * ldx;
+  float ss = 0.f;
+  for (int k = lane; k < D; k += 32) { const float v = x[k]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), eps);
+  if (lane == 0 && inv_norm) inv_norm[row] = inv;
+  for (int k = lane; k < D; k += 32) {
+    const float y = x[k] * inv;
+    if (Y) Y[(long long)row * ldy + k] = y;
+    if (Yb) Yb[(long long)row * ldyb + k] = f2bf(y);
+  }
+}
+
+__global__ void row_normalize_bwd_kernel(const float* __restrict__ Y, long long ldy, const float* __restrict__ inv_norm,
+                                         const float* __restrict__ dY, long long lddy, int rows, int D,
+                                         float* __restrict__ dX, long long lddx, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* y = Y + (long long)row * ldy;
+  const float* dy = dY + (long long)row * lddy;
+  float dot = 0.f;
+  for (int k = lane; k < D; k += 32) dot = fmaf(y[k], dy[k], dot);
+  dot = warp_sum(dot);
+  const float inv = inv_norm[row];
+  float* dx = dX + (long long)row * lddx;
+  for (int k = lane; k < D; k += 32) {
+    const float v = (dy[k] - y[k] * dot) * inv;
+    dx[k] = accumulate ? dx[k] + v : v;
+  }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ G, long long n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = G[i];
+    s = fmaf(v, v, s);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// vMF rsample given noise: one warp per row
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float vmf_x(const float* __restrict__ v, float w, float wt, int k) {
+  return k == 0 ? w : wt * v[k - 1];
+}
+
+__global__ void vmf_fwd_kernel(const float* __restrict__ E, long long lde, const float* __restrict__ nw,
+                               const float* __restrict__ nv, int rows, int D, float* __restrict__ Z, long long ldz,
+                               uint16_t* __restrict__ Zb, long long ldzb) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* e = E + (long long)row * lde;
+  const float* v = nv + (long long)row * (D - 1);
+  const float w = nw[row];
+  const float wt = sqrtf(fmaxf(1.0f - w * w, 1e-10f));
+  float ss = 0.f;
+  for (int k = lane; k < D; k += 32) ss = fmaf(e[k], e[k], ss);
+  ss = warp_sum(ss);
+  const float inv_n = 1.0f / sqrtf(ss);
+  float nu2 = 0.f, xu = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float up = (k == 0 ? 1.0f : 0.0f) - e[k] * inv_n;
+    nu2 = fmaf(up, up, nu2);
+    xu = fmaf(vmf_x(v, w, wt, k), up, xu);
+  }
+  nu2 = warp_sum(nu2);
+  xu = warp_sum(xu);
+  const float inv_d = 1.0f / (sqrtf(nu2) + 1e-5f);
+  const float c2 = 2.0f * xu * inv_d * inv_d;   // 2 <x,u> / (|u'|+eps)
+  for (int k = lane; k < D; k += 32) {
+    const float up = (k == 0 ? 1.0f : 0.0f) - e[k] * inv_n;
+    const float z = vmf_x(v, w, wt, k) - c2 * up;
+    if (Z) Z[(long long)row * ldz + k] = z;
+    if (Zb) Zb[(long long)row * ldzb + k] = f2bf(z);
+  }
+}
+
+__global__ void vmf_bwd_kernel(const float* __restrict__ E, long long lde, const float* __restrict__ nw,
+                               const float* __restrict__ nv, const float* __restrict__ dZ, long long lddz, int rows,
+                               int D, float* __restrict__ dE, long long ldde, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* e = E + (long long)row * lde;
+  const float* v = nv + (long long)row * (D - 1);
+  const float* g = dZ + (long long)row * lddz;
+  const float w = nw[row];
+  const float wt = sqrtf(fmaxf(1.0f - w * w, 1e-10f));
+  float ss = 0.f;
+  for (int k = lane; k < D; k += 32) ss = fmaf(e[k], e[k], ss);
+  ss = warp_sum(ss);
+  const float inv_n = 1.0f / sqrtf(ss);
+  float nu2 = 0.f, xu = 0.f, gu = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float up = (k == 0 ? 1.0f : 0.0f) - e[k] * inv_n;
+    nu2 = fmaf(up, up, nu2);
+    xu = fmaf(vmf_x(v, w, wt, k), up, xu);
+    gu = fmaf(g[k], up, gu);
+  }
+  nu2 = warp_sum(nu2);
+  xu = warp_sum(xu);
+  gu = warp_sum(gu);
+  const float nu = fmaxf(sqrtf(nu2), 1e-30f);
+  const float inv_d = 1.0f / (nu + 1e-5f);
+  const float c = xu * inv_d;      // <x,u>
+  const float gdu = gu * inv_d;    // <g,u>
+  // du_k = -2 (gdu x_k + c g_k);  accumulate <du,u'>, <du,loc>, <u',loc>
+  float du_up = 0.f, du_loc = 0.f, up_loc = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float loc = e[k] * inv_n;
+    const float up = (k == 0 ? 1.0f : 0.0f) - loc;
+    const float du = -2.0f * (gdu * vmf_x(v, w, wt, k) + c * g[k]);
+    du_up = fmaf(du, up, du_up);
+    du_loc = fmaf(du, loc, du_loc);
+    up_loc = fmaf(up, loc, up_loc);
+  }
+  du_up = warp_sum(du_up);
+  du_loc = warp_sum(du_loc);
+  up_loc = warp_sum(up_loc);
+  const float duu = du_up * inv_d;              // <du,u>
+  const float r = duu / nu;                     // coefficient of u' in du'
+  // du'_k = (du_k - r u'_k) * inv_d ; dloc = -du' ; <dloc,loc> = -(du_loc - r up_loc) * inv_d
+  const float dloc_loc = -(du_loc - r * up_loc) * inv_d;
+  float* de = dE + (long long)row * ldde;
+  for (int k = lane; k < D; k += 32) {
+    const float loc = e[k] * inv_n;
+    const float up = (k == 0 ? 1.0f : 0.0f) - loc;
+    const float du = -2.0f * (gdu * vmf_x(v, w, wt, k) + c * g[k]);
+    const float dloc = -(du - r * up) * inv_d;
+    const float val = (dloc - dloc_loc * loc) * inv_n;
+    de[k] = accumulate ? de[k] + val : val;
+  }
+}
+
+// Device-side vMF noise: distribution-equal to VonMisesFisher.__sample_w_rej + the tangent normal
+// draw (models/classifiers.py:349-431), not stream-equal.  One warp per row; Philox4x32-10.
+__device__ float gamma_mt(curandStatePhilox4_32_10_t* st, float alpha) {
+  // Marsaglia-Tsang; alpha < 1 boosted
+  float boost = 1.0f;
+  if (alpha < 1.0f) {
+    boost = powf(curand_uniform(st), 1.0f / alpha);
+    alpha += 1.0f;
+  }
+  const float d = alpha - 1.0f / 3.0f;
+  const float c = rsqrtf(9.0f * d);
+  for (int it = 0; it < 64; ++it) {
+    const float x = curand_normal(st);
+    float vv = 1.0f + c * x;
+    if (vv <= 0.f) continue;
+    vv = vv * vv * vv;
+    const float u = curand_uniform(st);
+    if (logf(u) < 0.5f * x * x + d - d * vv + d * logf(vv)) return d * vv * boost;
+  }
+  return d * boost;
+}
+
+__global__ void vmf_draw_kernel(float* __restrict__ nw, float* __restrict__ nv, int rows, int D, float kappa,
+                                unsigned long long seed, unsigned long long offset) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, (unsigned long long)row * 32 + lane, offset, &st);
+  float* v = nv + (long long)row * (D - 1);
+  float ss = 0.f;
+  for (int k = lane; k < D - 1; k += 32) {
+    const float z = curand_normal(&st);
+    v[k] = z;
+    ss = fmaf(z, z, ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(fmaxf(ss, 1e-30f));
+  for (int k = lane; k < D - 1; k += 32) v[k] *= inv;
+  if (lane == 0) {
+    const float m1 = (float)(D - 1);
+    const float c = sqrtf(4.0f * kappa * kappa + m1 * m1);
+    const float b_true = (-2.0f * kappa + c) / m1;
+    const float b_app = m1 / (4.0f * kappa);
+    const float s = fminf(fmaxf(kappa - 10.0f, 0.f), 1.0f);
+    const float b = b_app * s + b_true * (1.0f - s);
+    const float a = (m1 + 2.0f * kappa + c) / 4.0f;
+    const float d = (4.0f * a * b) / (1.0f + b) - m1 * logf(m1);
+    float w = 0.f;
+    for (int it = 0; it < 256; ++it) {
+      const float g1 = gamma_mt(&st, 0.5f * m1), g2 = gamma_mt(&st, 0.5f * m1);
+      const float eb = g1 / (g1 + g2);
+      const float u = curand_uniform(&st);
+      const float den = 1.0f - (1.0f - b) * eb;
+      w = (1.0f - (1.0f + b) * eb) / den;
+      const float t = (2.0f * a * b) / den;
+      if (m1 * logf(t) - t + d > logf(u)) break;
+    }
+    nw[row] = w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// DMVAE head
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxViews = 16;
+struct ViewPtrs {
+  const float* in[kMaxViews];
+  const float* in2[kMaxViews];
+  float* out[kMaxViews];
+};
+
+__global__ void dmvae_head_fwd_kernel(ViewPtrs P, const float* __restrict__ noise, int N, int B, int e, float poeT,
+                                      float* __restrict__ kl3) {
+  __shared__ float red[32];
+  const long long total = (long long)B * e;
+  float kl_p = 0.f, kl_poe = 0.f, kl_u = 0.f;
+  const float invT = 1.0f / fmaxf(poeT, 1e-8f);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / e), k = (int)(idx - (long long)b * e);
+    float psum = invT;   // prior expert: exp(-0)/T
+    float num = 0.f;
+    float zsu[kMaxViews];
+    for (int i = 0; i < N; ++i) {
+      const float* st = P.in[i] + (long long)b * 4 * e;
+      const float mu_s = st[k], lv_s = st[e + k], mu_p = st[2 * e + k], lv_p = st[3 * e + k];
+      const float zp = mu_p + noise[((long long)i * B + b) * e + k] * expf(0.5f * lv_p);
+      zsu[i] = mu_s + noise[((long long)(N + i) * B + b) * e + k] * expf(0.5f * lv_s);
+      kl_p += -0.5f * (1.0f + lv_p - mu_p * mu_p - expf(lv_p));
+      kl_u += -0.5f * (1.0f + lv_s - mu_s * mu_s - expf(lv_s));
+      const float prec = expf(-lv_s) * invT;
+      psum += prec;
+      num = fmaf(prec, mu_s, num);
+      float* di = P.out[i];
+      for (int j = 0; j < N; ++j) di[((long long)j * B + b) * 2 * e + k] = zp;
+    }
+    psum += 1e-8f;
+    const float var = 1.0f / psum;
+    const float mu = var * num;
+    const float lv = logf(var);
+    kl_poe += -0.5f * (1.0f + lv - mu * mu - expf(lv));
+    const float zs = mu + noise[((long long)(2 * N) * B + b) * e + k] * expf(0.5f * lv);
+    for (int i = 0; i < N; ++i) {
+      float* di = P.out[i];
+      for (int j = 0; j < N; ++j) di[((long long)j * B + b) * 2 * e + e + k] = (j == i) ? zs : zsu[j];
+    }
+  }
+  const float invB = 1.0f / (float)B;
+  const float s0 = block_sum(kl_p, red), s1 = block_sum(kl_poe, red), s2 = block_sum(kl_u, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(kl3 + 0, s0 * invB);
+    atomicAdd(kl3 + 1, s1 * invB);
+    atomicAdd(kl3 + 2, s2 * invB);
+  }
+}
+
+// P.in = stats, P.in2 = d_dec_in, P.out = d_stats
+__global__ void dmvae_head_bwd_kernel(ViewPtrs P, const float* __restrict__ noise, int N, int B, int e, float poeT,
+                                      const float* __restrict__ kl_grad3) {
+  const long long total = (long long)B * e;
+  const float invT = 1.0f / fmaxf(poeT, 1e-8f);
+  const float invB = 1.0f / (float)B;
+  const float wkl_p = __ldg(kl_grad3 + 0) * invB, wkl_poe = __ldg(kl_grad3 + 1) * invB, wkl_u = __ldg(kl_grad3 + 2) * invB;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / e), k = (int)(idx - (long long)b * e);
+    // PoE forward pieces
+    float psum = invT, num = 0.f;
+    for (int i = 0; i < N; ++i) {
+      const float* st = P.in[i] + (long long)b * 4 * e;
+      const float prec = expf(-st[e + k]) * invT;
+      psum += prec;
+      num = fmaf(prec, st[k], num);
+    }
+    psum += 1e-8f;
+    const float var = 1.0f / psum, mu = var * num, lv = logf(var);
+    const float eps_s = noise[((long long)(2 * N) * B + b) * e + k];
+    float dzs = 0.f;
+    for (int i = 0; i < N; ++i) dzs += P.in2[i][((long long)i * B + b) * 2 * e + e + k];
+    const float dmu = dzs + wkl_poe * mu;
+    const float dlv = dzs * eps_s * 0.5f * expf(0.5f * lv) + wkl_poe * 0.5f * (expf(lv) - 1.0f);
+    const float dnum = dmu * var;
+    const float dpsum = -dlv * var - dmu * mu * var;
+    for (int i = 0; i < N; ++i) {
+      const float* st = P.in[i] + (long long)b * 4 * e;
+      const float mu_s = st[k], lv_s = st[e + k], mu_p = st[2 * e + k], lv_p = st[3 * e + k];
+      float dzp = 0.f, dzu = 0.f;
+      for (int j = 0; j < N; ++j) dzp += P.in2[i][((long long)j * B + b) * 2 * e + k];
+      for (int j = 0; j < N; ++j)
+        if (j != i) dzu += P.in2[j][((long long)i * B + b) * 2 * e + e + k];
+      const float eps_p = noise[((long long)i * B + b) * e + k];
+      const float eps_u = noise[((long long)(N + i) * B + b) * e + k];
+      const float prec = expf(-lv_s) * invT;
+      const float dprec = dpsum + dnum * mu_s;
+      float* ds = P.out[i] + (long long)b * 4 * e;
+      ds[k] = dzu + wkl_u * mu_s + dnum * prec;
+      ds[e + k] = dzu * eps_u * 0.5f * expf(0.5f * lv_s) + wkl_u * 0.5f * (expf(lv_s) - 1.0f) - dprec * prec;
+      ds[2 * e + k] = dzp + wkl_p * mu_p;
+      ds[3 * e + k] = dzp * eps_p * 0.5f * expf(0.5f * lv_p) + wkl_p * 0.5f * (expf(lv_p) - 1.0f);
+    }
+  }
+}
+
+__global__ void dmvae_poe_mean_kernel(ViewPtrs P, int N, int B, int e, float poeT, float* __restrict__ mu_out) {
+  const long long total = (long long)B * e;
+  const float invT = 1.0f / fmaxf(poeT, 1e-8f);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / e), k = (int)(idx - (long long)b * e);
+    float psum = invT, num = 0.f;
+    for (int i = 0; i < N; ++i) {
+      const float* st = P.in[i] + (long long)b * 4 * e;
+      const float prec = expf(-st[e + k]) * invT;
+      psum += prec;
+      num = fmaf(prec, st[k], num);
+    }
+    psum += 1e-8f;
+    mu_out[idx] = (1.0f / psum) * num;
+  }
+}
+
+__global__ void dmvae_mse_kernel(const float* __restrict__ recon, long long ldr, const float* __restrict__ x,
+                                 long long ldx, int N, int B, int d, int view, float w_joint, float w_cross,
+                                 const float* __restrict__ gscale, float* __restrict__ out2,
+                                 float* __restrict__ d_recon, long long lddr) {
+  __shared__ float red[32];
+  const long long total = (long long)N * B * d;
+  const float g = gscale ? __ldg(gscale) : 1.0f;
+  const float inv = 1.0f / ((float)B * (float)d);
+  float sj = 0.f, sc = 0.f;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / d;
+    const int c = (int)(idx - row * d);
+    const int j = (int)(row / B), b = (int)(row - (long long)j * B);
+    const float diff = recon[row * ldr + c] - x[(long long)b * ldx + c];
+    const float w = (j == view) ? w_joint : w_cross;
+    if (j == view) sj = fmaf(diff, diff, sj); else sc = fmaf(diff, diff, sc);
+    if (d_recon) d_recon[row * lddr + c] = g * w * 2.0f * diff * inv;
+  }
+  const float s0 = block_sum(sj, red), s1 = block_sum(sc, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(out2 + 0, w_joint * s0 * inv);
+    atomicAdd(out2 + 1, w_cross * s1 * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam / AdamW over a flat buffer
+// ------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
+                            float wd, int decoupled, float step_size, float inv_bc2_sqrt, float gscale,
+                            uint16_t* __restrict__ pb) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    float gi = g[i] * gscale;
+    if (wd != 0.f) {
+      if (decoupled) pi *= (1.0f - lr * wd);
+      else gi = fmaf(wd, pi, gi);
+    }
+    float mi = m[i], vi = v[i];
+    mi = mi + (gi - mi) * (1.0f - beta1);
+    vi = vi * beta2 + (1.0f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+    pi = pi - step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (pb) pb[i] = f2bf(pi);
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, long long n, float value) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = value;
+}
+
+// ------------------------------------------------------------------------------------------
+// casts / transposes
+// ------------------------------------------------------------------------------------------
+__global__ void cast_bf16_kernel(const float* __restrict__ src, long long lds, uint16_t* __restrict__ dst,
+                                 long long ldd, int rows, int cols) {
+  const long long total = (long long)rows * cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cols;
+    const int c = (int)(idx - r * cols);
+    dst[r * ldd + c] = f2bf(src[r * lds + c]);
+  }
+}
+
+template <typename TIn>
+__global__ void transpose_to_bf16_kernel(const TIn* __restrict__ src, long long lds, uint16_t* __restrict__ dst,
+                                         long long ldd, int rows, int cols) {
+  __shared__ uint16_t tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    uint16_t v = 0;
+    if (r < rows && c < cols) {
+      if (sizeof(TIn) == 4) v = f2bf(reinterpret_cast<const float*>(src)[(long long)r * lds + c]);
+      else v = reinterpret_cast<const uint16_t*>(src)[(long long)r * lds + c];
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(long long)c * ldd + r] = tile[threadIdx.x][i];
+  }
+}
+
+inline int grid_for(long long n, int threads = 256) {
+  long long b = (n + threads - 1) / threads;
+  const long long cap = (long long)kNumSMs * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace dmf
+
+using namespace dmf;
+
+extern "C" int dmf_row_normalize_fwd(const float* X, long long ldx, int rows, int D, float eps, float* Y, long long ldy,
+                                     uint16_t* Yb, long long ldyb, float* inv_norm, dmf_stream_t s) {
+  DMF_REQUIRE(X && (Y || Yb) && rows >= 0 && D >= 1, "dmf_row_normalize_fwd: bad arguments");
+  if (rows == 0) return 0;
+  row_normalize_fwd_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(X, ldx, rows, D, eps, Y, ldy, Yb, ldyb, inv_norm);
+  return launched("dmf_row_normalize_fwd");
+}
+extern "C" int dmf_row_normalize_bwd(const float* Y, long long ldy, const float* inv_norm, const float* dY, long long lddy,
+                                     int rows, int D, float* dX, long long lddx, int accumulate, dmf_stream_t s) {
+  DMF_REQUIRE(Y && inv_norm && dY && dX && rows >= 0 && D >= 1, "dmf_row_normalize_bwd: bad arguments");
+  if (rows == 0) return 0;
+  row_normalize_bwd_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(Y, ldy, inv_norm, dY, lddy, rows, D, dX, lddx, accumulate);
+  return launched("dmf_row_normalize_bwd");
+}
+extern "C" int dmf_sumsq_f32(const float* G, long long n, float* out, dmf_stream_t s) {
+  DMF_REQUIRE(G && out && n >= 0, "dmf_sumsq_f32: bad arguments");
+  if (n == 0) return 0;
+  sumsq_kernel<<<grid_for(n), 256, 0, (cudaStream_t)s>>>(G, n, out);
+  return launched("dmf_sumsq_f32");
+}
+
+extern "C" int dmf_vmf_fwd(const float* E, long long lde, const float* nw, const float* nv, int rows, int D, float* Z,
+                           long long ldz, uint16_t* Zb, long long ldzb, dmf_stream_t s) {
+  DMF_REQUIRE(E && nw && nv && (Z || Zb) && rows >= 0 && D >= 2, "dmf_vmf_fwd: bad arguments");
+  if (rows == 0) return 0;
+  vmf_fwd_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(E, lde, nw, nv, rows, D, Z, ldz, Zb, ldzb);
+  return launched("dmf_vmf_fwd");
+}
+extern "C" int dmf_vmf_bwd(const float* E, long long lde, const float* nw, const float* nv, const float* dZ, long long lddz,
+                           int rows, int D, float* dE, long long ldde, int accumulate, dmf_stream_t s) {
+  DMF_REQUIRE(E && nw && nv && dZ && dE && rows >= 0 && D >= 2, "dmf_vmf_bwd: bad arguments");
+  if (rows == 0) return 0;
+  vmf_bwd_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(E, lde, nw, nv, dZ, lddz, rows, D, dE, ldde, accumulate);
+  return launched("dmf_vmf_bwd");
+}
+extern "C" int dmf_vmf_draw(float* nw, float* nv, int rows, int D, float kappa, unsigned long long seed,
+                            unsigned long long offset, dmf_stream_t s) {
+  DMF_REQUIRE(nw && nv && rows >= 0 && D >= 2 && D != 3 && kappa > 0.f, "dmf_vmf_draw: bad arguments (D=3 uses the host sampler)");
+  if (rows == 0) return 0;
+  vmf_draw_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(nw, nv, rows, D, kappa, seed, offset);
+  return launched("dmf_vmf_draw");
+}
+
+static int fill_views(ViewPtrs& P, const float* const* in, const float* const* in2, float* const* out, int N) {
+  for (int i = 0; i < N; ++i) {
+    P.in[i] = in ? in[i] : nullptr;
+    P.in2[i] = in2 ? in2[i] : nullptr;
+    P.out[i] = out ? out[i] : nullptr;
+  }
+  return 0;
+}
+
+extern "C" int dmf_dmvae_head_fwd(const float* const* stats, const float* noise, int N, int B, int e, float poeT,
+                                  float* const* dec_in, float* kl3, dmf_stream_t s) {
+  DMF_REQUIRE(stats && noise && dec_in && kl3, "dmf_dmvae_head_fwd: null argument");
+  DMF_REQUIRE(N >= 1 && N <= kMaxViews && B >= 1 && e >= 1, "dmf_dmvae_head_fwd: bad shape N=%d B=%d e=%d", N, B, e);
+  ViewPtrs P;
+  fill_views(P, stats, nullptr, dec_in, N);
+  dmvae_head_fwd_kernel<<<grid_for((long long)B * e), 256, 0, (cudaStream_t)s>>>(P, noise, N, B, e, poeT, kl3);
+  return launched("dmf_dmvae_head_fwd");
+}
+extern "C" int dmf_dmvae_head_bwd(const float* const* stats, const float* noise, const float* const* d_dec_in, int N,
+                                  int B, int e, float poeT, const float* kl_grad3, float* const* d_stats,
+                                  dmf_stream_t s) {
+  DMF_REQUIRE(stats && noise && d_dec_in && d_stats && kl_grad3, "dmf_dmvae_head_bwd: null argument");
+  DMF_REQUIRE(N >= 1 && N <= kMaxViews && B >= 1 && e >= 1, "dmf_dmvae_head_bwd: bad shape");
+  ViewPtrs P;
+  fill_views(P, stats, d_dec_in, d_stats, N);
+  dmvae_head_bwd_kernel<<<grid_for((long long)B * e), 256, 0, (cudaStream_t)s>>>(P, noise, N, B, e, poeT, kl_grad3);
+  return launched("dmf_dmvae_head_bwd");
+}
+extern "C" int dmf_dmvae_poe_mean(const float* const* stats, int N, int B, int e, float poeT, float* mu_poe, dmf_stream_t s) {
+  DMF_REQUIRE(stats && mu_poe && N >= 1 && N <= kMaxViews && B >= 1 && e >= 1, "dmf_dmvae_poe_mean: bad arguments");
+  ViewPtrs P;
+  fill_views(P, stats, nullptr, nullptr, N);
+  dmvae_poe_mean_kernel<<<grid_for((long long)B * e), 256, 0, (cudaStream_t)s>>>(P, N, B, e, poeT, mu_poe);
+  return launched("dmf_dmvae_poe_mean");
+}
+extern "C" int dmf_dmvae_mse_fwd_bwd(const float* recon, long long ldr, const float* x, long long ldx, int N, int B, int d,
+                                     int view, float w_joint, float w_cross, const float* gscale, float* out2,
+                                     float* d_recon, long long lddr, dmf_stream_t s) {
+  DMF_REQUIRE(recon && x && out2 && N >= 1 && B >= 1 && d >= 1, "dmf_dmvae_mse_fwd_bwd: bad arguments");
+  dmvae_mse_kernel<<<grid_for((long long)N * B * d), 256, 0, (cudaStream_t)s>>>(recon, ldr, x, ldx, N, B, d, view, w_joint,
+                                                                                w_cross, gscale, out2, d_recon, lddr);
+  return launched("dmf_dmvae_mse_fwd_bwd");
+}
+
+extern "C" int dmf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                             float eps, float wd, int decoupled, int step, float grad_scale, uint16_t* p_bf16,
+                             dmf_stream_t s) {
+  DMF_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "dmf_adam_step: bad arguments");
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, decoupled, step_size,
+                                                        inv_bc2_sqrt, grad_scale, p_bf16);
+  return launched("dmf_adam_step");
+}
+extern "C" int dmf_fill_f32(float* p, long long n, float value, dmf_stream_t s) {
+  DMF_REQUIRE(p && n >= 0, "dmf_fill_f32: bad arguments");
+  if (n == 0) return 0;
+  fill_kernel<<<grid_for(n), 256, 0, (cudaStream_t)s>>>(p, n, value);
+  return launched("dmf_fill_f32");
+}
+
+extern "C" int dmf_cast_f32_to_bf16(const float* src, long long lds, uint16_t* dst, long long ldd, int rows, int cols,
+                                    dmf_stream_t s) {
+  DMF_REQUIRE(src && dst && rows >= 0 && cols >= 0, "dmf_cast_f32_to_bf16: bad arguments");
+  if (rows == 0 || cols == 0) return 0;
+  cast_bf16_kernel<<<grid_for((long long)rows * cols), 256, 0, (cudaStream_t)s>>>(src, lds, dst, ldd, rows, cols);
+  return launched("dmf_cast_f32_to_bf16");
+}
+extern "C" int dmf_cast_transpose_f32_to_bf16(const float* src, long long lds, uint16_t* dst, long long ldd, int rows,
+                                              int cols, dmf_stream_t s) {
+  DMF_REQUIRE(src && dst && rows >= 0 && cols >= 0, "dmf_cast_transpose_f32_to_bf16: bad arguments");
+  if (rows == 0 || cols == 0) return 0;
+  dim3 block(32, 8), grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_to_bf16_kernel<float><<<grid, block, 0, (cudaStream_t)s>>>(src, lds, dst, ldd, rows, cols);
+  return launched("dmf_cast_transpose_f32_to_bf16");
+}
+extern "C" int dmf_transpose_bf16(const uint16_t* src, long long lds, uint16_t* dst, long long ldd, int rows, int cols,
+                                  dmf_stream_t s) {
+  DMF_REQUIRE(src && dst && rows >= 0 && cols >= 0, "dmf_transpose_bf16: bad arguments");
+  if (rows == 0 || cols == 0) return 0;
+  dim3 block(32, 8), grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_to_bf16_kernel<uint16_t><<<grid, block, 0, (cudaStream_t)s>>>(src, lds, dst, ldd, rows, cols);
+  return launched("dmf_transpose_bf16");
+}

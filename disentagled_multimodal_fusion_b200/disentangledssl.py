@@ -1,0 +1,178 @@
+"""Mirror of the reference's ``models/disentangledssl.py`` (2-view DisentangledSSL) on the B200 kernels.
+
+``forward(x1, x2, v1, v2)`` keeps the reference signature.  The original and augmented
+streams are stacked along the batch so every MLP layer is ONE grouped launch over both modalities;
+the four SupConLoss calls run in the tiled InfoNCE kernels (no [2B,2B] logits), and under
+torch.distributed the embeddings are all-gathered so negatives are global.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import require_device
+from .classifiers import IdentityEncoder, Linear, grouped_forward
+from .lightning import LightningModule
+from .losses import SupConLoss
+from .utils import ExponentialScheduler, augment_data, draw_vmf_noise
+
+
+class ProbabilisticEncoder(nn.Module):
+    """models/classifiers.py:444-466 ('vmf' branch): kept for surface parity; the sample itself is the
+    fused Householder kernel (ops.vmf_rsample) driven by explicit noise."""
+
+    def __init__(self, net, distribution='vmf', vmfkappa=1):
+        super().__init__()
+        self.net = net
+        self.distribution = distribution
+        self.vmfkappa = vmfkappa
+
+
+class DisentangledSSL(LightningModule):
+    def __init__(self, feature_encoders=None, output_dim=[100, 100], dropout=0., a=1,
+                 optimizer=torch.optim.Adam, hidden_dim=512, embed_dim=100,
+                 distribution='vmf', vmfkappa=1, lr=1e-4, lmd_start_value=0,
+                 lmd_end_value=0, lmd_n_iterations=8000, lmd_start_iteration=0,
+                 ortho_norm=True, condzs=True, usezsx=False, initialization='xavier', epochs=50,
+                 precision="fp32", noise_mode="reference"):
+        super().__init__()
+        if distribution != 'vmf' or not condzs or usezsx:
+            raise NotImplementedError("hot path covers the reference defaults: distribution='vmf', condzs=True, usezsx=False")
+        self.optimizer = optimizer
+        self.num_epochs = epochs
+        x1_dim, x2_dim = int(output_dim[0]), int(output_dim[1])
+        self.N = 2
+        self.x1_dim, self.x2_dim = x1_dim, x2_dim
+        self.hidden_dim, self.embed_dim = hidden_dim, embed_dim
+        if feature_encoders is not None:
+            self.feature_encoders = nn.ModuleList([i[0](**i[1]) for i in feature_encoders])
+        else:
+            self.feature_encoders = nn.ModuleList([IdentityEncoder() for _ in range(len(output_dim))])
+        self.lr = lr
+        self.ortho_norm, self.condzs, self.usezsx = ortho_norm, condzs, usezsx
+        self.vmfkappa = vmfkappa
+        self.iterations = 0
+        if lmd_end_value > 0:
+            self.lmd_scheduler = ExponentialScheduler(start_value=lmd_start_value, end_value=lmd_end_value,
+                                                      n_iterations=lmd_n_iterations, start_iteration=lmd_start_iteration)
+        self.lmd_start_value, self.lmd_end_value = lmd_start_value, lmd_end_value
+        self.a = a
+        self.precision = precision          # 'fp32' (FFMA, 1e-5) | 'bf16' (tcgen05, 2e-2)
+        self.noise_mode = noise_mode        # 'reference' (host generator, reference stream) | 'device'
+        self.noise_seed = 0
+
+        mk = lambda din: Linear(layers=(din, hidden_dim, hidden_dim), output_dims=embed_dim,
+                                initialization=initialization, dropout=0)
+        self.encoder_x1s = mk(x1_dim)
+        self.encoder_x2s = mk(x2_dim)
+        self.phead1 = ProbabilisticEncoder(nn.Identity(), distribution=distribution, vmfkappa=vmfkappa)
+        self.phead2 = ProbabilisticEncoder(nn.Identity(), distribution=distribution, vmfkappa=vmfkappa)
+        self.encoder_x1 = mk(x1_dim + embed_dim)
+        self.encoder_x2 = mk(x2_dim + embed_dim)
+        self.critic = SupConLoss(precision=precision)
+        self.shared_embedding_dim = 2 * embed_dim   # width of get_embedding()[0]
+
+    # ---------- models/disentangledssl.py:67-80
+    @torch.no_grad()
+    def get_embedding(self, x):
+        require_device()
+        x1 = self.feature_encoders[0](x[0].float())
+        x2 = self.feature_encoders[1](x[1].float())
+        zsx1, zsx2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], [x1, x2], precision="fp32")
+        z1x1, z2x2 = grouped_forward([self.encoder_x1, self.encoder_x2], [x1, x2], extras=[zsx1, zsx2], precision="fp32")
+        return torch.cat([zsx1, zsx2], dim=1), [z1x1, z2x2]
+
+    def draw_noise(self, B, device):
+        """Noise of the four rsample() calls in the reference order (zs1, zs2, zsv1, zsv2)."""
+        D = self.embed_dim
+        if self.noise_mode == "device":
+            self.noise_seed += 1
+            return [ops.vmf_draw(B, D, self.vmfkappa, 0x5EED + self.noise_seed, i, device) for i in range(4)]
+        out = []
+        for _ in range(4):
+            w, v = draw_vmf_noise(B, D, float(self.vmfkappa))
+            out.append((w.to(device, non_blocking=True), v.to(device, non_blocking=True)))
+        return out
+
+    # ---------- models/disentangledssl.py:82-160
+    def forward(self, x1, x2, v1, v2, noise=None):
+        require_device()
+        fe = self.feature_encoders
+        x1, v1, x2, v2 = fe[0](x1).float(), fe[0](v1).float(), fe[1](x2).float(), fe[1](v2).float()
+        B = x1.shape[0]
+        D = self.embed_dim
+        dev = x1.device
+        if noise is None:
+            noise = self.draw_noise(B, dev)
+        bf16 = self.precision == "bf16"
+
+        # stack original + augmented rows: one group per modality
+        if bf16:
+            bufs = []
+            for x, v in ((x1, v1), (x2, v2)):
+                d = x.shape[1]
+                buf = torch.empty(2 * B, d + D, dtype=torch.bfloat16, device=dev)
+                ops.cast_bf16(x.contiguous(), buf[:B], d + D)
+                ops.cast_bf16(v.contiguous(), buf[B:], d + D)
+                bufs.append(buf)
+            ins = [bufs[0][:, :x1.shape[1]], bufs[1][:, :x2.shape[1]]]
+        else:
+            ins = [torch.cat([x1, v1], 0), torch.cat([x2, v2], 0)]
+        E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision=self.precision)  # [2B,D] each
+
+        # vMF reparameterised samples (noise rows follow the stacking: modality 1 <- draws 0,2; modality 2 <- 1,3)
+        w1 = torch.cat([noise[0][0], noise[2][0]], 0)
+        vv1 = torch.cat([noise[0][1], noise[2][1]], 0)
+        w2 = torch.cat([noise[1][0], noise[3][0]], 0)
+        vv2 = torch.cat([noise[1][1], noise[3][1]], 0)
+        Z1 = ops.vmf_rsample(E1, w1, vv1)
+        Z2 = ops.vmf_rsample(E2, w2, vv2)
+        joint_loss, loss_x, loss_y = self.critic.pair(Z1[:B], Z2[:B])
+        joint_loss_v, loss_x_v, loss_y_v = self.critic.pair(Z1[B:], Z2[B:])
+        joint_loss = 0.5 * (joint_loss + joint_loss_v)
+        loss_x = 0.5 * (loss_x + loss_x_v)
+        loss_y = 0.5 * (loss_y + loss_y_v)
+        loss_shared = joint_loss
+
+        # private encoders conditioned on the shared code: layer-0 input = [x | e]
+        if bf16:
+            P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], bufs, extras=[E1, E2], precision="bf16")
+        else:
+            P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], ins, extras=[E1, E2], precision="fp32")
+        P1n, P2n = ops.row_normalize(P1), ops.row_normalize(P2)
+        specific_loss_x1, _, _ = self.critic.pair(P1n[:B], P1n[B:])
+        specific_loss_x2, _, _ = self.critic.pair(P2n[:B], P2n[B:])
+        loss_specific = specific_loss_x1 + specific_loss_x2
+
+        lmd = self.lmd_scheduler(self.iterations) if self.lmd_end_value > 0 else self.lmd_start_value
+        loss_ortho = 0.5 * (ops.ortho_loss(P1[:B], E1[:B]) + ops.ortho_loss(P2[:B], E2[:B])) + \
+            0.5 * (ops.ortho_loss(P1[B:], E1[B:]) + ops.ortho_loss(P2[B:], E2[B:]))
+        loss = 2 * loss_shared / (1 + self.a) + self.a * loss_specific / (1 + self.a) + lmd * loss_ortho
+        # device scalars (the reference does seven .item() syncs here)
+        logs = {'loss': loss.detach(), 'shared': loss_shared.detach(), 'clip': joint_loss.detach(),
+                'loss_x': loss_x, 'loss_y': loss_y, 'specific': loss_specific.detach(),
+                'ortho': loss_ortho.detach(), 'lmd': lmd}
+        return loss, logs
+
+    def training_step(self, batch, batch_idx):
+        x1, x2, v1, v2 = self.shared_step(batch)
+        loss, train_logs = self(x1, x2, v1, v2)
+        self.iterations += 1
+        self.log('train_loss', train_logs['loss'], on_epoch=True, prog_bar=True)
+        for k in ('shared', 'clip', 'loss_x', 'loss_y', 'specific', 'ortho', 'lmd'):
+            self.log(k, train_logs[k], on_epoch=True, prog_bar=True)
+        return loss
+
+    def shared_step(self, batch):
+        x1 = batch[0].float().cuda()
+        x2 = batch[1].float().cuda()
+        v1 = augment_data(x1)
+        v2 = augment_data(x2)
+        return x1, x2, v1, v2
+
+    def configure_optimizers(self):
+        optimizer = self.optimizer(self.parameters(), lr=self.lr)
+        scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=self.num_epochs, eta_min=0, last_epoch=-1)
+        return {'optimizer': optimizer,
+                'lr_scheduler': {'scheduler': scheduler, 'interval': 'epoch', 'monitor': 'train_loss'}}

@@ -1,0 +1,67 @@
+"""Data-parallel host logic (one process per GPU, torch.distributed; NCCL on the box, gloo in the CPU
+tests).  The path shards by batch rows: rank r owns rows [r*B/R, (r+1)*B/R) of every view, parameters
+are replicated.  Exchange steps: embeddings + row-LSEs all-gathered inside
+ops.infonce, the ortho Gram all-reduced inside ops.ortho_loss, and here the flat gradient
+all-reduce (SUM: every loss term is already normalised by the GLOBAL batch)."""
+from __future__ import annotations
+
+from typing import Iterable, List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_rows(global_batch: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Row range [begin, end) owned by ``rank``; the global batch must divide evenly so that every
+    rank contributes the same number of anchors to the all-gather."""
+    if global_batch % world_size != 0:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world_size}")
+    per = global_batch // world_size
+    return rank * per, (rank + 1) * per
+
+
+class FlatParams:
+    """Views of all trainable parameters (and their grads) inside two flat fp32 buffers, so that the
+    gradient all-reduce and the fused Adam step are ONE collective / ONE kernel per step."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        o = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + k].view_as(p.data)
+            p.grad = self.grad[o:o + k].view_as(p.data)
+            o += k
+        self.step_count = 0
+
+    def zero_grad(self):
+        self.grad.zero_()
+        o = 0
+        for p in self.params:           # autograd may have replaced .grad; re-point it at the flat buffer
+            k = p.numel()
+            p.grad = self.grad[o:o + k].view_as(p.data)
+            o += k
+
+    def allreduce_grads(self):
+        """SUM over ranks (losses are normalised by the global batch, so no division here)."""
+        rank, ws = world()
+        if ws > 1:
+            dist.all_reduce(self.grad)
+
+    def adam_step(self, lr: float, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False):
+        from . import ops
+        self.step_count += 1
+        ops.adam_step_flat(self.flat, self.grad, self.m, self.v, lr, self.step_count, betas, eps, weight_decay, decoupled)

@@ -1,0 +1,733 @@
+"""torch.autograd.Function wrappers over the C ABI (include/dmf_b200.h).
+
+Every function here launches hand-written sm_100a kernels from libdmf_b200.so on the current
+torch CUDA stream; torch supplies device memory, streams and (for data parallelism) the NCCL
+process group -- nothing else.  ``precision`` is 'fp32' (FFMA path, 1e-5 parity) or 'bf16'
+(tcgen05 tensor-core path, 2e-2 parity).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from ._lib import lib, check, ptr, stream
+
+Tensor = torch.Tensor
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _dist_on() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+# ----------------------------------------------------------------------------------------
+# low-level helpers (no autograd)
+# ----------------------------------------------------------------------------------------
+def gemm_f32(descs: Sequence[dict], epilogue: int) -> None:
+    """descs: dicts with A,a_rs,a_cs,B,b_rs,b_cs,C,ldc,M,N,K and optional bias,aux,ldaux,rowsum_a,accumulate."""
+    L.require_device()
+    for base in range(0, len(descs), 64):
+        chunk = descs[base:base + 64]
+        arr = (L.GemmDesc * len(chunk))()
+        for i, d in enumerate(chunk):
+            g = arr[i]
+            g.A, g.a_rs, g.a_cs = ptr(d["A"]), d["a_rs"], d["a_cs"]
+            g.B, g.b_rs, g.b_cs = ptr(d["B"]), d["b_rs"], d["b_cs"]
+            g.C, g.ldc = ptr(d["C"]), d["ldc"]
+            g.bias = ptr(d.get("bias"))
+            g.aux, g.ldaux = ptr(d.get("aux")), d.get("ldaux", 0)
+            g.rowsum_a = ptr(d.get("rowsum_a"))
+            g.M, g.N, g.K = d["M"], d["N"], d["K"]
+            g.accumulate = d.get("accumulate", 0)
+        check(lib.dmf_grouped_gemm_f32(arr, len(chunk), epilogue, stream()))
+
+
+def gemm_tc(descs: Sequence[dict], epilogue: int) -> None:
+    """descs: dicts with A,lda,B,ldb,M,N,K and out_f32/ldo_f32, out_bf16/ldo_bf16, bias, mask/ldmask."""
+    L.require_device()
+    arr = (L.TcGemmDesc * len(descs))()
+    for i, d in enumerate(descs):
+        g = arr[i]
+        g.A, g.lda, g.B, g.ldb = ptr(d["A"]), d["lda"], ptr(d["B"]), d["ldb"]
+        g.out_f32, g.ldo_f32 = ptr(d.get("out_f32")), d.get("ldo_f32", 0)
+        g.out_bf16, g.ldo_bf16 = ptr(d.get("out_bf16")), d.get("ldo_bf16", 0)
+        g.bias = ptr(d.get("bias"))
+        g.mask_bf16, g.ldmask = ptr(d.get("mask")), d.get("ldmask", 0)
+        g.M, g.N, g.K = d["M"], d["N"], d["K"]
+    check(lib.dmf_grouped_gemm_bf16_tc(arr, len(descs), epilogue, stream()))
+
+
+def cast_bf16(src: Tensor, dst: Optional[Tensor] = None, ldd: Optional[int] = None) -> Tensor:
+    """fp32 [R,C] (row stride src.stride(0)) -> bf16; dst may be a column slice of a wider buffer."""
+    R, Cc = src.shape
+    if dst is None:
+        dst = torch.empty(R, Cc, dtype=torch.bfloat16, device=src.device)
+    check(lib.dmf_cast_f32_to_bf16(ptr(src), src.stride(0), ptr(dst), ldd or dst.stride(0), R, Cc, stream()))
+    return dst
+
+
+def cast_transpose_bf16(src: Tensor) -> Tensor:
+    R, Cc = src.shape
+    Rp = (R + 7) // 8 * 8                       # TMA needs 16-byte row pitch
+    dst = torch.empty(Cc, Rp, dtype=torch.bfloat16, device=src.device)
+    if Rp != R:
+        dst[:, R:].zero_()
+    check(lib.dmf_cast_transpose_f32_to_bf16(ptr(src), src.stride(0), ptr(dst), Rp, R, Cc, stream()))
+    return dst
+
+
+def transpose_bf16(src: Tensor) -> Tensor:
+    R, Cc = src.shape
+    Rp = (R + 7) // 8 * 8
+    dst = torch.empty(Cc, Rp, dtype=torch.bfloat16, device=src.device)
+    if Rp != R:
+        dst[:, R:].zero_()
+    check(lib.dmf_transpose_bf16(ptr(src), src.stride(0), ptr(dst), Rp, R, Cc, stream()))
+    return dst
+
+
+def colsum(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    M, N = x.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=x.device)
+    check(lib.dmf_colsum_f32(ptr(x), x.stride(0), M, N, ptr(out), 0, stream()))
+    return out
+
+
+def vmf_draw(rows: int, D: int, kappa: float, seed: int, offset: int, device) -> Tuple[Tensor, Tensor]:
+    """Device-side vMF noise (distribution-equal to the reference sampler, not stream-equal)."""
+    L.require_device()
+    w = torch.empty(rows, 1, dtype=torch.float32, device=device)
+    v = torch.empty(rows, D - 1, dtype=torch.float32, device=device)
+    check(lib.dmf_vmf_draw(ptr(w), ptr(v), rows, D, float(kappa), seed, offset, stream()))
+    return w, v
+
+
+# ----------------------------------------------------------------------------------------
+# K1  grouped MLP   (models/classifiers.py:16-48, 469-502)
+# ----------------------------------------------------------------------------------------
+class _GroupedMLP(torch.autograd.Function):
+    """forward(cfg, *tensors): tensors = G inputs, G "extra" inputs (None or a tensor whose columns
+    are appended to the input: layer-0 input = [x | extra], gradient flows to ``extra`` only), then
+    per group L weights, then per group L biases.
+    cfg = (G, L, final, precision, dropout_masks) with final in {'none', 'evidence'}.
+    One kernel launch per layer covers all groups."""
+
+    @staticmethod
+    def forward(ctx, cfg, *tensors):
+        L.require_device()
+        G, NL, final, precision, masks = cfg
+        xs = [t for t in tensors[:G]]
+        extras = [t for t in tensors[G:2 * G]]
+        o = 2 * G
+        Ws = [list(tensors[o + g * NL: o + (g + 1) * NL]) for g in range(G)]
+        bs = [list(tensors[o + G * NL + g * NL: o + G * NL + (g + 1) * NL]) for g in range(G)]
+        ctx.cfg = cfg
+        ctx.in_needs_grad = [bool(x.requires_grad) and extras[g] is None for g, x in enumerate(xs)]
+        ctx.extra_cols = [0 if e is None else e.shape[1] for e in extras]
+        ctx.extra_needs_grad = [e is not None and bool(e.requires_grad) for e in extras]
+        if precision == "bf16":
+            outs, saved = _GroupedMLP._fwd_bf16(xs, extras, Ws, bs, G, NL, final)
+        else:
+            xs = [x if e is None else torch.cat([_f32c(x), _f32c(e)], dim=1) for x, e in zip(xs, extras)]
+            outs, saved = _GroupedMLP._fwd_f32(xs, Ws, bs, G, NL, final, masks)
+        ctx.saved = saved
+        ctx.Ws, ctx.bs = Ws, bs
+        return tuple(outs)
+
+    # ---------------- fp32 (FFMA) path
+    @staticmethod
+    def _fwd_f32(xs, Ws, bs, G, NL, final, masks):
+        xs = [_f32c(x) for x in xs]
+        acts = [[x] for x in xs]
+        pre = [None] * G
+        for l in range(NL):
+            last = l == NL - 1
+            descs = []
+            for g in range(G):
+                A = acts[g][-1]
+                W = Ws[g][l]
+                M, K = A.shape
+                N = W.shape[0]
+                out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+                d = dict(A=A, a_rs=A.stride(0), a_cs=1, B=W, b_rs=1, b_cs=W.stride(0), C=out, ldc=N,
+                         bias=bs[g][l], M=M, N=N, K=K)
+                if last and final == "evidence":
+                    pre[g] = torch.empty(M, N, dtype=torch.float32, device=A.device)
+                    d.update(aux=pre[g], ldaux=N)
+                descs.append(d)
+                acts[g].append(out)
+            epi = (L.EPI_BIAS_EVIDENCE if final == "evidence" else L.EPI_BIAS) if last else L.EPI_BIAS_RELU
+            gemm_f32(descs, epi)
+            if not last and masks is not None:
+                for g in range(G):
+                    if masks[g] is not None and masks[g][l] is not None:
+                        acts[g][-1].mul_(masks[g][l])       # inverted-dropout mask (train mode only)
+        outs = [acts[g][-1] for g in range(G)]
+        return outs, dict(acts=acts, pre=pre, masks=masks)
+
+    @staticmethod
+    def _bwd_f32(ctx, grads):
+        G, NL, final, precision, masks = ctx.cfg
+        acts, pre = ctx.saved["acts"], ctx.saved["pre"]
+        Ws = ctx.Ws
+        dev = acts[0][0].device
+        dYs = []
+        for g in range(G):
+            dy = grads[g]
+            if dy is None:
+                dy = torch.zeros_like(acts[g][-1])
+            dy = _f32c(dy)
+            if final == "evidence":
+                dh = torch.empty_like(dy)
+                check(lib.dmf_evidence_bwd(ptr(pre[g]), ptr(acts[g][-1]), ptr(dy), ptr(dh), dy.numel(), stream()))
+                dy = dh
+            dYs.append(dy)
+        dWs = [[None] * NL for _ in range(G)]
+        dbs = [[None] * NL for _ in range(G)]
+        dxs = [None] * G
+        for l in range(NL - 1, -1, -1):
+            wdescs, ddescs = [], []
+            new_dY = [None] * G
+            for g in range(G):
+                X = acts[g][l]
+                dY = dYs[g]
+                M, K = X.shape
+                N = dY.shape[1]
+                dW = torch.empty(N, K, dtype=torch.float32, device=dev)
+                db = torch.empty(N, dtype=torch.float32, device=dev)
+                # dW[n,k] = sum_m dY[m,n] X[m,k];  db[n] = sum_m dY[m,n]  (row sums of the A operand)
+                wdescs.append(dict(A=dY, a_rs=1, a_cs=dY.stride(0), B=X, b_rs=X.stride(0), b_cs=1, C=dW, ldc=K,
+                                   rowsum_a=db, M=N, N=K, K=M))
+                dWs[g][l], dbs[g][l] = dW, db
+                if l > 0 or ctx.in_needs_grad[g]:
+                    W = Ws[g][l]
+                    dX = torch.empty(M, K, dtype=torch.float32, device=dev)
+                    d = dict(A=dY, a_rs=dY.stride(0), a_cs=1, B=W, b_rs=W.stride(0), b_cs=1, C=dX, ldc=K, M=M, N=K, K=N)
+                    if l > 0:
+                        d.update(aux=X, ldaux=X.stride(0))     # ReLU backward: mask by the saved activation
+                    ddescs.append((g, d))
+                    new_dY[g] = dX
+                elif l == 0 and ctx.extra_needs_grad[g]:
+                    W = Ws[g][l]
+                    De = ctx.extra_cols[g]
+                    Wv = W[:, K - De:]                         # only the appended columns need a gradient
+                    dX = torch.empty(M, De, dtype=torch.float32, device=dev)
+                    ddescs.append((g, dict(A=dY, a_rs=dY.stride(0), a_cs=1, B=Wv, b_rs=W.stride(0), b_cs=1, C=dX,
+                                           ldc=De, M=M, N=De, K=N)))
+                    new_dY[g] = dX
+            gemm_f32(wdescs, L.EPI_NONE)
+            if ddescs:
+                if l > 0:
+                    gemm_f32([d for _, d in ddescs], L.EPI_RELU_MASK)
+                    if masks is not None:
+                        for g, _ in ddescs:
+                            if masks[g] is not None and masks[g][l - 1] is not None:
+                                new_dY[g].mul_(masks[g][l - 1])
+                else:
+                    gemm_f32([d for _, d in ddescs], L.EPI_NONE)
+            if l == 0:
+                dxs = new_dY
+            else:
+                dYs = new_dY
+        return dxs, dWs, dbs
+
+    # ---------------- bf16 tensor-core path
+    @staticmethod
+    def _fwd_bf16(xs, extras, Ws, bs, G, NL, final):
+        if final == "evidence":
+            raise L.DmfError("bf16 grouped MLP: evidence epilogue is only built for the fp32 path")
+        dev = xs[0].device
+        a0 = []
+        for x, ex in zip(xs, extras):
+            if ex is not None:
+                # x is a bf16 buffer [M, d + De] whose first d columns are filled; append bf16(extra)
+                De = ex.shape[1]
+                if x.dtype != torch.bfloat16 or x.shape[1] < De:
+                    raise L.DmfError("bf16 grouped MLP: with `extra`, pass the pre-cast bf16 concat buffer as x")
+                d0 = x.shape[1] - De
+                exc = _f32c(ex)
+                check(lib.dmf_cast_f32_to_bf16(ptr(exc), De, x.data_ptr() + 2 * d0, x.stride(0), x.shape[0], De, stream()))
+                a0.append(x)
+            elif x.dtype == torch.bfloat16:
+                a0.append(x)
+            else:
+                x = _f32c(x)
+                K = x.shape[1]
+                Kp = (K + 7) // 8 * 8
+                buf = torch.zeros(x.shape[0], Kp, dtype=torch.bfloat16, device=dev) if Kp != K else \
+                    torch.empty(x.shape[0], K, dtype=torch.bfloat16, device=dev)
+                cast_bf16(x, buf, Kp)
+                a0.append(buf[:, :K] if Kp != K else buf)
+        acts = [[a] for a in a0]
+        Wb = [[None] * NL for _ in range(G)]
+        outs = []
+        for l in range(NL):
+            last = l == NL - 1
+            descs = []
+            for g in range(G):
+                A = acts[g][-1]
+                W = Ws[g][l]
+                N, K = W.shape
+                Kp = (K + 7) // 8 * 8
+                wb = torch.zeros(N, Kp, dtype=torch.bfloat16, device=dev) if Kp != K else \
+                    torch.empty(N, K, dtype=torch.bfloat16, device=dev)
+                cast_bf16(W, wb, Kp)
+                Wb[g][l] = wb
+                M = A.shape[0]
+                d = dict(A=A, lda=A.stride(0), B=wb, ldb=Kp, bias=bs[g][l], M=M, N=N, K=K)
+                if last:
+                    o = torch.empty(M, N, dtype=torch.float32, device=dev)
+                    d.update(out_f32=o, ldo_f32=N)
+                    outs.append(o)
+                else:
+                    Np = (N + 7) // 8 * 8
+                    o = torch.zeros(M, Np, dtype=torch.bfloat16, device=dev) if Np != N else \
+                        torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+                    d.update(out_bf16=o, ldo_bf16=Np)
+                    acts[g].append(o[:, :N] if Np != N else o)
+                descs.append(d)
+            gemm_tc(descs, L.EPI_BIAS if last else L.EPI_BIAS_RELU)
+        return outs, dict(acts=acts, Wb=Wb)
+
+    @staticmethod
+    def _bwd_bf16(ctx, grads):
+        G, NL, final, precision, masks = ctx.cfg
+        acts = ctx.saved["acts"]
+        Ws = ctx.Ws
+        dev = acts[0][0].device
+        dY32 = []
+        for g in range(G):
+            dy = grads[g]
+            if dy is None:
+                dy = torch.zeros(acts[g][0].shape[0], Ws[g][-1].shape[0], dtype=torch.float32, device=dev)
+            dY32.append(_f32c(dy))
+        dWs = [[None] * NL for _ in range(G)]
+        dbs = [[None] * NL for _ in range(G)]
+        dxs = [None] * G
+        dYb = [None] * G
+        for l in range(NL - 1, -1, -1):
+            wdescs, ddescs = [], []
+            next32 = [None] * G
+            nextb = [None] * G
+            for g in range(G):
+                X = acts[g][l]                      # bf16 [M,K]
+                M, K = X.shape
+                N = dY32[g].shape[1]
+                dbs[g][l] = colsum(dY32[g])
+                dYT = cast_transpose_bf16(dY32[g])  # [N, Mp]
+                XT = transpose_bf16(X)              # [K, Mp]
+                dW = torch.empty(N, K, dtype=torch.float32, device=dev)
+                wdescs.append(dict(A=dYT, lda=dYT.stride(0), B=XT, ldb=XT.stride(0), out_f32=dW, ldo_f32=K,
+                                   M=N, N=K, K=M))
+                dWs[g][l] = dW
+                if l == 0 and not ctx.in_needs_grad[g] and ctx.extra_needs_grad[g]:
+                    De = ctx.extra_cols[g]
+                    if dYb[g] is None:
+                        dYb[g] = cast_bf16(dY32[g])
+                    WT = cast_transpose_bf16(Ws[g][l][:, K - De:])      # [De, N]
+                    dX32 = torch.empty(M, De, dtype=torch.float32, device=dev)
+                    ddescs.append(dict(A=dYb[g], lda=dYb[g].stride(0), B=WT, ldb=WT.stride(0), out_f32=dX32,
+                                       ldo_f32=De, M=M, N=De, K=N))
+                    next32[g] = dX32
+                elif l > 0 or ctx.in_needs_grad[g]:
+                    if dYb[g] is None:
+                        Np = (N + 7) // 8 * 8
+                        b = torch.zeros(M, Np, dtype=torch.bfloat16, device=dev) if Np != N else \
+                            torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+                        cast_bf16(dY32[g], b, Np)
+                        dYb[g] = b[:, :N] if Np != N else b
+                    WT = cast_transpose_bf16(Ws[g][l])          # [K, Np]
+                    dX32 = torch.empty(M, K, dtype=torch.float32, device=dev)
+                    d = dict(A=dYb[g], lda=dYb[g].stride(0), B=WT, ldb=WT.stride(0), out_f32=dX32, ldo_f32=K,
+                             M=M, N=K, K=N)
+                    if l > 0:
+                        Kp = (K + 7) // 8 * 8
+                        dXb = torch.zeros(M, Kp, dtype=torch.bfloat16, device=dev) if Kp != K else \
+                            torch.empty(M, K, dtype=torch.bfloat16, device=dev)
+                        d.update(out_bf16=dXb, ldo_bf16=Kp, mask=X, ldmask=X.stride(0))
+                        nextb[g] = dXb[:, :K] if Kp != K else dXb
+                    ddescs.append(d)
+                    next32[g] = dX32
+            gemm_tc(wdescs, L.EPI_NONE)
+            if ddescs:
+                gemm_tc(ddescs, L.EPI_RELU_MASK if l > 0 else L.EPI_NONE)
+            if l == 0:
+                dxs = next32
+            else:
+                dY32, dYb = next32, nextb
+        return dxs, dWs, dbs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        G, NL, final, precision, masks = ctx.cfg
+        if precision == "bf16":
+            dxs, dWs, dbs = _GroupedMLP._bwd_bf16(ctx, grads)
+        else:
+            dxs, dWs, dbs = _GroupedMLP._bwd_f32(ctx, grads)
+        out = [None]
+        out += [dxs[g] if ctx.in_needs_grad[g] else None for g in range(G)]
+        out += [dxs[g] if ctx.extra_needs_grad[g] else None for g in range(G)]
+        for g in range(G):
+            out += dWs[g]
+        for g in range(G):
+            out += dbs[g]
+        return tuple(out)
+
+
+def grouped_mlp(xs: Sequence[Tensor], weights: Sequence[Sequence[Tensor]], biases: Sequence[Sequence[Tensor]],
+                final: str = "none", precision: str = "fp32", dropout_masks=None, extras=None) -> List[Tensor]:
+    """Apply G independent MLPs (Linear->ReLU)*(L-1)->Linear in L launches.  ``weights[g]`` /
+    ``biases[g]`` list the L layers of group g (nn.Linear layout [out,in]).  ``extras[g]`` (optional)
+    is appended column-wise to input g (torch.cat([x, extra], 1) semantics; fp32 path concatenates,
+    bf16 path expects x to be the pre-cast bf16 concat buffer)."""
+    G, NL = len(xs), len(weights[0])
+    flat = list(xs) + (list(extras) if extras is not None else [None] * G)
+    for g in range(G):
+        flat += list(weights[g])
+    for g in range(G):
+        flat += list(biases[g])
+    return list(_GroupedMLP.apply((G, NL, final, precision, dropout_masks), *flat))
+
+
+# ----------------------------------------------------------------------------------------
+# K2  InfoNCE (SupConLoss default path, models/losses.py:17-101)
+# ----------------------------------------------------------------------------------------
+class _InfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z0, z1, temperature, precision):
+        L.require_device()
+        z0, z1 = _f32c(z0), _f32c(z1)
+        Bl, D = z0.shape
+        dev = z0.device
+        world = dist.get_world_size() if _dist_on() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        Bg = Bl * world
+        dt = 1 if precision == "bf16" else 0
+        if dt == 1:
+            a0, a1 = cast_bf16(z0), cast_bf16(z1)
+        else:
+            a0, a1 = z0, z1
+        if world > 1:        # embeddings all-gathered over NVLink so every rank sees global negatives
+            g0 = torch.empty(Bg, D, dtype=a0.dtype, device=dev)
+            g1 = torch.empty(Bg, D, dtype=a1.dtype, device=dev)
+            dist.all_gather_into_tensor(g0, a0)
+            dist.all_gather_into_tensor(g1, a1)
+        else:
+            g0, g1 = a0, a1
+        scale = 1.0 / temperature
+        st = torch.empty(12, Bl, dtype=torch.float32, device=dev)
+        wsb = lib.dmf_rowlse_workspace_bytes(Bl, Bg) if dt == 1 else 0
+        ws = torch.empty(max(1, wsb // 4), dtype=torch.float32, device=dev)
+        off = rank * Bl
+
+        def rowlse(A, Bm, mo, lo, do):
+            check(lib.dmf_rowlse(ptr(A), A.stride(0), Bl, ptr(Bm), Bm.stride(0), Bg, D, scale, ptr(st[mo]), ptr(st[lo]),
+                                 off, ptr(st[do]), ptr(ws), wsb, dt, stream()))
+        rowlse(a0, g1, 0, 1, 2)      # anchors z0 vs all z1: cross block, diag = positive
+        rowlse(a0, g0, 3, 4, 5)      # anchors z0 vs all z0: intra-view block, diag = self similarity
+        rowlse(a1, g0, 6, 7, 8)
+        rowlse(a1, g1, 9, 10, 11)
+        out3 = torch.zeros(3, dtype=torch.float32, device=dev)
+        lse = torch.empty(2, Bl, dtype=torch.float32, device=dev)
+        check(lib.dmf_infonce_finalize(ptr(st[0]), ptr(st[1]), ptr(st[3]), ptr(st[4]), ptr(st[2]), ptr(st[5]), Bl,
+                                       1.0 / (2 * Bg), 1.0 / Bg, 0, ptr(lse[0]), ptr(out3), stream()))
+        check(lib.dmf_infonce_finalize(ptr(st[6]), ptr(st[7]), ptr(st[9]), ptr(st[10]), ptr(st[8]), ptr(st[11]), Bl,
+                                       1.0 / (2 * Bg), 1.0 / Bg, 1, ptr(lse[1]), ptr(out3), stream()))
+        if world > 1:
+            dist.all_reduce(out3)
+            lse_all = torch.empty(2, Bg, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(lse_all[0], lse[0])
+            dist.all_gather_into_tensor(lse_all[1], lse[1])
+        else:
+            lse_all = lse
+        ctx.save_for_backward(a0, a1, g0, g1, lse, lse_all)
+        ctx.meta = (Bl, Bg, D, scale, off, dt)
+        return out3
+
+    @staticmethod
+    def backward(ctx, gout):
+        a0, a1, g0, g1, lse, lse_all = ctx.saved_tensors
+        Bl, Bg, D, scale, off, dt = ctx.meta
+        dev = a0.device
+        gs = gout[0:1].contiguous().float()         # only the loss has a gradient; diagnostics are no-grad
+        coef = scale / (2.0 * Bg)
+        dz0 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
+        dz1 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
+        if dt == 1:
+            g0T, g1T = transpose_bf16(g0), transpose_bf16(g1)
+        else:
+            g0T = g1T = None
+        check(lib.dmf_infonce_bwd(ptr(a0), a0.stride(0), Bl, ptr(lse[0]), ptr(g1), g1.stride(0), ptr(g1T),
+                                  g1T.stride(0) if g1T is not None else 0, Bg, ptr(lse_all[1]), D, scale, coef, ptr(gs),
+                                  off, ptr(dz0), D, 0, dt, stream()))
+        check(lib.dmf_infonce_bwd(ptr(a1), a1.stride(0), Bl, ptr(lse[1]), ptr(g0), g0.stride(0), ptr(g0T),
+                                  g0T.stride(0) if g0T is not None else 0, Bg, ptr(lse_all[0]), D, scale, coef, ptr(gs),
+                                  off, ptr(dz1), D, 0, dt, stream()))
+        return dz0, dz1, None, None
+
+
+def infonce(z0: Tensor, z1: Tensor, temperature: float = 0.07, precision: str = "fp32") -> Tuple[Tensor, Tensor, Tensor]:
+    """(loss, loss_x, loss_y) of SupConLoss()(stack([z0,z1],1)) without the [2B,2B] logits.
+    Under torch.distributed the negatives are global (embeddings all-gathered with NCCL)."""
+    out = _InfoNCE.apply(z0, z1, float(temperature), precision)
+    return out[0], out[1].detach(), out[2].detach()
+
+
+# ----------------------------------------------------------------------------------------
+# row normalisation, vMF sample, ortho loss
+# ----------------------------------------------------------------------------------------
+class _RowNormalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        L.require_device()
+        x = _f32c(x)
+        R, D = x.shape
+        y = torch.empty_like(x)
+        inv = torch.empty(R, dtype=torch.float32, device=x.device)
+        check(lib.dmf_row_normalize_fwd(ptr(x), D, R, D, eps, ptr(y), D, 0, 0, ptr(inv), stream()))
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        dy = _f32c(dy)
+        R, D = y.shape
+        dx = torch.empty_like(y)
+        check(lib.dmf_row_normalize_bwd(ptr(y), D, ptr(inv), ptr(dy), D, R, D, ptr(dx), D, 0, stream()))
+        return dx, None
+
+
+def row_normalize(x: Tensor, eps: float = 1e-12) -> Tensor:
+    """F.normalize(x, dim=-1)."""
+    return _RowNormalize.apply(x, eps)
+
+
+class _VmfSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e, w, v):
+        L.require_device()
+        e, w, v = _f32c(e), _f32c(w), _f32c(v)
+        R, D = e.shape
+        z = torch.empty_like(e)
+        check(lib.dmf_vmf_fwd(ptr(e), D, ptr(w), ptr(v), R, D, ptr(z), D, 0, 0, stream()))
+        ctx.save_for_backward(e, w, v)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        e, w, v = ctx.saved_tensors
+        dz = _f32c(dz)
+        R, D = e.shape
+        de = torch.empty_like(e)
+        check(lib.dmf_vmf_bwd(ptr(e), D, ptr(w), ptr(v), ptr(dz), D, R, D, ptr(de), D, 0, stream()))
+        return de, None, None
+
+
+def vmf_rsample(e: Tensor, w: Tensor, v: Tensor) -> Tensor:
+    """ProbabilisticEncoder('vmf')(e)[0].rsample() with the noise (w [B,1], v [B,D-1]) supplied."""
+    return _VmfSample.apply(e, w, v)
+
+
+class _OrthoLoss(torch.autograd.Function):
+    """|| normalize(z1)^T normalize(zs) ||_F  (models/losses.py:104-110); Gram partial sums are
+    all-reduced across ranks before the square root."""
+
+    @staticmethod
+    def forward(ctx, z1, zs):
+        L.require_device()
+        z1, zs = _f32c(z1), _f32c(zs)
+        R, D = z1.shape
+        dev = z1.device
+        n1, ns = torch.empty_like(z1), torch.empty_like(zs)
+        i1 = torch.empty(R, dtype=torch.float32, device=dev)
+        i2 = torch.empty(R, dtype=torch.float32, device=dev)
+        check(lib.dmf_row_normalize_fwd(ptr(z1), D, R, D, 1e-12, ptr(n1), D, 0, 0, ptr(i1), stream()))
+        check(lib.dmf_row_normalize_fwd(ptr(zs), D, R, D, 1e-12, ptr(ns), D, 0, 0, ptr(i2), stream()))
+        # split the batch (the contraction dim) over chunks so the grid fills the GPU
+        chunks = max(1, min(64, R // 512))
+        rows = (R + chunks - 1) // chunks
+        chunks = (R + rows - 1) // rows
+        part = torch.empty(chunks, D * D, dtype=torch.float32, device=dev)
+        descs = []
+        for c in range(chunks):
+            r0 = c * rows
+            rc = min(rows, R - r0)
+            descs.append(dict(A=n1[r0:], a_rs=1, a_cs=D, B=ns[r0:], b_rs=D, b_cs=1, C=part[c], ldc=D, M=D, N=D, K=rc))
+        gemm_f32(descs, L.EPI_NONE)
+        gram = colsum(part).view(D, D)
+        if _dist_on():
+            dist.all_reduce(gram)
+        ss = torch.zeros(1, dtype=torch.float32, device=dev)
+        check(lib.dmf_sumsq_f32(ptr(gram), D * D, ptr(ss), stream()))
+        loss = torch.sqrt(ss)[0]
+        ctx.save_for_backward(n1, ns, i1, i2, gram, loss)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        n1, ns, i1, i2, gram, loss = ctx.saved_tensors
+        R, D = n1.shape
+        dev = n1.device
+        dn1 = torch.empty_like(n1)
+        dns = torch.empty_like(ns)
+        # dN1 = Ns * M^T / L ; dNs = N1 * M / L
+        gemm_f32([dict(A=ns, a_rs=D, a_cs=1, B=gram, b_rs=1, b_cs=D, C=dn1, ldc=D, M=R, N=D, K=D),
+                  dict(A=n1, a_rs=D, a_cs=1, B=gram, b_rs=D, b_cs=1, C=dns, ldc=D, M=R, N=D, K=D)], L.EPI_NONE)
+        sc = (g / loss).reshape(1, 1)
+        dn1.mul_(sc)
+        dns.mul_(sc)
+        d1 = torch.empty_like(n1)
+        d2 = torch.empty_like(ns)
+        check(lib.dmf_row_normalize_bwd(ptr(n1), D, ptr(i1), ptr(dn1), D, R, D, ptr(d1), D, 0, stream()))
+        check(lib.dmf_row_normalize_bwd(ptr(ns), D, ptr(i2), ptr(dns), D, R, D, ptr(d2), D, 0, stream()))
+        return d1, d2
+
+
+def ortho_loss(z1: Tensor, zs: Tensor) -> Tensor:
+    return _OrthoLoss.apply(z1, zs)
+
+
+# ----------------------------------------------------------------------------------------
+# DMVAE head + reconstruction  (models/dmvae.py:74-176)
+# ----------------------------------------------------------------------------------------
+class _DmvaeHead(torch.autograd.Function):
+    """forward(cfg, noise, *stats) -> (dec_in_0..dec_in_{N-1}, kl3).  cfg = (N, B, e, T).
+    kl3 = (kl_private, kl_poe, kl_uni) batch means; differentiable through the same backward kernel."""
+
+    @staticmethod
+    def forward(ctx, cfg, noise, *stats):
+        L.require_device()
+        N, B, e, T = cfg
+        stats = [_f32c(s) for s in stats]
+        noise = _f32c(noise)
+        dev = stats[0].device
+        dec_in = [torch.empty(N * B, 2 * e, dtype=torch.float32, device=dev) for _ in range(N)]
+        kl3 = torch.zeros(3, dtype=torch.float32, device=dev)
+        check(lib.dmf_dmvae_head_fwd(L.ptr_array(stats), ptr(noise), N, B, e, T, L.ptr_array(dec_in), ptr(kl3), stream()))
+        ctx.cfg = cfg
+        ctx.save_for_backward(noise, *stats)
+        return (*dec_in, kl3)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        N, B, e, T = ctx.cfg
+        noise, *stats = ctx.saved_tensors
+        dev = noise.device
+        dd = [(_f32c(g) if g is not None else torch.zeros(N * B, 2 * e, dtype=torch.float32, device=dev))
+              for g in grads[:N]]
+        gk = grads[N]
+        gk = _f32c(gk) if gk is not None else torch.zeros(3, dtype=torch.float32, device=dev)
+        dst = [torch.empty(B, 4 * e, dtype=torch.float32, device=dev) for _ in range(N)]
+        check(lib.dmf_dmvae_head_bwd(L.ptr_array(stats), ptr(noise), L.ptr_array(dd), N, B, e, T, ptr(gk),
+                                     L.ptr_array(dst), stream()))
+        return (None, None, *dst)
+
+
+class _DmvaeMse(torch.autograd.Function):
+    """forward(cfg, recon, x) -> out2 = (w_joint*mse_joint, w_cross*sum mse_cross); the gradient
+    w.r.t. recon is produced by the same kernel pass.  cfg = (N, B, d, view, w_joint, w_cross)."""
+
+    @staticmethod
+    def forward(ctx, cfg, recon, x):
+        L.require_device()
+        N, B, d, view, wj, wc = cfg
+        recon, x = _f32c(recon), _f32c(x)
+        out2 = torch.zeros(2, dtype=torch.float32, device=recon.device)
+        dr = torch.empty_like(recon)
+        check(lib.dmf_dmvae_mse_fwd_bwd(ptr(recon), d, ptr(x), d, N, B, d, view, wj, wc, 0, ptr(out2), ptr(dr), d, stream()))
+        ctx.save_for_backward(dr)
+        return out2
+
+    @staticmethod
+    def backward(ctx, g):
+        (dr,) = ctx.saved_tensors
+        # both outputs enter the loss with the same upstream scale (loss = out2[0] + out2[1] + ...)
+        return None, dr * g[0], None
+
+
+# ----------------------------------------------------------------------------------------
+# K3  fused evidence fusion + EDL loss  (utils.py:66-116, models/losses.py:117-248)
+# ----------------------------------------------------------------------------------------
+class _EdlLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, evid, labels, agg, coef, dc_weight, inv_B_global):
+        L.require_device()
+        evid = _f32c(evid)
+        B, V, Cc = evid.shape
+        dev = evid.device
+        labels = labels.to(torch.int64).contiguous()
+        fused = torch.empty(B, Cc, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(evid)
+        parts = torch.zeros(4, dtype=torch.float32, device=dev)
+        p = L.EdlParams(B, V, Cc, L.AGG[agg], coef, dc_weight, inv_B_global)
+        check(lib.dmf_edl_fused(ptr(evid), ptr(labels), p, 0, ptr(fused), ptr(grad), 0, 0, 0, ptr(parts), stream()))
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(fused)
+        return fused, parts
+
+    @staticmethod
+    def backward(ctx, gf, gp):
+        (grad,) = ctx.saved_tensors
+        return grad * gp[3], None, None, None, None, None
+
+
+def edl_fused_loss(evid: Tensor, labels: Tensor, agg: str, annealing_step: int, annealing_start: int,
+                   fused: float = 1.0, gamma: float = 1.0, global_batch: Optional[int] = None):
+    """AvgTrustedLoss.forward + the aggregation rule in one kernel pass.
+    Returns (loss, fused_evidence [B,C], parts[4] = (edl, coef*kl, dc, total))."""
+    B = evid.shape[0]
+    coef = min(1.0, annealing_step / annealing_start)
+    t = min(1.0, annealing_step / max(1, annealing_start))
+    gamma_t = 0.2 * (1 - t) + gamma * t
+    fe, parts = _EdlLoss.apply(evid, labels, agg, float(coef), float(gamma_t * fused),
+                               1.0 / float(global_batch or B))
+    return parts[3], fe, parts
+
+
+def edl_summaries(evid: Tensor, labels: Tensor, agg: str):
+    """Forward-only pass: fused evidence, u = C/S, aleatoric, per-view and fused argmax."""
+    L.require_device()
+    evid = _f32c(evid)
+    B, V, Cc = evid.shape
+    dev = evid.device
+    fused = torch.empty(B, Cc, dtype=torch.float32, device=dev)
+    u = torch.empty(B, dtype=torch.float32, device=dev)
+    ale = torch.empty(B, dtype=torch.float32, device=dev)
+    pred = torch.empty(B, V + 1, dtype=torch.int32, device=dev)
+    p = L.EdlParams(B, V, Cc, L.AGG[agg], 0.0, 0.0, 1.0 / max(B, 1))
+    labels = labels.to(torch.int64).contiguous()
+    check(lib.dmf_edl_fused(ptr(evid), ptr(labels), p, 0, ptr(fused), 0, ptr(u), ptr(ale), ptr(pred), 0, stream()))
+    return fused, u, ale, pred
+
+
+def fuse_evidence(evid: Tensor, agg: str) -> Tensor:
+    """utils.py:66-116 aggregation only (no gradient: the reference loss ignores it)."""
+    B = evid.shape[0]
+    dummy = torch.zeros(B, dtype=torch.int64, device=evid.device)
+    L.require_device()
+    evid = _f32c(evid)
+    _, V, Cc = evid.shape
+    fused = torch.empty(B, Cc, dtype=torch.float32, device=evid.device)
+    p = L.EdlParams(B, V, Cc, L.AGG[agg], 0.0, 0.0, 1.0 / max(B, 1))
+    check(lib.dmf_edl_fused(ptr(evid), ptr(dummy), p, 0, ptr(fused), 0, 0, 0, 0, 0, stream()))
+    return fused
+
+
+# ----------------------------------------------------------------------------------------
+# optimizer (a18)
+# ----------------------------------------------------------------------------------------
+def adam_step_flat(p: Tensor, g: Tensor, m: Tensor, v: Tensor, lr: float, step: int, betas=(0.9, 0.999),
+                   eps: float = 1e-8, weight_decay: float = 0.0, decoupled: bool = False, grad_scale: float = 1.0) -> None:
+    L.require_device()
+    check(lib.dmf_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, betas[0], betas[1], eps, weight_decay,
+                            1 if decoupled else 0, step, grad_scale, 0, stream()))

@@ -1,0 +1,207 @@
+/*
+ * dmf_b200.h -- C ABI of libdmf_b200.so: the B200 (sm_100a) kernels behind the training-step
+ * hot path of Hassan-Sarwat/disentagled_multimodal_fusion.
+ *
+ * The reference is pure Python/PyTorch and has no FFI boundary of its own; each
+ * entry point below replaces an ATen op *chain* inside one reference function, cited as
+ * file:line into the reference tree.  The reference-side binding a maintainer would add (a
+ * ctypes stub inside the reference module) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns int: 0 = OK, <0 = argument/shape/alignment error, >0 = cudaError_t
+ *     of the launch.  dmf_last_error() returns a thread-local message for the last failure.
+ *   - the CALLER owns every buffer (device pointers unless stated "host"); the library never
+ *     allocates device memory, never synchronises, and launches only on the given stream.
+ *   - all matrices are row-major; "ld*" are leading dimensions in ELEMENTS.
+ *   - fp32 unless a parameter is named *_bf16 (raw uint16 bfloat16 bits).
+ *   - scalar results are ACCUMULATED (atomicAdd) into caller-zeroed float slots so that one
+ *     device->host read per step suffices.
+ */
+#ifndef DMF_B200_H
+#define DMF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dmf_stream_t; /* cudaStream_t */
+
+/* ------------------------------------------------------------------ library / device guard */
+int dmf_version(void);
+/* copies the calling thread's last error text into buf (NUL terminated); returns its length */
+int dmf_last_error(char* buf, size_t n);
+/* 0 iff the current device is compute capability 10.x (B200); otherwise an error (no fallback) */
+int dmf_device_check(void);
+/* number of kernel launches issued by this library since load (thread-safe counter) */
+long long dmf_launch_count(void);
+
+/* ------------------------------------------------------------------ K1 grouped MLP layers
+ * Replaces the per-view nn.Linear/ReLU chains of Linear.forward (models/classifiers.py:43-48) and
+ * EvidentialNN.forward (:497-502), called N + N^2 times per DMVAE step (models/dmvae.py:139,154,162)
+ * and 8x per DisentangledSSL step (models/disentangledssl.py:90-93,117-120): ONE launch per layer
+ * over all groups (views x streams).                                                          */
+enum {
+  DMF_EPI_NONE = 0,      /* C = A*B                                   */
+  DMF_EPI_BIAS = 1,      /* C = A*B + bias[n]                         */
+  DMF_EPI_BIAS_RELU = 2, /* C = relu(A*B + bias[n])                   */
+  DMF_EPI_RELU_MASK = 3, /* C = (aux[m,n] > 0) ? A*B : 0   (ReLU backward folded into dgrad) */
+  DMF_EPI_BIAS_EVIDENCE = 4 /* C = evidence(A*B + bias), utils.py:46-63; aux (optional) gets the pre-activation */
+};
+
+/* One GEMM problem  C[M,N] = epi( sum_k A(m,k) * B(k,n) ).  Strides are in elements and fully
+ * general, so forward (Y = X W^T), dgrad (dX = dY W) and wgrad (dW = dY^T X) are the same call. */
+typedef struct {
+  const void* A;  long long a_rs, a_cs;   /* A(m,k) = A[m*a_rs + k*a_cs] */
+  const void* B;  long long b_rs, b_cs;   /* B(k,n) = B[k*b_rs + n*b_cs] */
+  void* C;        long long ldc;          /* C[m*ldc + n], row-major      */
+  const float* bias;                      /* [N] or NULL                  */
+  void* aux;      long long ldaux;        /* epilogue-specific, may be NULL */
+  float* rowsum_a;                        /* optional [M]: rowsum_a[m] = sum_k A(m,k)  (bias grad in wgrad form) */
+  int M, N, K;
+  int accumulate;                         /* 1: C += result (epilogue NONE only) */
+} dmf_gemm_desc;
+
+/* fp32 path (FFMA, 1e-5 parity path).  `groups` is a HOST array of n_groups descriptors
+ * (n_groups <= 64 per call); it is passed by value to the kernel, no device copy needed.    */
+int dmf_grouped_gemm_f32(const dmf_gemm_desc* groups, int n_groups, int epilogue, dmf_stream_t s);
+
+/* bf16 tensor-core path: tcgen05.mma (kind::f16, fp32 accumulate in TMEM), operands staged by
+ * TMA (128B swizzle).  Both operands K-major: A [M,K] bf16 (lda), B [N,K] bf16 (ldb):
+ * C[M,N] = epi(A * B^T).  K*2 bytes and lda/ldb*2 bytes must be multiples of 16; pointers 16B
+ * aligned.  out_f32 / out_bf16 may each be NULL (at least one non-NULL).                      */
+typedef struct {
+  const uint16_t* A; long long lda;
+  const uint16_t* B; long long ldb;
+  float* out_f32;    long long ldo_f32;
+  uint16_t* out_bf16; long long ldo_bf16;
+  const float* bias;                 /* [N] or NULL */
+  const uint16_t* mask_bf16; long long ldmask; /* DMF_EPI_RELU_MASK: zero where mask<=0 */
+  int M, N, K;
+} dmf_tc_gemm_desc;
+int dmf_grouped_gemm_bf16_tc(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, dmf_stream_t s);
+
+/* column sums  out[n] (+)= sum_m X[m*ld + n]   (bias gradients)  */
+int dmf_colsum_f32(const float* X, long long ld, int M, int N, float* out, int accumulate, dmf_stream_t s);
+
+/* dtype / layout movers for the bf16 path (memory-bound): dst[r*ldd + c] = bf16(src[r*lds + c]);
+ * transpose variant writes dst[c*ldd + r].                                                    */
+int dmf_cast_f32_to_bf16(const float* src, long long lds, uint16_t* dst, long long ldd, int rows, int cols, dmf_stream_t s);
+int dmf_cast_transpose_f32_to_bf16(const float* src, long long lds, uint16_t* dst, long long ldd, int rows, int cols, dmf_stream_t s);
+int dmf_transpose_bf16(const uint16_t* src, long long lds, uint16_t* dst, long long ldd, int rows, int cols, dmf_stream_t s);
+
+/* ------------------------------------------------------------------ K2 fused InfoNCE
+ * Replaces matmul/div/max/sub/exp/sum/log/mean of SupConLoss.forward (models/losses.py:64-99)
+ * without materialising the [2B,2B] logits.
+ *
+ * dmf_rowlse: for anchors A [Ma,D] against columns Bm [Nb,D]:  s_ij = scale * <a_i, b_j>,
+ *   row_max[i] = max_j s_ij,  row_sum[i] = sum_j exp(s_ij - row_max[i]).
+ *   Optional diag: if diag_offset >= 0, diag_out[i] = s_{i, diag_offset+i} (the positive / self term).
+ * dtype 0: fp32 FFMA path; dtype 1: bf16 tcgen05 path (A,Bm are bf16, D % 64 == 0).           */
+int dmf_rowlse(const void* A, long long lda, int Ma, const void* Bm, long long ldb, int Nb, int D,
+               float scale, float* row_max, float* row_sum, long long diag_offset, float* diag_out,
+               void* workspace, size_t workspace_bytes, int dtype, dmf_stream_t s);
+/* scratch the bf16 path may use to split the columns across CTAs (0 is always accepted)     */
+size_t dmf_rowlse_workspace_bytes(int Ma, int Nb);
+
+/* Per-anchor finalisation of one SupConLoss call (models/losses.py:68-99) for BOTH anchor sets:
+ *   m_full = max(m_cross, m_intra); sum_c = l_cross*exp(m_cross-m_full);
+ *   loss_i = -(pos - m_full - log(sum_c + 1e-12));  lse_eff_i = m_full + log(sum_c + 1e-12)
+ *   diag_i = -(self - m_intra - log(l_intra))              (no-grad loss_x / loss_y)
+ * out3[0] += sum_i loss_i * inv_count ; out3[1+which] += sum_i diag_i * inv_count_diag.        */
+int dmf_infonce_finalize(const float* m_cross, const float* l_cross, const float* m_intra, const float* l_intra,
+                         const float* pos, const float* self, int n, float inv_count, float inv_count_diag,
+                         int which, float* lse_eff, float* out3, dmf_stream_t s);
+
+/* Backward for one anchor set (Appendix B of SURVEY, verified against reference autograd):
+ *   dA[i,:] (+)= coef*g * ( sum_j [exp(s_ij - lseA_i) + exp(s_ij - lseB_j)] * b_j  - 2 * b_{pos(i)} )
+ * with g read from the device scalar *gscale, pos(i) = diag_offset + i.                        */
+int dmf_infonce_bwd(const void* A, long long lda, int Ma, const float* lseA,
+                    const void* Bm, long long ldb, const void* BmT, long long ldbt, int Nb, const float* lseB, int D,
+                    float scale, float coef, const float* gscale, long long diag_offset,
+                    float* dA, long long ldda, int accumulate, int dtype, dmf_stream_t s);
+/* BmT: the bf16 path also needs the transposed column block [D, Nb] (dmf_transpose_bf16); NULL for fp32 */
+
+/* ------------------------------------------------------------------ K4 ortho Gram pieces
+ * ortho_loss (models/losses.py:104-110) = || normalize(z1)^T normalize(zs) ||_F.
+ * Row normalisation fwd/bwd (also F.normalize at models/disentangledssl.py:139-140).           */
+int dmf_row_normalize_fwd(const float* X, long long ldx, int rows, int D, float eps,
+                          float* Y, long long ldy, uint16_t* Y_bf16, long long ldyb, float* inv_norm, dmf_stream_t s);
+int dmf_row_normalize_bwd(const float* Y, long long ldy, const float* inv_norm, const float* dY, long long lddy,
+                          int rows, int D, float* dX, long long lddx, int accumulate, dmf_stream_t s);
+/* out[0] (+)= scale * sqrt(sum(G^2)) is NOT done here: returns sum of squares into out (atomicAdd) */
+int dmf_sumsq_f32(const float* G, long long n, float* out, dmf_stream_t s);
+
+/* ------------------------------------------------------------------ vMF reparameterised sample
+ * ProbabilisticEncoder('vmf') + VonMisesFisher.rsample given explicit noise
+ * (models/classifiers.py:314-335,433-437,456-466): loc=e/||e||, x=[w, sqrt(clamp(1-w^2,1e-10)) v],
+ * u=(e1-loc)/(||e1-loc||+1e-5), z = x - 2<x,u>u.  noise_w [rows], noise_v [rows, D-1].          */
+int dmf_vmf_fwd(const float* E, long long lde, const float* noise_w, const float* noise_v, int rows, int D,
+                float* Z, long long ldz, uint16_t* Z_bf16, long long ldzb, dmf_stream_t s);
+int dmf_vmf_bwd(const float* E, long long lde, const float* noise_w, const float* noise_v, const float* dZ, long long lddz,
+                int rows, int D, float* dE, long long ldde, int accumulate, dmf_stream_t s);
+/* Device-side draw of the vMF noise (distribution-equal to the reference sampler, not
+ * stream-equal): Philox counter RNG, Wood's rejection sampler per row.           */
+int dmf_vmf_draw(float* noise_w, float* noise_v, int rows, int D, float kappa, unsigned long long seed,
+                 unsigned long long offset, dmf_stream_t s);
+
+/* ------------------------------------------------------------------ DMVAE head + objectives
+ * Replaces chunk/exp/randn_like/PoE/KL of models/dmvae.py:74-112,142-150,170-172.
+ * stats [N][B,4e] (mu_s, lv_s, mu_p, lv_p), noise [2N+1][B,e] in the reference draw order.
+ * Writes decoder inputs dec_in[i] = [N*B, 2e]: block j of B rows = [z_p_i | (j==i ? z_s : z_s_uni_j)].
+ * kl3[0..2] += (kl_private, kl_poe, kl_uni) already divided by B.                              */
+int dmf_dmvae_head_fwd(const float* const* stats, const float* noise, int N, int B, int e, float poe_temperature,
+                       float* const* dec_in, float* kl3, dmf_stream_t s);
+/* backward: d_dec_in[i] [N*B,2e] and the upstream gradients of the three KL scalars
+ * (kl_grad3 = d loss / d (kl_private, kl_poe, kl_uni), a DEVICE array of 3 floats; the module forms
+ * loss = ... + a*(kl_private + N*kl_poe) + a*kl_uni, models/dmvae.py:174-176) -> d_stats[i] [B,4e] */
+int dmf_dmvae_head_bwd(const float* const* stats, const float* noise, const float* const* d_dec_in,
+                       int N, int B, int e, float poe_temperature, const float* kl_grad3,
+                       float* const* d_stats, dmf_stream_t s);
+/* get_embedding PoE of the means (models/dmvae.py:115-125): mu_poe [B,e]                        */
+int dmf_dmvae_poe_mean(const float* const* stats, int N, int B, int e, float poe_temperature, float* mu_poe, dmf_stream_t s);
+/* F.mse_loss x N^2 (models/dmvae.py:155,164) fused with its gradient: recon [N*B,d] vs x [B,d];
+ * block j==view is the joint term (weight w_joint), others cross (w_cross).
+ * out2[0] += w_joint*mse_joint, out2[1] += w_cross*sum_j mse_cross_j; d_recon = g*w*2*(r-x)/(B*d) */
+int dmf_dmvae_mse_fwd_bwd(const float* recon, long long ldr, const float* x, long long ldx, int N, int B, int d,
+                          int view, float w_joint, float w_cross, const float* gscale, float* out2,
+                          float* d_recon, long long lddr, dmf_stream_t s);
+
+/* ------------------------------------------------------------------ K3 evidence fusion + EDL
+ * One pass over evid [B,V,C] replacing utils.py:66-116 (fusion rules), models/losses.py:117-248
+ * (AvgTrustedLoss: EDL digamma loss + annealed KL + degree-of-conflict term) and the uncertainty
+ * summaries of models/evidential_probe.py:139-143.                                             */
+enum { DMF_AGG_CML = 0, DMF_AGG_AVG = 1, DMF_AGG_JOINT = 2, DMF_AGG_DISENTANGLED = 3, DMF_AGG_DBF = 4 };
+typedef struct {
+  int B, V, C;
+  int agg;                 /* DMF_AGG_* */
+  float coef;              /* min(1, annealing_step/annealing_start)            (losses.py:127-130) */
+  float dc_weight;         /* gamma_t * fused                                   (losses.py:243-247) */
+  float inv_B_global;      /* 1/B of the GLOBAL batch (data parallel: local sums scale by this) */
+} dmf_edl_params;
+/* outputs (each may be NULL): fused [B,C]; grad [B,V,C] = d loss/d evid * (*gscale, or 1 if NULL);
+ * u [B] = C/S; ale [B]; pred [B,V+1] int32 (per-view argmax then fused argmax);
+ * loss_parts[4] += {edl(A) term, coef*KL term, dc term, total loss}                              */
+int dmf_edl_fused(const float* evid, const long long* labels, const dmf_edl_params* p, const float* gscale,
+                  float* fused, float* grad, float* u, float* ale, int* pred, float* loss_parts, dmf_stream_t s);
+
+/* evidence activation alone (utils.py:46-63) and its backward (zero outside the clamp)          */
+int dmf_evidence_fwd(const float* h, float* e, long long n, dmf_stream_t s);
+int dmf_evidence_bwd(const float* h, const float* e, const float* de, float* dh, long long n, dmf_stream_t s);
+
+/* ------------------------------------------------------------------ optimizer (a18)
+ * Fused flat-buffer Adam / AdamW step (torch.optim semantics, models/dmvae.py:204-210,
+ * models/evidential_probe.py:205-212).  decoupled=1 -> AdamW.  step is the 1-based step count.
+ * Optionally refreshes a bf16 copy of the parameters for the tensor-core path.                  */
+int dmf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int decoupled, int step, float grad_scale,
+                  uint16_t* p_bf16, dmf_stream_t s);
+/* fill n floats with a value (buffer zeroing for the accumulate-style outputs) */
+int dmf_fill_f32(float* p, long long n, float value, dmf_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMF_B200_H */

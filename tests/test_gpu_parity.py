@@ -1,0 +1,397 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(ctypes -> libdmf_b200.so), against the golden fixtures minted from the unmodified reference and
+against the CPU oracle (oracle/port.py) on seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 path 1e-5 relative on losses / embeddings (gradients of
+deep chains 2e-5, same slack the oracle itself needs vs the reference); bf16 tensor-core path 2e-2;
+probe argmax predictions and uncertainty rankings exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import T, assert_close, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+FP32 = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dmf():
+    import disentagled_multimodal_fusion_b200 as pkg
+    pkg._lib.require_device()
+    return pkg
+
+
+def _load_sd(module, g, prefix="sd."):
+    sd = {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(prefix)}
+    missing, unexpected = module.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert not [m for m in missing if "acc" not in m], missing
+    return module
+
+
+# ------------------------------------------------------------------------------------- K3
+def test_activation(dmf):
+    from disentagled_multimodal_fusion_b200.utils import activation_function
+    g = load_golden("activation")
+    h = T(g["h"], DEV, grad=True)
+    e = activation_function(h)
+    assert_close(e, g["e"], 2e-6, "evidence")
+    (gr,) = torch.autograd.grad(e.sum(), h)
+    assert_close(gr, g["grad"], 2e-6, "evidence grad")
+
+
+@pytest.mark.parametrize("tag", ["c1", "c2", "c3scene", "c3late", "c4", "ragged", "single"])
+def test_edl_fused_kernel(dmf, tag):
+    ops = dmf.ops
+    g = load_golden("edl_" + tag)
+    evid, y = T(g["evid"], DEV), T(g["y"], DEV)
+    astart = int(g["annealing_start"])
+    for agg in ("cml", "avg", "joint", "disentangled", "dbf"):
+        fused, u, ale, pred = ops.edl_summaries(evid, y, agg)
+        assert_close(fused, g["fused_" + agg], 2e-6, f"fused {agg}")
+        assert_close(u, g["u_" + agg], 2e-6, f"u {agg}")
+        assert_close(ale, g["ale_" + agg], FP32, f"aleatoric {agg}")
+        # bit-exact decisions: fused argmax, per-view argmax, epistemic-uncertainty ranking
+        assert torch.equal(pred[:, -1].long().cpu(), T(g["pred_" + agg])), f"fused argmax {agg}"
+        assert torch.equal(pred[:, :-1].long().cpu(), T(g["pred_views"])), "per-view argmax"
+        r_ours = torch.argsort(u.cpu(), stable=True)
+        r_ref = torch.argsort(T(g["u_" + agg]), stable=True)
+        assert torch.equal(r_ours, r_ref), f"uncertainty ranking {agg}"
+    for step in g["steps"]:
+        for fused_flag in (1, 0):
+            ev = evid.clone().requires_grad_()
+            loss, fe, parts = ops.edl_fused_loss(ev, y, "cml", int(step), astart, fused=fused_flag)
+            (gr,) = torch.autograd.grad(loss, ev)
+            assert_close(loss, g[f"loss_s{step}_f{fused_flag}"], FP32, f"loss step {step} fused {fused_flag}")
+            assert_close(gr, g[f"grad_s{step}_f{fused_flag}"], FP32, f"grad step {step} fused {fused_flag}")
+
+
+def test_edl_large_matches_oracle(dmf):
+    """C4 shapes at a batch large enough for many CTAs; live oracle on the same seeded inputs."""
+    from oracle import port
+    gen = torch.Generator().manual_seed(5)
+    B, V, C = 20000, 4, 42
+    evid = port.evidence_activation((torch.randn(B, V, C, generator=gen) * 2).clamp(-10, 10))
+    y = torch.randint(0, C, (B,), generator=gen)
+    ev = evid.clone().requires_grad_()
+    ref = port.avg_trusted_loss(ev, y, None, 1, 15, 20)
+    (gref,) = torch.autograd.grad(ref, ev)
+    ed = evid.to(DEV).requires_grad_()
+    loss, fe, _ = dmf.ops.edl_fused_loss(ed, y.to(DEV), "dbf", 15, 20, fused=1)
+    (gd,) = torch.autograd.grad(loss, ed)
+    assert_close(loss, ref, FP32, "loss")
+    assert_close(gd, gref, FP32, "grad")
+    assert_close(fe, port.fuse(evid, "dbf"), FP32, "dbf fused")
+
+
+# ------------------------------------------------------------------------------------- K2 / K4
+@pytest.mark.parametrize("tag", ["b64d16", "b96d64", "b33d24raw", "b2d8"])
+def test_supcon_fp32(dmf, tag):
+    g = load_golden("supcon_" + tag)
+    z0, z1 = T(g["z0"], DEV, grad=True), T(g["z1"], DEV, grad=True)
+    crit = dmf.SupConLoss()
+    loss, lx, ly = crit(torch.stack([z0, z1], dim=1))
+    g0, g1 = torch.autograd.grad(loss, (z0, z1))
+    assert_close(loss, g["loss"], FP32, "loss")
+    assert_close(lx, g["loss_x"], 1e-4, "loss_x")
+    assert_close(ly, g["loss_y"], 1e-4, "loss_y")
+    assert_close(g0, g["g0"], FP32, "g0")
+    assert_close(g1, g["g1"], FP32, "g1")
+    a, b = T(g["oa"], DEV, grad=True), T(g["ob"], DEV, grad=True)
+    ol = dmf.ortho_loss(a, b)
+    ga, gb = torch.autograd.grad(ol, (a, b))
+    assert_close(ol, g["ortho"], FP32, "ortho")
+    assert_close(ga, g["goa"], FP32, "ortho grad a")
+    assert_close(gb, g["gob"], FP32, "ortho grad b")
+
+
+def test_supcon_bf16_tensor_core(dmf):
+    g = load_golden("supcon_b96d64")
+    z0, z1 = T(g["z0"], DEV, grad=True), T(g["z1"], DEV, grad=True)
+    crit = dmf.SupConLoss(precision="bf16")
+    loss, lx, ly = crit(torch.stack([z0, z1], dim=1))
+    g0, g1 = torch.autograd.grad(loss, (z0, z1))
+    assert_close(loss, g["loss"], 2e-2, "loss")
+    assert_close(g0, g["g0"], 2e-2, "g0")
+    assert_close(g1, g["g1"], 2e-2, "g1")
+
+
+@pytest.mark.parametrize("B,D", [(1000, 512), (2048, 256), (4096, 512)])
+def test_infonce_bf16_vs_fp32_large(dmf, B, D):
+    """Unit-norm embeddings at the C5 width: tensor-core tiles vs the FFMA tiles vs the oracle formula."""
+    gen = torch.Generator().manual_seed(B + D)
+    z0 = torch.nn.functional.normalize(torch.randn(B, D, generator=gen), dim=-1)
+    z1 = torch.nn.functional.normalize(0.5 * z0 + 0.1 * torch.randn(B, D, generator=gen), dim=-1)
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        a, b = z0.to(DEV).requires_grad_(), z1.to(DEV).requires_grad_()
+        loss, lx, ly = dmf.ops.infonce(a, b, 0.07, prec)
+        ga, gb = torch.autograd.grad(loss, (a, b))
+        outs[prec] = (loss, lx, ly, ga, gb)
+    if B <= 2048:
+        from oracle import port
+        a, b = z0.clone().requires_grad_(), z1.clone().requires_grad_()
+        ref, rx, ry = port.supcon(a, b)
+        ra, rb = torch.autograd.grad(ref, (a, b))
+        assert_close(outs["fp32"][0], ref, FP32, "fp32 loss vs oracle")
+        assert_close(outs["fp32"][3], ra, 2e-5, "fp32 grad vs oracle")
+        assert_close(outs["fp32"][1], rx, 1e-3, "loss_x vs oracle")
+    assert_close(outs["bf16"][0], outs["fp32"][0], 2e-2, "bf16 loss")
+    assert_close(outs["bf16"][3], outs["fp32"][3], 2e-2, "bf16 dz0")
+    assert_close(outs["bf16"][4], outs["fp32"][4], 2e-2, "bf16 dz1")
+
+
+def test_vmf(dmf):
+    g = load_golden("vmf")
+    e = T(g["e"], DEV, grad=True)
+    z = dmf.ops.vmf_rsample(e, T(g["w"], DEV), T(g["v"], DEV))
+    assert_close(z, g["z"], FP32, "vmf z")
+    (ge,) = torch.autograd.grad((z * torch.arange(16, dtype=torch.float32, device=DEV)).sum(), e)
+    assert_close(ge, g["grad_e"], 2e-5, "vmf grad")
+
+
+def test_vmf_device_draw_distribution(dmf):
+    """Device sampler is distribution-equal (not stream-equal): unit tangent vectors, w moments."""
+    B, D = 20000, 64
+    w, v = dmf.ops.vmf_draw(B, D, 1.0, 1234, 0, DEV)
+    assert torch.allclose(v.norm(dim=-1), torch.ones(B, device=DEV), atol=1e-4)
+    torch.manual_seed(0)
+    from disentagled_multimodal_fusion_b200.utils import draw_vmf_noise
+    wr, _ = draw_vmf_noise(B, D, 1.0)
+    assert abs(float(w.mean()) - float(wr.mean())) < 5e-3
+    assert abs(float(w.std()) - float(wr.std())) < 5e-3
+    assert abs(float(v.mean())) < 2e-3
+
+
+# ------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 512), (100, 800, 240), (131, 77, 136), (600, 47, 512)])
+def test_tc_gemm(dmf, M, N, K):
+    ops = dmf.ops
+    gen = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, Kp)
+    A[:, :K] = torch.randn(M, K, generator=gen)
+    W = torch.zeros(N, Kp)
+    W[:, :K] = torch.randn(N, K, generator=gen) / K ** 0.5
+    bias = torch.randn(N, generator=gen)
+    Ab, Wb = A.to(DEV).bfloat16(), W.to(DEV).bfloat16()
+    ref = torch.relu(Ab.float().cpu()[:, :K] @ Wb.float().cpu()[:, :K].T + bias)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    Np = (N + 7) // 8 * 8
+    outb = torch.zeros(M, Np, dtype=torch.bfloat16, device=DEV)
+    ops.gemm_tc([dict(A=Ab, lda=Kp, B=Wb, ldb=Kp, out_f32=out, ldo_f32=N, out_bf16=outb, ldo_bf16=Np,
+                      bias=bias.to(DEV), M=M, N=N, K=K)], dmf._lib.EPI_BIAS_RELU)
+    assert_close(out, ref, 1e-4, "tc gemm f32 out")
+    assert_close(outb[:, :N].float(), ref, 1e-2, "tc gemm bf16 out")
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", FP32), ("bf16", 2e-2)])
+def test_grouped_mlp_vs_torch(dmf, prec, tol):
+    """Ragged groups (HandWritten-like widths), fwd + dgrad + wgrad + bias grad vs plain torch fp32."""
+    gen = torch.Generator().manual_seed(3)
+    dims, h, out, B = [240, 76, 6], 64, 40, 100
+    xs = [torch.rand(B, d, generator=gen) for d in dims]
+    Ws = [[torch.randn(h, d, generator=gen) / d ** 0.5, torch.randn(h, h, generator=gen) / h ** 0.5,
+           torch.randn(out, h, generator=gen) / h ** 0.5] for d in dims]
+    bs = [[torch.randn(h, generator=gen) * 0.1, torch.randn(h, generator=gen) * 0.1,
+           torch.randn(out, generator=gen) * 0.1] for _ in dims]
+    dy = [torch.randn(B, out, generator=gen) for _ in dims]
+
+    def run(dev, fn):
+        X = [x.to(dev).requires_grad_() for x in xs]
+        W = [[w.to(dev).requires_grad_() for w in ws] for ws in Ws]
+        Bz = [[b.to(dev).requires_grad_() for b in bb] for bb in bs]
+        ys = fn(X, W, Bz)
+        loss = sum((y * d.to(dev)).sum() for y, d in zip(ys, dy))
+        loss.backward()
+        return ys, X, W, Bz
+
+    def torch_fn(X, W, Bz):
+        outs = []
+        for x, ws, bb in zip(X, W, Bz):
+            hcur = x
+            for i, (w, b) in enumerate(zip(ws, bb)):
+                hcur = torch.nn.functional.linear(hcur, w, b)
+                if i < 2:
+                    hcur = torch.relu(hcur)
+            outs.append(hcur)
+        return outs
+    ry, rX, rW, rB = run("cpu", torch_fn)
+    oy, oX, oW, oB = run(DEV, lambda X, W, Bz: dmf.ops.grouped_mlp(X, W, Bz, precision=prec))
+    for g in range(len(dims)):
+        assert_close(oy[g], ry[g], tol, f"y[{g}]")
+        assert_close(oX[g].grad, rX[g].grad, tol, f"dx[{g}]")
+        for l in range(3):
+            assert_close(oW[g][l].grad, rW[g][l].grad, tol, f"dW[{g}][{l}]")
+            assert_close(oB[g][l].grad, rB[g][l].grad, tol, f"db[{g}][{l}]")
+
+
+# ------------------------------------------------------------------------------------- modules
+@pytest.mark.parametrize("tag", ["scene_small", "hw_small", "syn_small"])
+def test_dmvae_module(dmf, tag):
+    g = load_golden("dmvae_" + tag)
+    h, e, B = (int(v) for v in g["meta"])
+    dims = [int(d) for d in g["dims"]]
+    m = _load_sd(dmf.DMVAE(output_dim=dims, a=float(g["a"]), hidden_dim=h, embed_dim=e), g).to(DEV)
+    xs = [T(g[f"x{i}"], DEV) for i in range(len(dims))]
+    noise = [T(g[f"noise{i}"], DEV) for i in range(2 * len(dims) + 1)]
+    loss, logs = m(xs, noise=noise)
+    assert_close(loss, g["loss"], FP32, "loss")
+    for k in ("loss_joint_recon", "loss_cross_recon", "kl_private", "kl_shared_poe", "kl_shared_uni_sum"):
+        assert_close(logs[k], g["log." + k], FP32, k)
+    loss.backward()
+    for k, p in m.named_parameters():
+        assert_close(p.grad, g["grad." + k], 2e-5, "grad " + k)
+    mu, mups = m.get_embedding(xs)
+    assert_close(mu, g["emb_shared"], FP32, "emb_shared")
+    for i in range(len(dims)):
+        assert_close(mups[i], g[f"emb_private{i}"], FP32, f"emb_private{i}")
+
+
+@pytest.mark.parametrize("tag", ["small", "wide"])
+def test_dssl_module(dmf, tag):
+    g = load_golden("dssl_" + tag)
+    h, e, B = (int(v) for v in g["meta"])
+    dims = [int(d) for d in g["dims"]]
+    m = _load_sd(dmf.DisentangledSSL(output_dim=dims, hidden_dim=h, embed_dim=e, a=float(g["a"]),
+                                     lmd_start_value=float(g["log.lmd"])), g).to(DEV)
+    noise = [(T(g[f"noise_w{i}"], DEV), T(g[f"noise_v{i}"], DEV)) for i in range(4)]
+    x1, x2, v1, v2 = (T(g[k], DEV) for k in ("x1", "x2", "v1", "v2"))
+    loss, logs = m(x1, x2, v1, v2, noise=noise)
+    assert_close(loss, g["loss"], FP32, "loss")
+    for k in ("shared", "specific", "ortho"):
+        assert_close(logs[k], g["log." + k], FP32, k)
+    assert_close(logs["loss_x"], g["log.loss_x"], 1e-3, "loss_x")
+    loss.backward()
+    for k, p in m.named_parameters():
+        assert_close(p.grad, g["grad." + k], 3e-5, "grad " + k)
+    es, ep = m.get_embedding([x1, x2])
+    assert_close(es, g["emb_shared"], FP32, "emb_shared")
+    assert_close(ep[0], g["emb_private0"], FP32, "emb_private0")
+    assert_close(ep[1], g["emb_private1"], FP32, "emb_private1")
+
+
+def test_dssl_seed_parity(dmf):
+    """Same seed => same vMF noise stream as the reference => same loss without passing noise."""
+    g = load_golden("dssl_small")
+    h, e, B = (int(v) for v in g["meta"])
+    dims = [int(d) for d in g["dims"]]
+    m = _load_sd(dmf.DisentangledSSL(output_dim=dims, hidden_dim=h, embed_dim=e, a=float(g["a"]),
+                                     lmd_start_value=float(g["log.lmd"])), g).to(DEV)
+    x1, x2, v1, v2 = (T(g[k], DEV) for k in ("x1", "x2", "v1", "v2"))
+    torch.manual_seed(1234)
+    loss, _ = m(x1, x2, v1, v2)
+    assert_close(loss, g["loss"], FP32, "loss (seeded)")
+
+
+def test_dssl_bf16_path(dmf):
+    """Tensor-core path of the whole DSSL step vs the fp32 path (2e-2), widths that are multiples of 64."""
+    torch.manual_seed(0)
+    dims, h, e, B = [128, 192], 128, 64, 256
+    m32 = dmf.DisentangledSSL(output_dim=dims, hidden_dim=h, embed_dim=e).to(DEV)
+    mbf = dmf.DisentangledSSL(output_dim=dims, hidden_dim=h, embed_dim=e, precision="bf16").to(DEV)
+    mbf.load_state_dict(m32.state_dict())
+    gen = torch.Generator().manual_seed(1)
+    x1, x2 = torch.randn(B, dims[0], generator=gen).to(DEV), torch.randn(B, dims[1], generator=gen).to(DEV)
+    v1, v2 = x1 + 0.01 * torch.randn_like(x1), x2 + 0.01 * torch.randn_like(x2)
+    torch.manual_seed(7)
+    noise = m32.draw_noise(B, DEV)
+    l32, logs32 = m32(x1, x2, v1, v2, noise=noise)
+    lbf, logsbf = mbf(x1, x2, v1, v2, noise=noise)
+    l32.backward()
+    lbf.backward()
+    assert_close(lbf, l32, 2e-2, "loss")
+    for (k, p), (_, q) in zip(mbf.named_parameters(), m32.named_parameters()):
+        assert_close(p.grad, q.grad, 5e-2, "grad " + k)
+
+
+@pytest.mark.parametrize("name,agg", [("probe_cml", "cml"), ("probe_avg", "avg"), ("probe_joint", "joint"),
+                                      ("probe_disentangled", "disentangled")])
+def test_probe_module(dmf, name, agg):
+    g = load_golden(name)
+    h, e, B, C = (int(v) for v in g["meta"])
+    dims = [int(d) for d in g["dims"]]
+    backbone = dmf.DMVAE(output_dim=dims, a=1e-5, hidden_dim=h, embed_dim=e)
+    pm = dmf.EvidentialProbeModule(backbone, num_classes=C, input_dim=e, hidden_dim=(16,), dropout=0.1,
+                                   annealing_start=50, aggregation=agg, fused=1)
+    _load_sd(pm, g).to(DEV).eval()
+    pm.criterion.annealing_step = int(g["annealing_step"])
+    batch = [T(g[f"x{i}"], DEV) for i in range(len(dims))] + [T(g["y"], DEV)]
+    loss, ea, _, ev = pm.shared_step(batch)
+    assert_close(loss, g["loss"], FP32, "loss")
+    assert_close(ev, g["evidences"], FP32, "evidences")
+    assert_close(ea, g["evidences_a"], FP32, "evidences_a")
+    assert torch.equal(ea.argmax(-1).cpu(), T(g["evidences_a"]).argmax(-1)), "fused argmax"
+    assert torch.equal(ev.argmax(-1).cpu(), T(g["evidences"]).argmax(-1)), "per-view argmax"
+    loss.backward()
+    for k, p in pm.named_parameters():
+        if p.requires_grad:
+            assert_close(p.grad, g["grad." + k], 2e-5, "grad " + k)
+
+
+def test_disentangled_probe_module(dmf):
+    g = load_golden("probe_dis_cml")
+    h, e, B, C = (int(v) for v in g["meta"])
+    dims = [int(d) for d in g["dims"]]
+    backbone = dmf.DMVAE(output_dim=dims, a=1e-5, hidden_dim=h, embed_dim=e)
+    pm = dmf.DisentangledEvidentialProbeModule(backbone, num_classes=C, input_dim=e, hidden_dim=(16,), dropout=0.1,
+                                               annealing_start=50, aggregation="cml")
+    _load_sd(pm, g).to(DEV).eval()
+    pm.criterion.annealing_step = int(g["annealing_step"])
+    batch = [T(g[f"x{i}"], DEV) for i in range(len(dims))] + [T(g["y"], DEV)]
+    loss, ea, _, ev = pm.shared_step(batch)
+    assert_close(loss, g["loss"], FP32, "loss")
+    assert_close(ev, g["evidences"], FP32, "evidences")
+    loss.backward()
+    for k, p in pm.named_parameters():
+        if p.requires_grad:
+            assert_close(p.grad, g["grad." + k], 2e-5, "grad " + k)
+
+
+@pytest.mark.parametrize("name", ["latefusion_dbf", "latefusion_cml", "latefusion_avg", "latefusion_handwritten"])
+def test_latefusion_module(dmf, name):
+    g = load_golden(name)
+    _, _, B, C = (int(v) for v in g["meta"])
+    dims = [int(d) for d in g["dims"]]
+    agg = name.split("_")[1] if "handwritten" not in name else "cml"
+    hid = (32,) if "handwritten" in name else (16,)
+    lf = dmf.LateFusion([(dmf.IdentityEncoder, {}) for _ in dims], dims, C, dropout=0.1, aggregation=agg,
+                        annealing_start=50, hidden_dim=hid)
+    _load_sd(lf, g).to(DEV).eval()
+    lf.criterion.annealing_step = int(g["annealing_step"])
+    batch = [T(g[f"x{i}"], DEV) for i in range(len(dims))] + [T(g["y"], DEV)]
+    loss, ea, _, ev = lf.shared_step(batch)
+    assert_close(loss, g["loss"], FP32, "loss")
+    assert_close(ev, g["evidences"], FP32, "evidences")
+    assert_close(ea, g["evidences_a"], FP32, "evidences_a")
+    assert torch.equal(ea.argmax(-1).cpu(), T(g["evidences_a"]).argmax(-1)), "fused argmax"
+    loss.backward()
+    for k, p in lf.named_parameters():
+        if p.requires_grad:
+            assert_close(p.grad, g["grad." + k], 2e-5, "grad " + k)
+
+
+def test_adam_matches_torch(dmf):
+    gen = torch.Generator().manual_seed(0)
+    n = 10007
+    p0 = torch.randn(n, generator=gen)
+    for decoupled, wd in ((False, 0.0), (True, 1e-4), (False, 1e-2)):
+        pt = p0.clone().requires_grad_()
+        opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)([pt], lr=1e-3, weight_decay=wd)
+        pd = p0.clone().to(DEV)
+        m, v = torch.zeros_like(pd), torch.zeros_like(pd)
+        for step in range(1, 4):
+            gk = torch.randn(n, generator=gen)
+            pt.grad = gk.clone()
+            opt.step()
+            dmf.ops.adam_step_flat(pd, gk.to(DEV), m, v, 1e-3, step, weight_decay=wd, decoupled=decoupled)
+        assert_close(pd, pt, 2e-6, f"adam decoupled={decoupled} wd={wd}")
+
+
+def test_launch_counter_moves(dmf):
+    before = dmf._lib.launch_count()
+    dmf.ops.fuse_evidence(torch.rand(8, 3, 4, device=DEV), "cml")
+    assert dmf._lib.launch_count() == before + 1

@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- train samples/sec of the encoder + InfoNCE + EDL step (BASELINE.json metric).
+
+Workload (config C5 of SURVEY §8): DisentangledSSL 2-view, 1024-d per view, hidden 512, embed 512,
+T=0.07, global batch 65536 sharded by rows over the ranks (data parallel: embeddings + row-LSEs
+all-gathered with NCCL inside the InfoNCE op, ortho Gram and flat gradients all-reduced), followed by
+an evidential probe (3 heads, C=10, hidden 128, cml fusion, fused EDL kernel) on the same batch.
+One step = backbone fwd + bwd + fused Adam, then probe fwd + bwd + fused AdamW.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference ...                     # CPU oracle port of the reference path
+
+Prints ONE JSON line (rank 0).  `value` = device-resident inputs, CUDA-event timed, max over ranks;
+`e2e` = same step fed from pinned host buffers (H2D inside the timed region) with a device->host read
+of the loss every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "train samples/sec (encoder+InfoNCE+EDL step)"
+UNIT = "samples/s"
+DIMS, HID, EMB, NCLS, TEMP = [1024, 1024], 512, 512, 10, 0.07
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.sm_max = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference step, timed on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_factory(B, seed=0):
+    from oracle import port
+    g = torch.Generator().manual_seed(seed)
+    names = {"x1s": (DIMS[0], EMB), "x2s": (DIMS[1], EMB), "x1": (DIMS[0] + EMB, EMB), "x2": (DIMS[1] + EMB, EMB)}
+    p = {k: port.xavier_mlp_params((din, HID, HID), dout, g) for k, (din, dout) in names.items()}
+    heads = [port.xavier_mlp_params((2 * EMB, 128), NCLS, g)] + [port.xavier_mlp_params((EMB, 128), NCLS, g) for _ in range(2)]
+    bb_params = [t for ws, bs in p.values() for t in ws + bs]
+    hd_params = [t for ws, bs in heads for t in ws + bs]
+    opt_b = torch.optim.Adam(bb_params, lr=1e-4)
+    opt_h = torch.optim.AdamW(hd_params, lr=3e-3, weight_decay=1e-4)
+    x1, x2 = torch.randn(B, DIMS[0], generator=g), torch.randn(B, DIMS[1], generator=g)
+    v1, v2 = x1 + 0.01 * torch.randn(B, DIMS[0], generator=g), x2 + 0.01 * torch.randn(B, DIMS[1], generator=g)
+    y = torch.randint(0, NCLS, (B,), generator=g)
+
+    def step():
+        noise = [port.draw_vmf_noise(B, EMB, 1.0) for _ in range(4)]
+        loss, _ = port.dssl_forward(x1, x2, v1, v2, p, noise, a=1.0, lmd=0.0, T=TEMP)
+        opt_b.zero_grad(set_to_none=True)
+        loss.backward()
+        opt_b.step()
+        with torch.no_grad():
+            es, ep = port.dssl_get_embedding(x1, x2, p)
+        l2, _, _, _ = port.probe_shared_step([es] + ep, heads, y, "cml", 1, 5, 50)
+        opt_h.zero_grad(set_to_none=True)
+        l2.backward()
+        opt_h.step()
+        return float(loss) + float(l2)
+    return step
+
+
+def time_cpu(B, steps, warmup):
+    step = cpu_step_factory(B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return B / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    torch.set_float32_matmul_precision("highest")
+    B = args.cpu_batch
+    cores = torch.get_num_threads()
+    val, dt = time_cpu(B, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C5 DisentangledSSL 2x1024-d, hidden 512, embed 512, T=0.07 + 3-head evidential probe",
+                   "global_batch": B, "note": "CPU oracle port of the reference step (oracle/port.py, torch CPU fp32 'highest'); "
+                   "the reference materialises [2B,2B] logits so it is timed at a bounded batch; cost grows ~B^2"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full steps (fwd+bwd+Adam, probe fwd+bwd+AdamW) at batch {B}"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, world, local_rank):
+    import disentagled_multimodal_fusion_b200 as pkg
+    from disentagled_multimodal_fusion_b200 import ops, _lib
+    from disentagled_multimodal_fusion_b200.dp import FlatParams, shard_rows
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.require_device()
+    Bg = args.batch
+    lo, hi = shard_rows(Bg, rank, world)
+    Bl = hi - lo
+    prec = args.precision
+
+    torch.manual_seed(0)                      # identical replicated parameters on every rank
+    model = pkg.DisentangledSSL(output_dim=DIMS, hidden_dim=HID, embed_dim=EMB, a=1.0, vmfkappa=1, precision=prec,
+                                noise_mode="device").to(dev)
+    probe = pkg.EvidentialProbeModule(model, num_classes=NCLS, input_dim=EMB, hidden_dim=(128,), lr=3e-3, dropout=0.0,
+                                      annealing_start=50, aggregation="cml", fused=1).to(dev)
+    probe.backbone = model                    # the probe reads the live (frozen-for-it) backbone of this step
+    probe.criterion.annealing_step = 5
+    bb = FlatParams(model.parameters())
+    hd = FlatParams([p for n, p in probe.named_parameters() if not n.startswith("backbone.")])
+
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host = {}
+    for k, d in (("x1", DIMS[0]), ("x2", DIMS[1])):
+        host[k] = torch.randn(Bl, d, generator=gen).pin_memory()
+    host["v1"] = (host["x1"] + 0.01 * torch.randn(Bl, DIMS[0], generator=gen)).pin_memory()
+    host["v2"] = (host["x2"] + 0.01 * torch.randn(Bl, DIMS[1], generator=gen)).pin_memory()
+    host["y"] = torch.randint(0, NCLS, (Bl,), generator=gen).pin_memory()
+    devin = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def step(inp):
+        loss, logs = model(inp["x1"], inp["x2"], inp["v1"], inp["v2"])
+        bb.zero_grad()
+        loss.backward()
+        bb.allreduce_grads()
+        bb.adam_step(1e-4)
+        ploss, _, _, _ = probe.shared_step([inp["x1"], inp["x2"], inp["y"]])
+        hd.zero_grad()
+        ploss.backward()
+        hd.allreduce_grads()
+        hd.adam_step(3e-3, weight_decay=1e-4, decoupled=True)
+        return loss.detach() + ploss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, fn):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(nsteps):
+            fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step(devin)
+    # ---- main number: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = _lib.launch_count()
+    ops.PROFILE.clear()
+    ops.PROFILE_ON = True
+    ms = timed(args.steps, lambda: step(devin))
+    ops.PROFILE_ON = False
+    launches = _lib.launch_count() - l0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    value = Bg * args.steps / (ms / 1e3)
+
+    # ---- end-to-end: pinned host -> device copies every step + loss read back
+    copy_stream = torch.cuda.Stream()
+    bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            for k, v in host.items():
+                bufs[i][k].copy_(v, non_blocking=True)
+            ready[i].record(copy_stream)
+    state = {"i": 0}
+    d2h = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        i = state["i"]
+        torch.cuda.current_stream().wait_event(ready[i])
+        copy_stream.wait_stream(torch.cuda.current_stream())   # next copy must not overwrite a buffer in use
+        prefetch(i ^ 1)
+        out = step(bufs[i])
+        d2h.copy_(out.reshape(1), non_blocking=False)           # device->host read of the step's loss
+        state["i"] = i ^ 1
+    prefetch(0)
+    e2e_step()
+    ms_e2e = timed(args.steps, e2e_step)
+    e2e_value = Bg * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        return
+    pk = peaks()
+    # roofline of the dominant kernel (InfoNCE backward): algorithmic FLOPs per launch = 2*Ma*Nb*D
+    prof = ops.profile_summary()
+    roof = None
+    if "infonce_bwd" in prof:
+        n, tot_ms = prof["infonce_bwd"]
+        avg_ms = tot_ms / n
+        flops = 2.0 * Bl * Bg * EMB
+        ach = flops / (avg_ms * 1e-3) / 1e12
+        roof = {"kernel": "infonce_bwd_tc_kernel", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                "frac": ach / pk["tf_sust"], "traffic": None, "launches": n, "avg_ms": avg_ms,
+                "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
+                "share_of_step": tot_ms / ms,
+                "other_kernels_ms_per_step": {k: v[1] / args.steps for k, v in prof.items()}}
+    step_flops = 73.9e12 * (Bg / 65536.0) ** 2 if Bg else 0
+    cpu = None
+    if not args.no_cpu_baseline:
+        torch.set_float32_matmul_precision("highest")
+        cval, cdt = time_cpu(args.cpu_batch, 2, 1)
+        cpu = {"value": cval, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"2 full steps of the oracle port at batch {args.cpu_batch} (reference cost grows ~B^2; B=65536 needs 64 GiB per logits temp)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": "C5 DisentangledSSL 2x1024-d, hidden 512, embed 512, T=0.07 + 3-head evidential probe (C=10)",
+                   "global_batch": Bg, "per_gpu_batch": Bl, "parallelism": f"dp{world}",
+                   "l2": "inputs (1 GiB/step/GPU at dp1) and embeddings are larger than the 126 MB L2",
+                   "noise": "vMF noise drawn on device every step (dmf_vmf_draw)"},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "step_tflops_algorithmic": step_flops / 1e12,
+        "step_frac_of_sustained_bf16": step_flops / (ms / args.steps * 1e-3) / 1e12 / (pk["tf_sust"] * world),
+        "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="GLOBAL batch (sharded over ranks)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_gpu(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -74,13 +74,37 @@ class DisentangledSSL(LightningModule):
         self.shared_embedding_dim = 2 * embed_dim   # width of get_embedding()[0]
 
     # ---------- models/disentangledssl.py:67-80
+    def _encode(self, rows1, rows2):
+        """shared + private encoders on row-stacked inputs of the two modalities (one grouped launch
+        per layer): returns (E1, E2, P1, P2).  bf16 path: inputs are cast once into the
+        [rows, d + D] concat buffers that feed both the shared (K = d) and the private (K = d + D) MLP."""
+        D = self.embed_dim
+        if self.precision == "bf16":
+            bufs = []
+            for parts in (rows1, rows2):
+                d = parts[0].shape[1]
+                n = sum(p.shape[0] for p in parts)
+                buf = torch.empty(n, d + D, dtype=torch.bfloat16, device=parts[0].device)
+                o = 0
+                for p in parts:
+                    ops.cast_bf16(p.contiguous(), buf[o:], d + D)
+                    o += p.shape[0]
+                bufs.append(buf)
+            ins = [bufs[0][:, :rows1[0].shape[1]], bufs[1][:, :rows2[0].shape[1]]]
+            E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="bf16")
+            P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], bufs, extras=[E1, E2], precision="bf16")
+        else:
+            ins = [torch.cat(rows1, 0) if len(rows1) > 1 else rows1[0], torch.cat(rows2, 0) if len(rows2) > 1 else rows2[0]]
+            E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="fp32")
+            P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], ins, extras=[E1, E2], precision="fp32")
+        return E1, E2, P1, P2
+
     @torch.no_grad()
     def get_embedding(self, x):
         require_device()
         x1 = self.feature_encoders[0](x[0].float())
         x2 = self.feature_encoders[1](x[1].float())
-        zsx1, zsx2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], [x1, x2], precision="fp32")
-        z1x1, z2x2 = grouped_forward([self.encoder_x1, self.encoder_x2], [x1, x2], extras=[zsx1, zsx2], precision="fp32")
+        zsx1, zsx2, z1x1, z2x2 = self._encode([x1], [x2])
         return torch.cat([zsx1, zsx2], dim=1), [z1x1, z2x2]
 
     def draw_noise(self, B, device):
@@ -105,21 +129,9 @@ class DisentangledSSL(LightningModule):
         dev = x1.device
         if noise is None:
             noise = self.draw_noise(B, dev)
-        bf16 = self.precision == "bf16"
-
-        # stack original + augmented rows: one group per modality
-        if bf16:
-            bufs = []
-            for x, v in ((x1, v1), (x2, v2)):
-                d = x.shape[1]
-                buf = torch.empty(2 * B, d + D, dtype=torch.bfloat16, device=dev)
-                ops.cast_bf16(x.contiguous(), buf[:B], d + D)
-                ops.cast_bf16(v.contiguous(), buf[B:], d + D)
-                bufs.append(buf)
-            ins = [bufs[0][:, :x1.shape[1]], bufs[1][:, :x2.shape[1]]]
-        else:
-            ins = [torch.cat([x1, v1], 0), torch.cat([x2, v2], 0)]
-        E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision=self.precision)  # [2B,D] each
+        # stack original + augmented rows: one group per modality; private encoders are conditioned
+        # on the shared code (layer-0 input = [x | e])
+        E1, E2, P1, P2 = self._encode([x1, v1], [x2, v2])                       # [2B, D] each
 
         # vMF reparameterised samples (noise rows follow the stacking: modality 1 <- draws 0,2; modality 2 <- 1,3)
         w1 = torch.cat([noise[0][0], noise[2][0]], 0)
@@ -135,11 +147,6 @@ class DisentangledSSL(LightningModule):
         loss_y = 0.5 * (loss_y + loss_y_v)
         loss_shared = joint_loss
 
-        # private encoders conditioned on the shared code: layer-0 input = [x | e]
-        if bf16:
-            P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], bufs, extras=[E1, E2], precision="bf16")
-        else:
-            P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], ins, extras=[E1, E2], precision="fp32")
         P1n, P2n = ops.row_normalize(P1), ops.row_normalize(P2)
         specific_loss_x1, _, _ = self.critic.pair(P1n[:B], P1n[B:])
         specific_loss_x2, _, _ = self.critic.pair(P2n[:B], P2n[B:])

@@ -28,6 +28,34 @@ def _dist_on() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+# ---- optional per-kernel timing with CUDA events on the launching stream (used by bench.py)
+PROFILE_ON = False
+PROFILE: dict = {}
+
+
+class _Prof:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE_ON:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE_ON:
+            self.e.record()
+            PROFILE.setdefault(self.name, []).append((self.s, self.e))
+        return False
+
+
+def profile_summary():
+    """{name: (number of timed regions, total ms)}; call after a device synchronize."""
+    return {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in PROFILE.items()}
+
+
 # ----------------------------------------------------------------------------------------
 # low-level helpers (no autograd)
 # ----------------------------------------------------------------------------------------
@@ -134,11 +162,12 @@ class _GroupedMLP(torch.autograd.Function):
         ctx.in_needs_grad = [bool(x.requires_grad) and extras[g] is None for g, x in enumerate(xs)]
         ctx.extra_cols = [0 if e is None else e.shape[1] for e in extras]
         ctx.extra_needs_grad = [e is not None and bool(e.requires_grad) for e in extras]
-        if precision == "bf16":
-            outs, saved = _GroupedMLP._fwd_bf16(xs, extras, Ws, bs, G, NL, final)
-        else:
-            xs = [x if e is None else torch.cat([_f32c(x), _f32c(e)], dim=1) for x, e in zip(xs, extras)]
-            outs, saved = _GroupedMLP._fwd_f32(xs, Ws, bs, G, NL, final, masks)
+        with _Prof("mlp_fwd"):
+            if precision == "bf16":
+                outs, saved = _GroupedMLP._fwd_bf16(xs, extras, Ws, bs, G, NL, final)
+            else:
+                xs = [x if e is None else torch.cat([_f32c(x), _f32c(e)], dim=1) for x, e in zip(xs, extras)]
+                outs, saved = _GroupedMLP._fwd_f32(xs, Ws, bs, G, NL, final, masks)
         ctx.saved = saved
         ctx.Ws, ctx.bs = Ws, bs
         return tuple(outs)
@@ -369,10 +398,11 @@ class _GroupedMLP(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         G, NL, final, precision, masks = ctx.cfg
-        if precision == "bf16":
-            dxs, dWs, dbs = _GroupedMLP._bwd_bf16(ctx, grads)
-        else:
-            dxs, dWs, dbs = _GroupedMLP._bwd_f32(ctx, grads)
+        with _Prof("mlp_bwd"):
+            if precision == "bf16":
+                dxs, dWs, dbs = _GroupedMLP._bwd_bf16(ctx, grads)
+            else:
+                dxs, dWs, dbs = _GroupedMLP._bwd_f32(ctx, grads)
         out = [None]
         out += [dxs[g] if ctx.in_needs_grad[g] else None for g in range(G)]
         out += [dxs[g] if ctx.extra_needs_grad[g] else None for g in range(G)]
@@ -432,10 +462,11 @@ class _InfoNCE(torch.autograd.Function):
         def rowlse(A, Bm, mo, lo, do):
             check(lib.dmf_rowlse(ptr(A), A.stride(0), Bl, ptr(Bm), Bm.stride(0), Bg, D, scale, ptr(st[mo]), ptr(st[lo]),
                                  off, ptr(st[do]), ptr(ws), wsb, dt, stream()))
-        rowlse(a0, g1, 0, 1, 2)      # anchors z0 vs all z1: cross block, diag = positive
-        rowlse(a0, g0, 3, 4, 5)      # anchors z0 vs all z0: intra-view block, diag = self similarity
-        rowlse(a1, g0, 6, 7, 8)
-        rowlse(a1, g1, 9, 10, 11)
+        with _Prof("rowlse_x4"):
+            rowlse(a0, g1, 0, 1, 2)      # anchors z0 vs all z1: cross block, diag = positive
+            rowlse(a0, g0, 3, 4, 5)      # anchors z0 vs all z0: intra-view block, diag = self similarity
+            rowlse(a1, g0, 6, 7, 8)
+            rowlse(a1, g1, 9, 10, 11)
         out3 = torch.zeros(3, dtype=torch.float32, device=dev)
         lse = torch.empty(2, Bl, dtype=torch.float32, device=dev)
         check(lib.dmf_infonce_finalize(ptr(st[0]), ptr(st[1]), ptr(st[3]), ptr(st[4]), ptr(st[2]), ptr(st[5]), Bl,
@@ -466,12 +497,14 @@ class _InfoNCE(torch.autograd.Function):
             g0T, g1T = transpose_bf16(g0), transpose_bf16(g1)
         else:
             g0T = g1T = None
-        check(lib.dmf_infonce_bwd(ptr(a0), a0.stride(0), Bl, ptr(lse[0]), ptr(g1), g1.stride(0), ptr(g1T),
-                                  g1T.stride(0) if g1T is not None else 0, Bg, ptr(lse_all[1]), D, scale, coef, ptr(gs),
-                                  off, ptr(dz0), D, 0, dt, stream()))
-        check(lib.dmf_infonce_bwd(ptr(a1), a1.stride(0), Bl, ptr(lse[1]), ptr(g0), g0.stride(0), ptr(g0T),
-                                  g0T.stride(0) if g0T is not None else 0, Bg, ptr(lse_all[0]), D, scale, coef, ptr(gs),
-                                  off, ptr(dz1), D, 0, dt, stream()))
+        with _Prof("infonce_bwd"):
+            check(lib.dmf_infonce_bwd(ptr(a0), a0.stride(0), Bl, ptr(lse[0]), ptr(g1), g1.stride(0), ptr(g1T),
+                                      g1T.stride(0) if g1T is not None else 0, Bg, ptr(lse_all[1]), D, scale, coef, ptr(gs),
+                                      off, ptr(dz0), D, 0, dt, stream()))
+        with _Prof("infonce_bwd"):
+            check(lib.dmf_infonce_bwd(ptr(a1), a1.stride(0), Bl, ptr(lse[1]), ptr(g0), g0.stride(0), ptr(g0T),
+                                      g0T.stride(0) if g0T is not None else 0, Bg, ptr(lse_all[0]), D, scale, coef, ptr(gs),
+                                      off, ptr(dz1), D, 0, dt, stream()))
         return dz0, dz1, None, None
 
 
@@ -670,7 +703,8 @@ class _EdlLoss(torch.autograd.Function):
         grad = torch.empty_like(evid)
         parts = torch.zeros(4, dtype=torch.float32, device=dev)
         p = L.EdlParams(B, V, Cc, L.AGG[agg], coef, dc_weight, inv_B_global)
-        check(lib.dmf_edl_fused(ptr(evid), ptr(labels), p, 0, ptr(fused), ptr(grad), 0, 0, 0, ptr(parts), stream()))
+        with _Prof("edl_fused"):
+            check(lib.dmf_edl_fused(ptr(evid), ptr(labels), p, 0, ptr(fused), ptr(grad), 0, 0, 0, ptr(parts), stream()))
         ctx.save_for_backward(grad)
         ctx.mark_non_differentiable(fused)
         return fused, parts

@@ -1,0 +1,85 @@
+"""Micro-benchmark of the individual C-ABI kernels at the C5 shapes (CUDA events, warm-up, L2-cold
+inputs by rotating buffers).  Prints one line per kernel: ms, executed TFLOP/s or GB/s."""
+import argparse
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import disentagled_multimodal_fusion_b200 as pkg
+from disentagled_multimodal_fusion_b200 import ops, _lib as L
+from disentagled_multimodal_fusion_b200._lib import lib, check, ptr, stream
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=16384)
+    ap.add_argument("--D", type=int, default=512)
+    ap.add_argument("--what", default="all")
+    a = ap.parse_args()
+    L.require_device()
+    dev = "cuda"
+    B, D = a.B, a.D
+    torch.manual_seed(0)
+    z0 = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=-1)
+    z1 = torch.nn.functional.normalize(0.5 * z0 + 0.1 * torch.randn(B, D, device=dev), dim=-1)
+    b0, b1 = ops.cast_bf16(z0), ops.cast_bf16(z1)
+    st = torch.empty(4, B, device=dev)
+    wsb = lib.dmf_rowlse_workspace_bytes(B, B)
+    ws = torch.empty(max(1, wsb // 4), device=dev)
+    scale = 1 / 0.07
+    if a.what in ("all", "rowlse"):
+        f = lambda: check(lib.dmf_rowlse(ptr(b0), D, B, ptr(b1), D, B, D, scale, ptr(st[0]), ptr(st[1]), 0, ptr(st[2]), ptr(ws), wsb, 1, stream()))
+        ms = timeit(f)
+        print(f"rowlse_tc B={B} D={D}: {ms:.3f} ms  {2*B*B*D/ms/1e9:.1f} TFLOP/s executed")
+    if a.what in ("all", "bwd"):
+        lse = torch.full((2, B), 3.0, device=dev)
+        f = lambda: check(lib.dmf_rowlse(ptr(b0), D, B, ptr(b1), D, B, D, scale, ptr(st[0]), ptr(st[1]), 0, ptr(st[2]), ptr(ws), wsb, 1, stream()))
+        f()
+        lse[0] = st[0] + torch.log(st[1])
+        check(lib.dmf_rowlse(ptr(b1), D, B, ptr(b0), D, B, D, scale, ptr(st[0]), ptr(st[1]), 0, ptr(st[2]), ptr(ws), wsb, 1, stream()))
+        lse[1] = st[0] + torch.log(st[1])
+        b1T = ops.transpose_bf16(b1)
+        dz = torch.empty(B, D, device=dev)
+        one = torch.ones(1, device=dev)
+        g = lambda: check(lib.dmf_infonce_bwd(ptr(b0), D, B, ptr(lse[0]), ptr(b1), D, ptr(b1T), b1T.stride(0), B, ptr(lse[1]), D,
+                                              scale, scale / (2 * B), ptr(one), 0, ptr(dz), D, 0, 1, stream()))
+        ms = timeit(g)
+        print(f"infonce_bwd_tc B={B} D={D}: {ms:.3f} ms  algorithmic {2*B*B*D/ms/1e9:.1f} TFLOP/s, executed {(D//128)*(2*B*B*D + 2*B*B*128)/ms/1e9:.1f} TFLOP/s")
+    if a.what in ("all", "gemm"):
+        M = 2 * B
+        for (K, N) in ((1024, 512), (512, 512), (1536, 512)):
+            A = torch.randn(M, K, device=dev).bfloat16()
+            W = torch.randn(N, K, device=dev).bfloat16()
+            o = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+            bias = torch.zeros(N, device=dev)
+            h = lambda: ops.gemm_tc([dict(A=A, lda=K, B=W, ldb=K, out_bf16=o, ldo_bf16=N, bias=bias, M=M, N=N, K=K)] * 2, L.EPI_BIAS_RELU)
+            ms = timeit(h)
+            print(f"gemm_tc 2 groups M={M} N={N} K={K}: {ms:.3f} ms  {2*2*M*N*K/ms/1e9:.1f} TFLOP/s")
+    if a.what in ("all", "edl"):
+        Be, V, C = 1 << 22, 4, 42
+        evid = torch.rand(Be, V, C, device=dev) * 3
+        y = torch.randint(0, C, (Be,), device=dev)
+        fused = torch.empty(Be, C, device=dev); grad = torch.empty_like(evid)
+        u = torch.empty(Be, device=dev); ale = torch.empty(Be, device=dev); parts = torch.zeros(4, device=dev)
+        for dcw, tag in ((0.6, "fused=1"), (0.0, "fused=0")):
+            p = L.EdlParams(Be, V, C, 0, 0.5, dcw, 1.0 / Be)
+            k = lambda: check(lib.dmf_edl_fused(ptr(evid), ptr(y), p, 0, ptr(fused), ptr(grad), ptr(u), ptr(ale), 0, ptr(parts), stream()))
+            ms = timeit(k, iters=3, warm=1)
+            byt = Be * (8 * V * C + 4 * C + 16 + 8)
+            print(f"edl_fused B={Be} V={V} C={C} {tag}: {ms:.3f} ms  {byt/ms/1e6:.1f} GB/s algorithmic")
+
+
+if __name__ == "__main__":
+    main()

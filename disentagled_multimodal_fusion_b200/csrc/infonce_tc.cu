@@ -16,6 +16,7 @@
 // All operands are K-major / 128B swizzle, the same descriptor family as gemm_tc.cu.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace dmf {
 
@@ -32,9 +33,9 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 // ------------------------------------------------------------------------------------------ forward
-constexpr int FW_STAGES = 5, FW_BUFS = 4;
+constexpr int FW_STAGES = 5, FW_BUFS = 4, FW_THREADS = 320;
 
-__global__ void __launch_bounds__(NT_THREADS, 1)
+__global__ void __launch_bounds__(FW_THREADS, 1)
 rowlse_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Ma, int Nb,
                  int num_kb, float scale, int tiles_per_split, float* __restrict__ part_max,
                  float* __restrict__ part_sum, long long diag_offset, float* __restrict__ diag_out) {
@@ -61,7 +62,7 @@ rowlse_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc::tma_prefetch_desc(&tmB);
     tc::mbar_init(a_full, 1);
     for (int s = 0; s < FW_STAGES; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
-    for (int b = 0; b < FW_BUFS; ++b) { tc::mbar_init(s_full + b, 1); tc::mbar_init(s_empty + b, 4); }
+    for (int b = 0; b < FW_BUFS; ++b) { tc::mbar_init(s_full + b, 1); tc::mbar_init(s_empty + b, 8); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
@@ -113,52 +114,84 @@ rowlse_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
+    // 8 softmax warps: lane quarter q = warp % 4 (TMEM access rule), column half ch of every tile
+    const int sw = warp - 2;
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
+    const int ch = sw >> 2;
+    const int rloc = q * 32 + lane;
+    const int row = m0 + rloc;
     const float sl2 = scale * kLog2e;
     float m = -INFINITY, l = 0.f, diag = 0.f;
+    bool has_diag = false;
     const long long dj = (diag_offset >= 0 && row < Ma) ? diag_offset + row : -1;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t % FW_BUFS;
       tc::mbar_wait(s_full + buf, ((uint32_t)(t / FW_BUFS)) & 1);
       tc::tc_fence_after_sync();
-      const int j0 = (jt0 + t) * 128;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      const int j0 = (jt0 + t) * 128 + ch * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + c * 32), r);
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + ch * 64 + c * 32), r);
         tc::tmem_ld_wait();
         const int nbase = j0 + c * 32;
         const int nvalid = Nb - nbase;   // columns >= Nb are TMA zero fill: excluded
         if (nvalid <= 0) continue;
-        float tv[32];
-        float cmax = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          tv[j] = (j < nvalid) ? __uint_as_float(r[j]) * sl2 : -INFINITY;
-          cmax = fmaxf(cmax, tv[j]);
-        }
         if (dj >= nbase && dj < nbase + 32) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (nbase + j == dj) diag = __uint_as_float(r[j]) * scale;
+            if (nbase + j == dj) { diag = __uint_as_float(r[j]) * scale; has_diag = true; }
         }
-        const float mn = fmaxf(m, cmax);
-        float ps = 0.f;
+        float cmax = -INFINITY;
+        if (nvalid >= 32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) ps += fast_exp2(tv[j] - mn);
-        l = l * fast_exp2(m - mn) + ps;
+          for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) cmax = fmaxf(cmax, __uint_as_float(r[j]));
+        }
+        const float mn = fmaxf(m, cmax * sl2);     // sl2 > 0: max commutes with the scaling
+        float ps0 = 0.f, ps1 = 0.f;
+        if (nvalid >= 32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            ps0 += fast_exp2(fmaf(__uint_as_float(r[j]), sl2, -mn));
+            ps1 += fast_exp2(fmaf(__uint_as_float(r[j + 1]), sl2, -mn));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) ps0 += fast_exp2(fmaf(__uint_as_float(r[j]), sl2, -mn));
+        }
+        l = l * fast_exp2(m - mn) + (ps0 + ps1);
         m = mn;
       }
       tc::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(s_empty + buf);
     }
-    if (row < Ma) {
-      part_max[(long long)blockIdx.y * Ma + row] = m;   // log2 domain
-      part_sum[(long long)blockIdx.y * Ma + row] = l;
-      if (diag_out && dj >= 0 && dj >= (long long)jt0 * 128 && dj < (long long)(jt0 + ntiles) * 128 && dj < Nb)
-        diag_out[row] = diag;
+    // merge the two column halves of every row (warps w and w+4 share a lane quarter)
+    float* mrg = reinterpret_cast<float*>(tmem_slot + 4);     // [4][128]: m, l, diag, has_diag of half 1
+    if (ch == 1) {
+      mrg[rloc] = m;
+      mrg[128 + rloc] = l;
+      mrg[256 + rloc] = diag;
+      mrg[384 + rloc] = has_diag ? 1.f : 0.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (ch == 0 && row < Ma) {
+      const float m1 = mrg[rloc], l1 = mrg[128 + rloc];
+      const float M = fmaxf(m, m1);
+      float Lc = 0.f;
+      if (m > -INFINITY) Lc += l * fast_exp2(m - M);
+      if (m1 > -INFINITY) Lc += l1 * fast_exp2(m1 - M);
+      part_max[(long long)blockIdx.y * Ma + row] = M;   // log2 domain
+      part_sum[(long long)blockIdx.y * Ma + row] = Lc;
+      if (diag_out) {
+        if (has_diag) diag_out[row] = diag;
+        else if (mrg[384 + rloc] != 0.f) diag_out[row] = mrg[256 + rloc];
+      }
     }
   }
   tc::tc_fence_before_sync();
@@ -387,6 +420,11 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
 using namespace dmf;
 
+int dmf_infonce_bwd_bf16_tc2(const void* A, long long lda, int Ma, const float* lseA, const void* Bm, long long ldb,
+                             const void* BmT, long long ldbt, int Nb, const float* lseB, int D, float scale, float coef,
+                             const float* gscale, long long diag_offset, float* dA, long long ldda, int accumulate,
+                             cudaStream_t s);
+
 static int pick_nsplit(int row_blocks, int col_tiles) {
   int best = 1;
   double best_eff = 0.0;
@@ -419,11 +457,11 @@ int dmf_rowlse_bf16_tc(const void* A, long long lda, int Ma, const void* Bm, lon
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, Bm, Nb, D, ldb, 128);
   if (rc) return rc;
-  const size_t smem = 1024 + (size_t)(num_kb + FW_STAGES) * NT_TILE + 256;
+  const size_t smem = 1024 + (size_t)(num_kb + FW_STAGES) * NT_TILE + 256 + 2048;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(rowlse_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(1024 + (size_t)(NT_MAX_KB + FW_STAGES) * NT_TILE + 256));
+                                         (int)(1024 + (size_t)(NT_MAX_KB + FW_STAGES) * NT_TILE + 256 + 2048));
     if (e != cudaSuccess) return fail((int)e, "dmf_rowlse(bf16): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr = true;
   }
@@ -431,7 +469,7 @@ int dmf_rowlse_bf16_tc(const void* A, long long lda, int Ma, const void* Bm, lon
   float* pm = nsplit > 1 ? (float*)workspace : row_max;
   float* ps = nsplit > 1 ? (float*)workspace + (size_t)nsplit * Ma : row_sum;
   dim3 grid(row_blocks, nsplit);
-  rowlse_tc_kernel<<<grid, NT_THREADS, smem, s>>>(tmA, tmB, Ma, Nb, num_kb, scale, tiles_per_split, pm, ps, diag_offset,
+  rowlse_tc_kernel<<<grid, FW_THREADS, smem, s>>>(tmA, tmB, Ma, Nb, num_kb, scale, tiles_per_split, pm, ps, diag_offset,
                                                   diag_out);
   rc = launched("dmf_rowlse(bf16)");
   if (rc) return rc;
@@ -447,6 +485,13 @@ int dmf_infonce_bwd_bf16_tc(const void* A, long long lda, int Ma, const float* l
   DMF_REQUIRE(D % 64 == 0 && D >= 64 && D <= 64 * NT_MAX_KB, "dmf_infonce_bwd(bf16): D=%d must be a multiple of 64 in [64,%d]",
               D, 64 * NT_MAX_KB);
   DMF_REQUIRE(BmT, "dmf_infonce_bwd(bf16): needs the transposed column block BmT [D, Nb]");
+  {
+    static int use_v1 = -1;
+    if (use_v1 < 0) use_v1 = getenv("DMF_BWD_V1") ? 1 : 0;
+    if (!use_v1)
+      return dmf_infonce_bwd_bf16_tc2(A, lda, Ma, lseA, Bm, ldb, BmT, ldbt, Nb, lseB, D, scale, coef, gscale, diag_offset,
+                                      dA, ldda, accumulate, s);
+  }
   const int num_kb = D / 64;
   CUtensorMap tmA, tmB, tmBT;
   int rc = make_tmap_bf16_2d(&tmA, A, Ma, D, lda, 128);

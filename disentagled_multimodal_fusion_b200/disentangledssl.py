@@ -153,9 +153,20 @@ class DisentangledSSL(LightningModule):
         loss_specific = specific_loss_x1 + specific_loss_x2
 
         lmd = self.lmd_scheduler(self.iterations) if self.lmd_end_value > 0 else self.lmd_start_value
-        loss_ortho = 0.5 * (ops.ortho_loss(P1[:B], E1[:B]) + ops.ortho_loss(P2[:B], E2[:B])) + \
-            0.5 * (ops.ortho_loss(P1[B:], E1[B:]) + ops.ortho_loss(P2[B:], E2[B:]))
-        loss = 2 * loss_shared / (1 + self.a) + self.a * loss_specific / (1 + self.a) + lmd * loss_ortho
+
+        def _ortho():
+            pr = self.precision
+            return 0.5 * (ops.ortho_loss(P1[:B], E1[:B], pr) + ops.ortho_loss(P2[:B], E2[:B], pr)) + \
+                0.5 * (ops.ortho_loss(P1[B:], E1[B:], pr) + ops.ortho_loss(P2[B:], E2[B:], pr))
+        if lmd == 0:
+            # reference default (lmd_start_value = lmd_end_value = 0): the term is logged but its weight is
+            # exactly zero, so its backward pass (two R x D x D GEMMs per call) is skipped
+            with torch.no_grad():
+                loss_ortho = _ortho()
+            loss = 2 * loss_shared / (1 + self.a) + self.a * loss_specific / (1 + self.a)
+        else:
+            loss_ortho = _ortho()
+            loss = 2 * loss_shared / (1 + self.a) + self.a * loss_specific / (1 + self.a) + lmd * loss_ortho
         # device scalars (the reference does seven .item() syncs here)
         logs = {'loss': loss.detach(), 'shared': loss_shared.detach(), 'clip': joint_loss.detach(),
                 'loss_x': loss_x, 'loss_y': loss_y, 'specific': loss_specific.detach(),

@@ -576,7 +576,7 @@ class _OrthoLoss(torch.autograd.Function):
     all-reduced across ranks before the square root."""
 
     @staticmethod
-    def forward(ctx, z1, zs):
+    def forward(ctx, z1, zs, precision):
         L.require_device()
         z1, zs = _f32c(z1), _f32c(zs)
         R, D = z1.shape
@@ -587,16 +587,32 @@ class _OrthoLoss(torch.autograd.Function):
         check(lib.dmf_row_normalize_fwd(ptr(z1), D, R, D, 1e-12, ptr(n1), D, 0, 0, ptr(i1), stream()))
         check(lib.dmf_row_normalize_fwd(ptr(zs), D, R, D, 1e-12, ptr(ns), D, 0, 0, ptr(i2), stream()))
         # split the batch (the contraction dim) over chunks so the grid fills the GPU
-        chunks = max(1, min(64, R // 512))
-        rows = (R + chunks - 1) // chunks
-        chunks = (R + rows - 1) // rows
-        part = torch.empty(chunks, D * D, dtype=torch.float32, device=dev)
-        descs = []
-        for c in range(chunks):
-            r0 = c * rows
-            rc = min(rows, R - r0)
-            descs.append(dict(A=n1[r0:], a_rs=1, a_cs=D, B=ns[r0:], b_rs=D, b_cs=1, C=part[c], ldc=D, M=D, N=D, K=rc))
-        gemm_f32(descs, L.EPI_NONE)
+        if precision == "bf16" and R >= 64:
+            # tensor-core Gram: both operands K-major after a cast+transpose ([D, R] bf16)
+            n1T, nsT = cast_transpose_bf16(n1), cast_transpose_bf16(ns)
+            Rp = n1T.stride(0)
+            tiles = ((D + 127) // 128) ** 2
+            chunks = max(1, min(48, (2 * 148 + tiles - 1) // tiles, R // 256))
+            rows = ((R + chunks - 1) // chunks + 63) // 64 * 64
+            chunks = (R + rows - 1) // rows
+            part = torch.empty(chunks, D * D, dtype=torch.float32, device=dev)
+            descs = []
+            for c in range(chunks):
+                r0 = c * rows
+                rc = min(rows, R - r0)
+                descs.append(dict(A=n1T[:, r0:], lda=Rp, B=nsT[:, r0:], ldb=Rp, out_f32=part[c], ldo_f32=D, M=D, N=D, K=rc))
+            gemm_tc(descs, L.EPI_NONE)
+        else:
+            chunks = max(1, min(64, R // 512))
+            rows = (R + chunks - 1) // chunks
+            chunks = (R + rows - 1) // rows
+            part = torch.empty(chunks, D * D, dtype=torch.float32, device=dev)
+            descs = []
+            for c in range(chunks):
+                r0 = c * rows
+                rc = min(rows, R - r0)
+                descs.append(dict(A=n1[r0:], a_rs=1, a_cs=D, B=ns[r0:], b_rs=D, b_cs=1, C=part[c], ldc=D, M=D, N=D, K=rc))
+            gemm_f32(descs, L.EPI_NONE)
         gram = colsum(part).view(D, D)
         if _dist_on():
             dist.all_reduce(gram)
@@ -623,11 +639,11 @@ class _OrthoLoss(torch.autograd.Function):
         d2 = torch.empty_like(ns)
         check(lib.dmf_row_normalize_bwd(ptr(n1), D, ptr(i1), ptr(dn1), D, R, D, ptr(d1), D, 0, stream()))
         check(lib.dmf_row_normalize_bwd(ptr(ns), D, ptr(i2), ptr(dns), D, R, D, ptr(d2), D, 0, stream()))
-        return d1, d2
+        return d1, d2, None
 
 
-def ortho_loss(z1: Tensor, zs: Tensor) -> Tensor:
-    return _OrthoLoss.apply(z1, zs)
+def ortho_loss(z1: Tensor, zs: Tensor, precision: str = "fp32") -> Tensor:
+    return _OrthoLoss.apply(z1, zs, precision)
 
 
 # ----------------------------------------------------------------------------------------

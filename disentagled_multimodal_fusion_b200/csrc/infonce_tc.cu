@@ -424,6 +424,10 @@ int dmf_infonce_bwd_bf16_tc2(const void* A, long long lda, int Ma, const float* 
                              const void* BmT, long long ldbt, int Nb, const float* lseB, int D, float scale, float coef,
                              const float* gscale, long long diag_offset, float* dA, long long ldda, int accumulate,
                              cudaStream_t s);
+int dmf_infonce_bwd_bf16_tc3(const void* A, long long lda, int Ma, const float* lseA, const void* Bm, long long ldb,
+                             const void* BmT, long long ldbt, int Nb, const float* lseB, int D, float scale, float coef,
+                             const float* gscale, long long diag_offset, float* dA, long long ldda, int accumulate,
+                             cudaStream_t s);
 
 static int pick_nsplit(int row_blocks, int col_tiles) {
   int best = 1;
@@ -442,11 +446,31 @@ extern "C" size_t dmf_rowlse_workspace_bytes(int Ma, int Nb) {
   return (size_t)8 * 2 * sizeof(float) * (size_t)(Ma > 0 ? Ma : 0);
 }
 
+int dmf_rowlse_bf16_tc2(const void* A, long long lda, int Ma, const void* Bm, long long ldb, int Nb, int D, float scale,
+                        float* pm, float* ps, int nsplit, int tiles_per_split, long long diag_offset, float* diag_out,
+                        cudaStream_t s);
+
 int dmf_rowlse_bf16_tc(const void* A, long long lda, int Ma, const void* Bm, long long ldb, int Nb, int D, float scale,
                        float* row_max, float* row_sum, long long diag_offset, float* diag_out, void* workspace,
                        size_t workspace_bytes, cudaStream_t s) {
   DMF_REQUIRE(D % 64 == 0 && D >= 64 && D <= 64 * NT_MAX_KB, "dmf_rowlse(bf16): D=%d must be a multiple of 64 in [64,%d]", D,
               64 * NT_MAX_KB);
+  static int use_v1 = -1;
+  if (use_v1 < 0) use_v1 = getenv("DMF_FWD_V1") ? 1 : 0;
+  if (!use_v1) {
+    // CTA-pair kernel: 256-row anchor blocks x 256-column tiles
+    const int pairs = (Ma + 255) / 256, col_tiles2 = (Nb + 255) / 256;
+    int ns = pick_nsplit(2 * pairs, col_tiles2);
+    const size_t need2 = (size_t)ns * 2 * sizeof(float) * (size_t)Ma;
+    if (ns > 1 && (!workspace || workspace_bytes < need2)) ns = 1;
+    const int tps = (col_tiles2 + ns - 1) / ns;
+    float* pm2 = ns > 1 ? (float*)workspace : row_max;
+    float* ps2 = ns > 1 ? (float*)workspace + (size_t)ns * Ma : row_sum;
+    int rc2 = dmf_rowlse_bf16_tc2(A, lda, Ma, Bm, ldb, Nb, D, scale, pm2, ps2, ns, tps, diag_offset, diag_out, s);
+    if (rc2) return rc2;
+    rowlse_combine_kernel<<<(Ma + 255) / 256, 256, 0, s>>>(pm2, ps2, Ma, ns, row_max, row_sum);
+    return launched("dmf_rowlse(bf16) combine");
+  }
   const int num_kb = D / 64;
   const int row_blocks = (Ma + 127) / 128, col_tiles = (Nb + 127) / 128;
   int nsplit = pick_nsplit(row_blocks, col_tiles);
@@ -486,8 +510,11 @@ int dmf_infonce_bwd_bf16_tc(const void* A, long long lda, int Ma, const float* l
               D, 64 * NT_MAX_KB);
   DMF_REQUIRE(BmT, "dmf_infonce_bwd(bf16): needs the transposed column block BmT [D, Nb]");
   {
-    static int use_v1 = -1;
-    if (use_v1 < 0) use_v1 = getenv("DMF_BWD_V1") ? 1 : 0;
+    static int use_v1 = -1, use_v2 = -1;
+    if (use_v1 < 0) { use_v1 = getenv("DMF_BWD_V1") ? 1 : 0; use_v2 = getenv("DMF_BWD_V2") ? 1 : 0; }
+    if (!use_v1 && !use_v2)
+      return dmf_infonce_bwd_bf16_tc3(A, lda, Ma, lseA, Bm, ldb, BmT, ldbt, Nb, lseB, D, scale, coef, gscale, diag_offset,
+                                      dA, ldda, accumulate, s);
     if (!use_v1)
       return dmf_infonce_bwd_bf16_tc2(A, lda, Ma, lseA, Bm, ldb, BmT, ldbt, Nb, lseB, D, scale, coef, gscale, diag_offset,
                                       dA, ldda, accumulate, s);

@@ -52,7 +52,9 @@ class TcGemmDesc(C.Structure):
                 ("out_bf16", c_p), ("ldo_bf16", c_ll),
                 ("bias", c_p),
                 ("mask_bf16", c_p), ("ldmask", c_ll),
-                ("M", c_i), ("N", c_i), ("K", c_i)]
+                ("M", c_i), ("N", c_i), ("K", c_i),
+                ("out_bf16_t", c_p), ("ldo_t", c_ll),
+                ("split_k", c_i)]
 
 
 class EdlParams(C.Structure):
@@ -74,6 +76,8 @@ _SIGS = {
     "dmf_cast_f32_to_bf16": ([c_p, c_ll, c_p, c_ll, c_i, c_i, c_p], c_i),
     "dmf_cast_transpose_f32_to_bf16": ([c_p, c_ll, c_p, c_ll, c_i, c_i, c_p], c_i),
     "dmf_transpose_bf16": ([c_p, c_ll, c_p, c_ll, c_i, c_i, c_p], c_i),
+    "dmf_cast_dual_bf16": ([c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_i, c_i, c_p], c_i),
+    "dmf_colsum_bf16": ([c_p, c_ll, c_i, c_i, c_p, c_p], c_i),
     "dmf_rowlse": ([c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_f, c_p, c_p, c_ll, c_p, c_p, c_sz, c_i, c_p], c_i),
     "dmf_rowlse_workspace_bytes": ([c_i, c_i], c_sz),
     "dmf_infonce_finalize": ([c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_f, c_i, c_p, c_p, c_p], c_i),

@@ -73,10 +73,10 @@ class EvidentialNN(Linear):
         super().__init__(dropout=dropout, output_dims=output_dims, layers=layers, initialization=initialization)
 
 
-def grouped_forward(mods, xs, extras=None, precision=None):
+def grouped_forward(mods, xs, extras=None, precision=None, opts=None):
     """Run several same-depth MLP modules in one launch per layer (views x streams)."""
     masks = [m.dropout_masks(x) for m, x in zip(mods, xs)]
     if all(mk is None for mk in masks):
         masks = None
     return ops.grouped_mlp(list(xs), [m.weights() for m in mods], [m.biases() for m in mods], final=mods[0].final,
-                           precision=precision or mods[0].precision, dropout_masks=masks, extras=extras)
+                           precision=precision or mods[0].precision, dropout_masks=masks, extras=extras, opts=opts)

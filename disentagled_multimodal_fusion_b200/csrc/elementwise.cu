@@ -431,6 +431,120 @@ __global__ void transpose_to_bf16_kernel(const TIn* __restrict__ src, long long 
   }
 }
 
+
+// fp32 [rows, cols] -> bf16 row-major copy AND bf16 transposed copy in ONE pass over the source, plus
+// optional column sums (bias gradient).  The transposed copy is what the wgrad GEMM consumes as a K-major
+// operand (K = batch).  64 x 64 tile per CTA; fp32 tile in smem (65-word pitch).
+__global__ void __launch_bounds__(256)
+cast_dual_kernel(const float* __restrict__ src, long long lds, uint16_t* __restrict__ dst, long long ldd,
+                 uint16_t* __restrict__ dstT, long long ldt, float* __restrict__ colsum, int rows, int cols) {
+  __shared__ float tile[64][65];
+  __shared__ float cacc[64];
+  const int t = threadIdx.x;
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int cg = (t & 15) * 4, rl = t >> 4;              // 16 column groups of 4, 16 row lanes
+  if (colsum && t < 64) cacc[t] = 0.f;
+  float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
+  const bool vec = ((lds & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (c0 + 64 <= cols);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int r = rl + p * 16;
+    const int gr = r0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < rows) {
+      const float* sp = src + (long long)gr * lds + c0 + cg;
+      if (vec) {
+        v = __ldg(reinterpret_cast<const float4*>(sp));
+      } else {
+        if (c0 + cg + 0 < cols) v.x = sp[0];
+        if (c0 + cg + 1 < cols) v.y = sp[1];
+        if (c0 + cg + 2 < cols) v.z = sp[2];
+        if (c0 + cg + 3 < cols) v.w = sp[3];
+      }
+      if (dst) {
+        uint16_t* dp = dst + (long long)gr * ldd + c0 + cg;
+        if (vec && ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+          uint2 pk;
+          pk.x = (uint32_t)f2bf(v.x) | ((uint32_t)f2bf(v.y) << 16);
+          pk.y = (uint32_t)f2bf(v.z) | ((uint32_t)f2bf(v.w) << 16);
+          *reinterpret_cast<uint2*>(dp) = pk;
+        } else {
+          if (c0 + cg + 0 < cols) dp[0] = f2bf(v.x);
+          if (c0 + cg + 1 < cols) dp[1] = f2bf(v.y);
+          if (c0 + cg + 2 < cols) dp[2] = f2bf(v.z);
+          if (c0 + cg + 3 < cols) dp[3] = f2bf(v.w);
+        }
+      }
+    }
+    cs0 += v.x; cs1 += v.y; cs2 += v.z; cs3 += v.w;
+    tile[r][cg + 0] = v.x; tile[r][cg + 1] = v.y; tile[r][cg + 2] = v.z; tile[r][cg + 3] = v.w;
+  }
+  __syncthreads();
+  if (colsum) {
+    atomicAdd(&cacc[cg + 0], cs0); atomicAdd(&cacc[cg + 1], cs1);
+    atomicAdd(&cacc[cg + 2], cs2); atomicAdd(&cacc[cg + 3], cs3);
+  }
+  if (dstT) {
+    const int rg = (t & 15) * 4, cl = t >> 4;            // 16 row groups of 4, 16 column lanes
+    const bool vt = ((ldt & 3) == 0) && ((reinterpret_cast<uintptr_t>(dstT) & 7) == 0) && (r0 + 64 <= rows);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int c = cl + p * 16;
+      if (c0 + c >= cols) continue;
+      uint16_t* dp = dstT + (long long)(c0 + c) * ldt + r0 + rg;
+      const float a = tile[rg + 0][c], b = tile[rg + 1][c], cc = tile[rg + 2][c], d = tile[rg + 3][c];
+      if (vt) {
+        uint2 pk;
+        pk.x = (uint32_t)f2bf(a) | ((uint32_t)f2bf(b) << 16);
+        pk.y = (uint32_t)f2bf(cc) | ((uint32_t)f2bf(d) << 16);
+        *reinterpret_cast<uint2*>(dp) = pk;
+      } else {
+        if (r0 + rg + 0 < rows) dp[0] = f2bf(a);
+        if (r0 + rg + 1 < rows) dp[1] = f2bf(b);
+        if (r0 + rg + 2 < rows) dp[2] = f2bf(cc);
+        if (r0 + rg + 3 < rows) dp[3] = f2bf(d);
+      }
+    }
+  }
+  if (colsum) {
+    __syncthreads();
+    if (t < 64 && c0 + t < cols) atomicAdd(colsum + c0 + t, cacc[t]);
+  }
+}
+
+// column sums of a bf16 matrix (bias gradient of a hidden layer from the bf16 dgrad output):
+// out[n] += sum_m X[m, n]; CTA = 64 columns x 256 rows, 4-byte loads (two columns per thread)
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const uint16_t* __restrict__ X, long long ld, int M, int N, float* __restrict__ out) {
+  __shared__ float red[8][64];
+  const int cp = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + cp * 2;
+  const int r0 = blockIdx.y * 256;
+  float s0 = 0.f, s1 = 0.f;
+  const bool pair_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(X) & 3) == 0) && (c + 1 < N);
+  for (int r = r0 + rl; r < min(M, r0 + 256); r += 8) {
+    const uint16_t* p = X + (long long)r * ld + c;
+    if (pair_ok) {
+      const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+      s0 += bf2f((uint16_t)(w & 0xFFFFu));
+      s1 += bf2f((uint16_t)(w >> 16));
+    } else {
+      if (c < N) s0 += bf2f(p[0]);
+      if (c + 1 < N) s1 += bf2f(p[1]);
+    }
+  }
+  red[rl][cp * 2] = s0;
+  red[rl][cp * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < N) atomicAdd(out + cc, s);
+  }
+}
+
 inline int grid_for(long long n, int threads = 256) {
   long long b = (n + threads - 1) / threads;
   const long long cap = (long long)kNumSMs * 8;
@@ -570,4 +684,22 @@ extern "C" int dmf_transpose_bf16(const uint16_t* src, long long lds, uint16_t* 
   dim3 block(32, 8), grid((cols + 31) / 32, (rows + 31) / 32);
   transpose_to_bf16_kernel<uint16_t><<<grid, block, 0, (cudaStream_t)s>>>(src, lds, dst, ldd, rows, cols);
   return launched("dmf_transpose_bf16");
+}
+
+extern "C" int dmf_cast_dual_bf16(const float* src, long long lds, uint16_t* dst, long long ldd, uint16_t* dst_t,
+                                  long long ldt, float* colsum, int rows, int cols, dmf_stream_t s) {
+  DMF_REQUIRE(src && (dst || dst_t || colsum) && rows >= 0 && cols >= 0, "dmf_cast_dual_bf16: bad arguments");
+  if (rows == 0 || cols == 0) return 0;
+  dim3 grid((cols + 63) / 64, (rows + 63) / 64);
+  DMF_REQUIRE(grid.y <= 65535, "dmf_cast_dual_bf16: too many rows (%d)", rows);
+  cast_dual_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(src, lds, dst, ldd, dst_t, ldt, colsum, rows, cols);
+  return launched("dmf_cast_dual_bf16");
+}
+extern "C" int dmf_colsum_bf16(const uint16_t* X, long long ld, int M, int N, float* out, dmf_stream_t s) {
+  DMF_REQUIRE(X && out && M >= 0 && N >= 0, "dmf_colsum_bf16: bad arguments");
+  if (M == 0 || N == 0) return 0;
+  dim3 grid((N + 63) / 64, (M + 255) / 256);
+  DMF_REQUIRE(grid.y <= 65535, "dmf_colsum_bf16: too many rows (%d)", M);
+  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(X, ld, M, N, out);
+  return launched("dmf_colsum_bf16");
 }

@@ -14,6 +14,7 @@
 // Ragged M/N/K are handled by TMA zero fill + masked stores.  ~131 KB smem/CTA -> 1 CTA/SM.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "gemm_tc_epi.cuh"
 
 namespace dmf {
 
@@ -23,12 +24,10 @@ constexpr int kMaxTcGroups = 8;
 constexpr size_t TC_SMEM_BYTES = 1024 /*align slack*/ + (size_t)TC_STAGES * 2 * TC_TILE_BYTES + 256;
 
 struct TcGroup {
-  float* out_f32; long long ldo_f32;
-  uint16_t* out_bf16; long long ldo_bf16;
-  const float* bias;
-  const uint16_t* mask; long long ldmask;
-  int M, N, K;
+  TcEpi epi;
+  int K;
 };
+int launch_gemm_tc2(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, cudaStream_t st);  // gemm_tc2.cu
 struct alignas(64) TcGemmParams {
   CUtensorMap tmA[kMaxTcGroups];
   CUtensorMap tmB[kMaxTcGroups];
@@ -55,7 +54,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ TcGemmParams P) {
   while (gi + 1 < P.n && tile >= P.tile_start[gi + 1]) ++gi;
   const TcGroup& g = P.g[gi];
   const int lt = tile - P.tile_start[gi];
-  const int tiles_n = (g.N + TC_BN - 1) / TC_BN;
+  const int tiles_n = (g.epi.N + TC_BN - 1) / TC_BN;
   const int tm = lt / tiles_n, tn = lt - tm * tiles_n;
   const int m0 = tm * TC_BM, n0 = tn * TC_BN;
   const int num_kb = (g.K + TC_BK - 1) / TC_BK;
@@ -119,52 +118,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ TcGemmParams P) {
       uint32_t r[32];
       tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
       tc::tmem_ld_wait();
-      const int nbase = n0 + c * 32;
-      if (row < g.M && nbase < g.N) {
-        const int nvalid = min(32, g.N - nbase);
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          if (EPI == DMF_EPI_BIAS || EPI == DMF_EPI_BIAS_RELU) {
-            if (g.bias && j < nvalid) x += __ldg(g.bias + nbase + j);
-          }
-          if (EPI == DMF_EPI_BIAS_RELU) x = fmaxf(x, 0.f);
-          v[j] = x;
-        }
-        if (EPI == DMF_EPI_RELU_MASK) {
-          const uint16_t* mk = g.mask + (long long)row * g.ldmask + nbase;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid && !(bf2f(mk[j]) > 0.f)) v[j] = 0.f;
-        }
-        if (g.out_f32) {
-          float* dst = g.out_f32 + (long long)row * g.ldo_f32 + nbase;
-          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < nvalid; ++j) dst[j] = v[j];
-          }
-        }
-        if (g.out_bf16) {
-          uint16_t* dst = g.out_bf16 + (long long)row * g.ldo_bf16 + nbase;
-          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              pk.x = (uint32_t)f2bf(v[j]) | ((uint32_t)f2bf(v[j + 1]) << 16);
-              pk.y = (uint32_t)f2bf(v[j + 2]) | ((uint32_t)f2bf(v[j + 3]) << 16);
-              pk.z = (uint32_t)f2bf(v[j + 4]) | ((uint32_t)f2bf(v[j + 5]) << 16);
-              pk.w = (uint32_t)f2bf(v[j + 6]) | ((uint32_t)f2bf(v[j + 7]) << 16);
-              *reinterpret_cast<uint4*>(dst + j) = pk;
-            }
-          } else {
-            for (int j = 0; j < nvalid; ++j) dst[j] = f2bf(v[j]);
-          }
-        }
-      }
+      tc_epilogue_chunk<EPI, false>(g.epi, r, row, n0 + c * 32, true);
     }
   }
   tc::tc_fence_before_sync();
@@ -223,6 +177,17 @@ static int launch_tc(const TcGemmParams& P, int tiles, cudaStream_t st) {
 
 extern "C" int dmf_grouped_gemm_bf16_tc(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, dmf_stream_t s) {
   DMF_REQUIRE(groups && n_groups >= 1, "dmf_grouped_gemm_bf16_tc: no groups");
+  // validate, then route: CTA-pair persistent kernel when every group can feed 256-row x 256-col tiles
+  bool pair_ok = true;
+  for (int i = 0; i < n_groups; ++i) {
+    const dmf_tc_gemm_desc& d = groups[i];
+    DMF_REQUIRE(d.M >= 0 && d.N >= 0 && d.K >= 1, "dmf_grouped_gemm_bf16_tc: bad dims in group %d", i);
+    if (d.M == 0 || d.N == 0) continue;
+    DMF_REQUIRE(d.A && d.B && (d.out_f32 || d.out_bf16 || d.out_bf16_t), "dmf_grouped_gemm_bf16_tc: null pointer in group %d", i);
+    DMF_REQUIRE(epilogue != DMF_EPI_RELU_MASK || d.mask_bf16, "dmf_grouped_gemm_bf16_tc: RELU_MASK needs mask (group %d)", i);
+    if (d.M < 512 || d.N < 128) pair_ok = false;
+  }
+  if (pair_ok) return launch_gemm_tc2(groups, n_groups, epilogue, (cudaStream_t)s);
   for (int base = 0; base < n_groups; base += kMaxTcGroups) {
     TcGemmParams P;
     P.n = 0;
@@ -239,10 +204,11 @@ extern "C" int dmf_grouped_gemm_bf16_tc(const dmf_tc_gemm_desc* groups, int n_gr
       rc = make_tmap_bf16_2d(&P.tmB[P.n], d.B, d.N, d.K, d.ldb, TC_BN);
       if (rc) return rc;
       TcGroup& g = P.g[P.n];
-      g.out_f32 = d.out_f32; g.ldo_f32 = d.ldo_f32;
-      g.out_bf16 = d.out_bf16; g.ldo_bf16 = d.ldo_bf16;
-      g.bias = d.bias; g.mask = d.mask_bf16; g.ldmask = d.ldmask;
-      g.M = d.M; g.N = d.N; g.K = d.K;
+      g.epi.out_f32 = d.out_f32; g.epi.ldo_f32 = d.ldo_f32;
+      g.epi.out_bf16 = d.out_bf16; g.epi.ldo_bf16 = d.ldo_bf16;
+      g.epi.out_t = d.out_bf16_t; g.epi.ldo_t = d.ldo_t;
+      g.epi.bias = d.bias; g.epi.mask = d.mask_bf16; g.epi.ldmask = d.ldmask;
+      g.epi.M = d.M; g.epi.N = d.N; g.K = d.K;
       P.tile_start[P.n] = tiles;
       tiles += ((d.M + TC_BM - 1) / TC_BM) * ((d.N + TC_BN - 1) / TC_BN);
       ++P.n;

@@ -1,0 +1,261 @@
+// K1, CTA-pair generation: persistent grouped  C = epi(A * B^T)  with tcgen05.mma.cta_group::2.
+//
+// Replaces the cuBLAS addmm/mm chain of Linear.forward (models/classifiers.py:43-48) and the mm pairs that
+// autograd runs for it in backward, for ALL groups (modalities x {orig, augmented} streams) of one MLP layer
+// in one launch.  Both operands K-major bf16 in global memory (A [M,K], B [N,K]).
+//
+// One cluster = 2 CTAs = one 256 x 256 output tile at a time (M split 128/128 across the pair, each CTA
+// stages HALF of the B tile: 64 B/clk of smem operand traffic per CTA instead of 128).  Clusters are
+// persistent: work items (group, tile_m, tile_n, k_split) are dealt round-robin, tile_n fastest so that
+// concurrently running clusters share A rows in L2.  Per CTA:
+//   warp 0     TMA producer: 6-stage ring of {A 128x64, B-half 128x64} bf16 tiles (128B swizzle); all loads
+//              complete on the LEADER's full barrier
+//   warp 1     (leader only) MMA issuer: 4 x tcgen05.mma 256x256x16 per stage, commit -> empty barrier of
+//              both CTAs; accumulators DOUBLE-BUFFERED in TMEM (2 x 256 columns) so the epilogue of item i
+//              overlaps the main loop of item i+1
+//   warps 2-9  epilogue: tcgen05.ld (lane quarter x column half), bias / ReLU / ReLU-mask, fp32 / bf16 /
+//              transposed-bf16 stores; split-K items accumulate with red.global.add.v4.f32
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_pair.cuh"
+#include "gemm_tc_epi.cuh"
+
+namespace dmf {
+
+constexpr int G2_THREADS = 320;
+constexpr int G2_TILE = 128 * 64 * 2;   // 16 KB
+constexpr int G2_STAGES = 6;
+constexpr int G2_BN = 256;
+constexpr int kMaxG2Groups = 8;
+constexpr size_t G2_SMEM_BYTES = 1024 + (size_t)G2_STAGES * 2 * G2_TILE + 512;
+
+struct G2Group {
+  TcEpi epi;
+  int K;
+  int tiles_n, splits, kb_per_split, num_kb;
+  int item_start;
+};
+struct alignas(64) G2Params {
+  CUtensorMap tmA[kMaxG2Groups];
+  CUtensorMap tmB[kMaxG2Groups];
+  G2Group g[kMaxG2Groups];
+  int n;
+  int total_items;
+};
+
+struct G2Item {
+  int gi, m0, n0, kb0, kb1, ks;
+};
+
+__device__ __forceinline__ G2Item g2_decode(const G2Params& P, int item) {
+  int gi = 0;
+  while (gi + 1 < P.n && item >= P.g[gi + 1].item_start) ++gi;
+  const G2Group& g = P.g[gi];
+  int lt = item - g.item_start;
+  const int per_m = g.tiles_n * g.splits;
+  const int tm = lt / per_m;
+  lt -= tm * per_m;
+  const int ks = lt / g.tiles_n;
+  const int tn = lt - ks * g.tiles_n;
+  G2Item it;
+  it.gi = gi;
+  it.m0 = tm * 256;
+  it.n0 = tn * G2_BN;
+  it.ks = ks;
+  it.kb0 = ks * g.kb_per_split;
+  it.kb1 = min(g.num_kb, it.kb0 + g.kb_per_split);
+  return it;
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + G2_STAGES * G2_TILE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * G2_STAGES * G2_TILE);
+  uint64_t* empty_bar = full_bar + G2_STAGES;
+  uint64_t* acc_full = empty_bar + G2_STAGES;   // [2] per CTA (multicast commit)
+  uint64_t* acc_empty = acc_full + 2;           // [2] leader: 16 epilogue warps of the pair drained the buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc2::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < P.n; ++i) {
+      tc::tma_prefetch_desc(&P.tmA[i]);
+      tc::tma_prefetch_desc(&P.tmB[i]);
+    }
+    for (int s = 0; s < G2_STAGES; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(acc_full + b, 1); tc::mbar_init(acc_empty + b, 16); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc2::tmem_alloc2<512>(tmem_slot);
+  tc::tc_fence_before_sync();
+  tc2::cluster_sync_all();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < P.total_items; item += num_clusters) {
+        const G2Item it = g2_decode(P, item);
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          tc::mbar_wait(empty_bar + stage, phase ^ 1);
+          if (leader) tc::mbar_expect_tx(full_bar + stage, 4 * G2_TILE);      // A + B-half of BOTH CTAs
+          tc2::tma_load_2d_pair(smemA + stage * G2_TILE, &P.tmA[it.gi], kb * 64, it.m0 + (int)rank * 128, full_bar + stage);
+          tc2::tma_load_2d_pair(smemB + stage * G2_TILE, &P.tmB[it.gi], kb * 64, it.n0 + (int)rank * 128, full_bar + stage);
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(256, G2_BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t n = 0;
+      for (int item = cluster_id; item < P.total_items; item += num_clusters, ++n) {
+        const G2Item it = g2_decode(P, item);
+        const uint32_t buf = n & 1;
+        tc::mbar_wait(acc_empty + buf, ((n >> 1) & 1) ^ 1);
+        tc::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * G2_BN;
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          tc::mbar_wait(full_bar + stage, phase);
+          tc::tc_fence_after_sync();
+          const uint32_t a_addr = tc::smem_u32(smemA + stage * G2_TILE);
+          const uint32_t b_addr = tc::smem_u32(smemB + stage * G2_TILE);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc2::umma_ss2(d_tmem, tc::make_smem_desc(a_addr + k * 32, 16, 1024),
+                          tc::make_smem_desc(b_addr + k * 32, 16, 1024), idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+          tc2::umma_commit2(empty_bar + stage);
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc2::umma_commit2(acc_full + buf);
+      }
+    }
+  } else {
+    const int q = warp & 3;                  // TMEM lane quarter
+    const int ch = (warp - 2) >> 2;          // column half (128 columns) of the 256-wide tile
+    const uint32_t acc_empty_leader = tc2::mapa(tc::smem_u32(acc_empty), 0);
+    uint32_t n = 0;
+    for (int item = cluster_id; item < P.total_items; item += num_clusters, ++n) {
+      const G2Item it = g2_decode(P, item);
+      const G2Group& g = P.g[it.gi];
+      const uint32_t buf = n & 1;
+      const int row = it.m0 + (int)rank * 128 + q * 32 + lane;
+      tc::mbar_wait(acc_full + buf, (n >> 1) & 1);
+      tc::tc_fence_after_sync();
+      if (it.kb1 > it.kb0) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * G2_BN + (uint32_t)(ch * 128 + c * 32), r);
+          tc::tmem_ld_wait();
+          const int nbase = it.n0 + ch * 128 + c * 32;
+          if (g.splits > 1) tc_epilogue_chunk<EPI, true>(g.epi, r, row, nbase, it.ks == 0);
+          else tc_epilogue_chunk<EPI, false>(g.epi, r, row, nbase, true);
+        }
+      }
+      tc::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc2::mbar_arrive_cluster(acc_empty_leader + buf * 8);
+    }
+  }
+  __syncwarp();
+  tc::tc_fence_before_sync();
+  tc2::cluster_sync_all();          // the peer may still target this CTA's barriers / TMEM until here
+  if (warp == 1) tc2::tmem_dealloc2<512>(tmem_base);
+}
+
+template <int EPI>
+static int launch_g2(const G2Params& P, int clusters, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)G2_SMEM_BYTES);
+    if (e != cudaSuccess) return fail((int)e, "gemm_bf16_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  gemm_bf16_tc2_kernel<EPI><<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, st>>>(P);
+  return launched("dmf_grouped_gemm_bf16_tc(pair)");
+}
+
+// Host entry used by dmf_grouped_gemm_bf16_tc for groups large enough to feed CTA pairs.
+int launch_gemm_tc2(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, cudaStream_t st) {
+  constexpr int kClusters = kNumSMs / 2;
+  for (int base = 0; base < n_groups; base += kMaxG2Groups) {
+    G2Params P;
+    P.n = 0;
+    int items = 0, tiles_total = 0;
+    const int cnt = n_groups - base < kMaxG2Groups ? n_groups - base : kMaxG2Groups;
+    for (int i = 0; i < cnt; ++i) {
+      const dmf_tc_gemm_desc& d = groups[base + i];
+      if (d.M == 0 || d.N == 0) continue;
+      tiles_total += ((d.M + 255) / 256) * ((d.N + G2_BN - 1) / G2_BN);
+    }
+    for (int i = 0; i < cnt; ++i) {
+      const dmf_tc_gemm_desc& d = groups[base + i];
+      if (d.M == 0 || d.N == 0) continue;
+      int rc = make_tmap_bf16_2d(&P.tmA[P.n], d.A, d.M, d.K, d.lda, 128);
+      if (rc) return rc;
+      rc = make_tmap_bf16_2d(&P.tmB[P.n], d.B, d.N, d.K, d.ldb, 128);
+      if (rc) return rc;
+      G2Group& g = P.g[P.n];
+      g.epi.out_f32 = d.out_f32; g.epi.ldo_f32 = d.ldo_f32;
+      g.epi.out_bf16 = d.out_bf16; g.epi.ldo_bf16 = d.ldo_bf16;
+      g.epi.out_t = d.out_bf16_t; g.epi.ldo_t = d.ldo_t;
+      g.epi.bias = d.bias; g.epi.mask = d.mask_bf16; g.epi.ldmask = d.ldmask;
+      g.epi.M = d.M; g.epi.N = d.N;
+      g.K = d.K;
+      g.num_kb = (d.K + 63) / 64;
+      g.tiles_n = (d.N + G2_BN - 1) / G2_BN;
+      const int tiles = ((d.M + 255) / 256) * g.tiles_n;
+      // split-K: only for plain fp32 accumulation (wgrad: tiny output, K = batch); the caller zeroes out_f32
+      int splits = 1;
+      if (d.split_k != 1 && epilogue == DMF_EPI_NONE && d.out_f32 && !d.out_bf16 && !d.out_bf16_t) {
+        const int max_splits = g.num_kb / 8 > 0 ? (g.num_kb / 8 < 64 ? g.num_kb / 8 : 64) : 1;
+        if (d.split_k > 1) {
+          splits = d.split_k < max_splits ? d.split_k : max_splits;
+        } else {
+          // smallest split count whose item total fills whole waves of the 74 clusters to >= 95 %
+          double best = 0.0;
+          for (int sp = 1; sp <= max_splits; ++sp) {
+            const int it = tiles_total * sp;
+            const double eff = (double)it / (double)(((it + kClusters - 1) / kClusters) * kClusters);
+            if (eff > best + 1e-9) { best = eff; splits = sp; }
+            if (eff >= 0.95) break;
+          }
+        }
+      }
+      g.kb_per_split = (g.num_kb + splits - 1) / splits;
+      g.splits = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;
+      g.item_start = items;
+      items += tiles * g.splits;
+      ++P.n;
+    }
+    if (P.n == 0) continue;
+    P.total_items = items;
+    const int clusters = items < kClusters ? items : kClusters;
+    int rc;
+    switch (epilogue) {
+      case DMF_EPI_NONE: rc = launch_g2<DMF_EPI_NONE>(P, clusters, st); break;
+      case DMF_EPI_BIAS: rc = launch_g2<DMF_EPI_BIAS>(P, clusters, st); break;
+      case DMF_EPI_BIAS_RELU: rc = launch_g2<DMF_EPI_BIAS_RELU>(P, clusters, st); break;
+      case DMF_EPI_RELU_MASK: rc = launch_g2<DMF_EPI_RELU_MASK>(P, clusters, st); break;
+      default: return fail(-1, "dmf_grouped_gemm_bf16_tc: unsupported epilogue %d", epilogue);
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace dmf

@@ -80,19 +80,30 @@ class DisentangledSSL(LightningModule):
         [rows, d + D] concat buffers that feed both the shared (K = d) and the private (K = d + D) MLP."""
         D = self.embed_dim
         if self.precision == "bf16":
-            bufs = []
+            need_t = torch.is_grad_enabled()
+            bufs, bufTs, dims = [], [], []
             for parts in (rows1, rows2):
                 d = parts[0].shape[1]
                 n = sum(p.shape[0] for p in parts)
+                npad = (n + 7) // 8 * 8
                 buf = torch.empty(n, d + D, dtype=torch.bfloat16, device=parts[0].device)
+                bufT = torch.empty(d + D, npad, dtype=torch.bfloat16, device=parts[0].device) if need_t else None
                 o = 0
                 for p in parts:
-                    ops.cast_bf16(p.contiguous(), buf[o:], d + D)
+                    ops.cast_dual_bf16(p, buf[o:], d + D, bufT[:, o:] if need_t else None, npad)
                     o += p.shape[0]
                 bufs.append(buf)
-            ins = [bufs[0][:, :rows1[0].shape[1]], bufs[1][:, :rows2[0].shape[1]]]
-            E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="bf16")
-            P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], bufs, extras=[E1, E2], precision="bf16")
+                bufTs.append(bufT)
+                dims.append(d)
+            ins = [bufs[0][:, :dims[0]], bufs[1][:, :dims[1]]]
+            # the shared encoders' last GEMM also writes bf16(E) (and its transpose) straight into the tail
+            # columns of the concat buffers that feed the private encoders: no cat, no cast, no transpose pass
+            o1 = dict(xTs=[bufTs[0][:dims[0]], bufTs[1][:dims[1]]] if need_t else None,
+                      out_bf16=[bufs[0][:, dims[0]:], bufs[1][:, dims[1]:]],
+                      out_bf16T=[bufTs[0][dims[0]:], bufTs[1][dims[1]:]] if need_t else None)
+            E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="bf16", opts=o1)
+            o2 = dict(xTs=list(bufTs) if need_t else None, extras_prefilled=True)
+            P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], bufs, extras=[E1, E2], precision="bf16", opts=o2)
         else:
             ins = [torch.cat(rows1, 0) if len(rows1) > 1 else rows1[0], torch.cat(rows2, 0) if len(rows2) > 1 else rows2[0]]
             E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="fp32")

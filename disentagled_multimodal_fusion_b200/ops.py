@@ -90,6 +90,8 @@ def gemm_tc(descs: Sequence[dict], epilogue: int) -> None:
         g.bias = ptr(d.get("bias"))
         g.mask_bf16, g.ldmask = ptr(d.get("mask")), d.get("ldmask", 0)
         g.M, g.N, g.K = d["M"], d["N"], d["K"]
+        g.out_bf16_t, g.ldo_t = ptr(d.get("out_t")), d.get("ldo_t", 0)
+        g.split_k = d.get("split_k", 1)
     check(lib.dmf_grouped_gemm_bf16_tc(arr, len(descs), epilogue, stream()))
 
 
@@ -100,6 +102,16 @@ def cast_bf16(src: Tensor, dst: Optional[Tensor] = None, ldd: Optional[int] = No
         dst = torch.empty(R, Cc, dtype=torch.bfloat16, device=src.device)
     check(lib.dmf_cast_f32_to_bf16(ptr(src), src.stride(0), ptr(dst), ldd or dst.stride(0), R, Cc, stream()))
     return dst
+
+
+def cast_dual_bf16(src: Tensor, dst: Optional[Tensor], ldd: int, dstT: Optional[Tensor], ldt: int,
+                   colsum_out: Optional[Tensor] = None) -> None:
+    """One pass over fp32 ``src`` [R,C]: bf16 copy into ``dst`` (row pitch ldd), transposed bf16 copy into
+    ``dstT`` (row pitch ldt) and optionally column sums accumulated into ``colsum_out`` (caller zeroes)."""
+    L.require_device()
+    src = _f32c(src)
+    R, Cc = src.shape
+    check(lib.dmf_cast_dual_bf16(ptr(src), src.stride(0), ptr(dst), ldd, ptr(dstT), ldt, ptr(colsum_out), R, Cc, stream()))
 
 
 def cast_transpose_bf16(src: Tensor) -> Tensor:
@@ -152,7 +164,7 @@ class _GroupedMLP(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, *tensors):
         L.require_device()
-        G, NL, final, precision, masks = cfg
+        G, NL, final, precision, masks, opts = cfg
         xs = [t for t in tensors[:G]]
         extras = [t for t in tensors[G:2 * G]]
         o = 2 * G
@@ -164,7 +176,7 @@ class _GroupedMLP(torch.autograd.Function):
         ctx.extra_needs_grad = [e is not None and bool(e.requires_grad) for e in extras]
         with _Prof("mlp_fwd"):
             if precision == "bf16":
-                outs, saved = _GroupedMLP._fwd_bf16(xs, extras, Ws, bs, G, NL, final)
+                outs, saved = _GroupedMLP._fwd_bf16(xs, extras, Ws, bs, G, NL, final, opts or {})
             else:
                 xs = [x if e is None else torch.cat([_f32c(x), _f32c(e)], dim=1) for x, e in zip(xs, extras)]
                 outs, saved = _GroupedMLP._fwd_f32(xs, Ws, bs, G, NL, final, masks)
@@ -205,7 +217,7 @@ class _GroupedMLP(torch.autograd.Function):
 
     @staticmethod
     def _bwd_f32(ctx, grads):
-        G, NL, final, precision, masks = ctx.cfg
+        G, NL, final, precision, masks, opts = ctx.cfg
         acts, pre = ctx.saved["acts"], ctx.saved["pre"]
         Ws = ctx.Ws
         dev = acts[0][0].device
@@ -270,33 +282,46 @@ class _GroupedMLP(torch.autograd.Function):
         return dxs, dWs, dbs
 
     # ---------------- bf16 tensor-core path
+    # Every activation / gradient that a later wgrad needs as a K-major operand (K = batch) is written
+    # TRANSPOSED by the epilogue of the GEMM that produces it (out_t), so no transpose pass runs over them.
     @staticmethod
-    def _fwd_bf16(xs, extras, Ws, bs, G, NL, final):
+    def _fwd_bf16(xs, extras, Ws, bs, G, NL, final, opts):
         if final == "evidence":
             raise L.DmfError("bf16 grouped MLP: evidence epilogue is only built for the fp32 path")
         dev = xs[0].device
-        a0 = []
-        for x, ex in zip(xs, extras):
+        need_t = torch.is_grad_enabled() and any(w.requires_grad for ws in Ws for w in ws)
+        xTs = opts.get("xTs") or [None] * G
+        out_b = opts.get("out_bf16") or [None] * G
+        out_bt = opts.get("out_bf16T") or [None] * G
+        a0, a0T = [], []
+        for g, (x, ex) in enumerate(zip(xs, extras)):
             if ex is not None:
-                # x is a bf16 buffer [M, d + De] whose first d columns are filled; append bf16(extra)
+                # x is a bf16 buffer [M, d + De] whose first d columns are filled; the tail columns hold
+                # bf16(extra) -- either written already by the producing GEMM's epilogue or cast here
                 De = ex.shape[1]
                 if x.dtype != torch.bfloat16 or x.shape[1] < De:
                     raise L.DmfError("bf16 grouped MLP: with `extra`, pass the pre-cast bf16 concat buffer as x")
-                d0 = x.shape[1] - De
-                exc = _f32c(ex)
-                check(lib.dmf_cast_f32_to_bf16(ptr(exc), De, x.data_ptr() + 2 * d0, x.stride(0), x.shape[0], De, stream()))
+                if not opts.get("extras_prefilled", False):
+                    d0 = x.shape[1] - De
+                    exc = _f32c(ex)
+                    check(lib.dmf_cast_f32_to_bf16(ptr(exc), De, x.data_ptr() + 2 * d0, x.stride(0), x.shape[0], De, stream()))
+                    xTs[g] = None
                 a0.append(x)
+                a0T.append(xTs[g])
             elif x.dtype == torch.bfloat16:
                 a0.append(x)
+                a0T.append(xTs[g])
             else:
                 x = _f32c(x)
-                K = x.shape[1]
-                Kp = (K + 7) // 8 * 8
-                buf = torch.zeros(x.shape[0], Kp, dtype=torch.bfloat16, device=dev) if Kp != K else \
-                    torch.empty(x.shape[0], K, dtype=torch.bfloat16, device=dev)
-                cast_bf16(x, buf, Kp)
+                M, K = x.shape
+                Kp, Mp = (K + 7) // 8 * 8, (M + 7) // 8 * 8
+                buf = torch.empty(M, Kp, dtype=torch.bfloat16, device=dev)
+                bufT = torch.empty(K, Mp, dtype=torch.bfloat16, device=dev) if need_t else None
+                check(lib.dmf_cast_dual_bf16(ptr(x), x.stride(0), ptr(buf), Kp, ptr(bufT), Mp, 0, M, K, stream()))
                 a0.append(buf[:, :K] if Kp != K else buf)
+                a0T.append(bufT)
         acts = [[a] for a in a0]
+        actTs = [[t] for t in a0T]
         Wb = [[None] * NL for _ in range(G)]
         outs = []
         for l in range(NL):
@@ -307,97 +332,114 @@ class _GroupedMLP(torch.autograd.Function):
                 W = Ws[g][l]
                 N, K = W.shape
                 Kp = (K + 7) // 8 * 8
-                wb = torch.zeros(N, Kp, dtype=torch.bfloat16, device=dev) if Kp != K else \
-                    torch.empty(N, K, dtype=torch.bfloat16, device=dev)
+                wb = torch.empty(N, Kp, dtype=torch.bfloat16, device=dev)
                 cast_bf16(W, wb, Kp)
                 Wb[g][l] = wb
                 M = A.shape[0]
+                Mp = (M + 7) // 8 * 8
                 d = dict(A=A, lda=A.stride(0), B=wb, ldb=Kp, bias=bs[g][l], M=M, N=N, K=K)
                 if last:
                     o = torch.empty(M, N, dtype=torch.float32, device=dev)
                     d.update(out_f32=o, ldo_f32=N)
+                    if out_b[g] is not None:
+                        d.update(out_bf16=out_b[g], ldo_bf16=out_b[g].stride(0))
+                    if out_bt[g] is not None:
+                        d.update(out_t=out_bt[g], ldo_t=out_bt[g].stride(0))
                     outs.append(o)
                 else:
                     Np = (N + 7) // 8 * 8
-                    o = torch.zeros(M, Np, dtype=torch.bfloat16, device=dev) if Np != N else \
-                        torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+                    o = torch.empty(M, Np, dtype=torch.bfloat16, device=dev)
                     d.update(out_bf16=o, ldo_bf16=Np)
                     acts[g].append(o[:, :N] if Np != N else o)
+                    if need_t:
+                        oT = torch.empty(N, Mp, dtype=torch.bfloat16, device=dev)
+                        d.update(out_t=oT, ldo_t=Mp)
+                        actTs[g].append(oT)
+                    else:
+                        actTs[g].append(None)
                 descs.append(d)
             gemm_tc(descs, L.EPI_BIAS if last else L.EPI_BIAS_RELU)
-        return outs, dict(acts=acts, Wb=Wb)
+        return outs, dict(acts=acts, actTs=actTs, Wb=Wb)
 
     @staticmethod
     def _bwd_bf16(ctx, grads):
-        G, NL, final, precision, masks = ctx.cfg
-        acts = ctx.saved["acts"]
+        G, NL, final, precision, masks, opts = ctx.cfg
+        acts, actTs = ctx.saved["acts"], ctx.saved["actTs"]
         Ws = ctx.Ws
         dev = acts[0][0].device
-        dY32 = []
-        for g in range(G):
-            dy = grads[g]
-            if dy is None:
-                dy = torch.zeros(acts[g][0].shape[0], Ws[g][-1].shape[0], dtype=torch.float32, device=dev)
-            dY32.append(_f32c(dy))
         dWs = [[None] * NL for _ in range(G)]
         dbs = [[None] * NL for _ in range(G)]
         dxs = [None] * G
-        dYb = [None] * G
+        dYb, dYT = [None] * G, [None] * G
+        for g in range(G):
+            M = acts[g][0].shape[0]
+            N = Ws[g][-1].shape[0]
+            dy = grads[g]
+            if dy is None:
+                dy = torch.zeros(M, N, dtype=torch.float32, device=dev)
+            dy = _f32c(dy)
+            Np, Mp = (N + 7) // 8 * 8, (M + 7) // 8 * 8
+            b = torch.empty(M, Np, dtype=torch.bfloat16, device=dev)
+            bT = torch.empty(N, Mp, dtype=torch.bfloat16, device=dev)
+            db = torch.zeros(N, dtype=torch.float32, device=dev)
+            check(lib.dmf_cast_dual_bf16(ptr(dy), dy.stride(0), ptr(b), Np, ptr(bT), Mp, ptr(db), M, N, stream()))
+            dYb[g], dYT[g] = (b[:, :N] if Np != N else b), bT
+            dbs[g][NL - 1] = db
         for l in range(NL - 1, -1, -1):
             wdescs, ddescs = [], []
+            nextb, nextT = [None] * G, [None] * G
             next32 = [None] * G
-            nextb = [None] * G
             for g in range(G):
                 X = acts[g][l]                      # bf16 [M,K]
                 M, K = X.shape
-                N = dY32[g].shape[1]
-                dbs[g][l] = colsum(dY32[g])
-                dYT = cast_transpose_bf16(dY32[g])  # [N, Mp]
-                XT = transpose_bf16(X)              # [K, Mp]
-                dW = torch.empty(N, K, dtype=torch.float32, device=dev)
-                wdescs.append(dict(A=dYT, lda=dYT.stride(0), B=XT, ldb=XT.stride(0), out_f32=dW, ldo_f32=K,
-                                   M=N, N=K, K=M))
+                N = dYb[g].shape[1]
+                Mp = (M + 7) // 8 * 8
+                XT = actTs[g][l]
+                if XT is None:
+                    XT = transpose_bf16(X)          # [K, Mp]
+                dW = torch.zeros(N, K, dtype=torch.float32, device=dev)
+                wdescs.append(dict(A=dYT[g], lda=dYT[g].stride(0), B=XT, ldb=XT.stride(0), out_f32=dW, ldo_f32=K,
+                                   M=N, N=K, K=M, split_k=0))
                 dWs[g][l] = dW
                 if l == 0 and not ctx.in_needs_grad[g] and ctx.extra_needs_grad[g]:
                     De = ctx.extra_cols[g]
-                    if dYb[g] is None:
-                        dYb[g] = cast_bf16(dY32[g])
-                    WT = cast_transpose_bf16(Ws[g][l][:, K - De:])      # [De, N]
+                    WT = cast_transpose_bf16(Ws[g][l][:, K - De:])      # [De, Np]
                     dX32 = torch.empty(M, De, dtype=torch.float32, device=dev)
                     ddescs.append(dict(A=dYb[g], lda=dYb[g].stride(0), B=WT, ldb=WT.stride(0), out_f32=dX32,
                                        ldo_f32=De, M=M, N=De, K=N))
                     next32[g] = dX32
                 elif l > 0 or ctx.in_needs_grad[g]:
-                    if dYb[g] is None:
-                        Np = (N + 7) // 8 * 8
-                        b = torch.zeros(M, Np, dtype=torch.bfloat16, device=dev) if Np != N else \
-                            torch.empty(M, N, dtype=torch.bfloat16, device=dev)
-                        cast_bf16(dY32[g], b, Np)
-                        dYb[g] = b[:, :N] if Np != N else b
                     WT = cast_transpose_bf16(Ws[g][l])          # [K, Np]
-                    dX32 = torch.empty(M, K, dtype=torch.float32, device=dev)
-                    d = dict(A=dYb[g], lda=dYb[g].stride(0), B=WT, ldb=WT.stride(0), out_f32=dX32, ldo_f32=K,
-                             M=M, N=K, K=N)
+                    d = dict(A=dYb[g], lda=dYb[g].stride(0), B=WT, ldb=WT.stride(0), M=M, N=K, K=N)
                     if l > 0:
                         Kp = (K + 7) // 8 * 8
-                        dXb = torch.zeros(M, Kp, dtype=torch.bfloat16, device=dev) if Kp != K else \
-                            torch.empty(M, K, dtype=torch.bfloat16, device=dev)
-                        d.update(out_bf16=dXb, ldo_bf16=Kp, mask=X, ldmask=X.stride(0))
+                        dXb = torch.empty(M, Kp, dtype=torch.bfloat16, device=dev)
+                        dXT = torch.empty(K, Mp, dtype=torch.bfloat16, device=dev)
+                        d.update(out_bf16=dXb, ldo_bf16=Kp, out_t=dXT, ldo_t=Mp, mask=X, ldmask=X.stride(0))
                         nextb[g] = dXb[:, :K] if Kp != K else dXb
+                        nextT[g] = dXT
+                    else:
+                        dX32 = torch.empty(M, K, dtype=torch.float32, device=dev)
+                        d.update(out_f32=dX32, ldo_f32=K)
+                        next32[g] = dX32
                     ddescs.append(d)
-                    next32[g] = dX32
             gemm_tc(wdescs, L.EPI_NONE)
             if ddescs:
                 gemm_tc(ddescs, L.EPI_RELU_MASK if l > 0 else L.EPI_NONE)
             if l == 0:
                 dxs = next32
             else:
-                dY32, dYb = next32, nextb
+                for g in range(G):
+                    K = nextb[g].shape[1]
+                    db = torch.zeros(K, dtype=torch.float32, device=dev)
+                    check(lib.dmf_colsum_bf16(ptr(nextb[g]), nextb[g].stride(0), nextb[g].shape[0], K, ptr(db), stream()))
+                    dbs[g][l - 1] = db
+                dYb, dYT = nextb, nextT
         return dxs, dWs, dbs
 
     @staticmethod
     def backward(ctx, *grads):
-        G, NL, final, precision, masks = ctx.cfg
+        G, NL, final, precision, masks, opts = ctx.cfg
         with _Prof("mlp_bwd"):
             if precision == "bf16":
                 dxs, dWs, dbs = _GroupedMLP._bwd_bf16(ctx, grads)
@@ -414,18 +456,22 @@ class _GroupedMLP(torch.autograd.Function):
 
 
 def grouped_mlp(xs: Sequence[Tensor], weights: Sequence[Sequence[Tensor]], biases: Sequence[Sequence[Tensor]],
-                final: str = "none", precision: str = "fp32", dropout_masks=None, extras=None) -> List[Tensor]:
+                final: str = "none", precision: str = "fp32", dropout_masks=None, extras=None, opts=None) -> List[Tensor]:
     """Apply G independent MLPs (Linear->ReLU)*(L-1)->Linear in L launches.  ``weights[g]`` /
     ``biases[g]`` list the L layers of group g (nn.Linear layout [out,in]).  ``extras[g]`` (optional)
     is appended column-wise to input g (torch.cat([x, extra], 1) semantics; fp32 path concatenates,
-    bf16 path expects x to be the pre-cast bf16 concat buffer)."""
+    bf16 path expects x to be the pre-cast bf16 concat buffer).  ``opts`` (bf16 path only): ``xTs`` = transposed
+    bf16 copies [K0, Mp] of the inputs (K-major operand of the layer-0 wgrad), ``out_bf16`` / ``out_bf16T`` =
+    per-group destinations (views into a later concat buffer) that also receive bf16 / transposed-bf16 copies
+    of the final output from the last GEMM's epilogue, ``extras_prefilled`` = the tail columns of x already
+    hold bf16(extra)."""
     G, NL = len(xs), len(weights[0])
     flat = list(xs) + (list(extras) if extras is not None else [None] * G)
     for g in range(G):
         flat += list(weights[g])
     for g in range(G):
         flat += list(biases[g])
-    return list(_GroupedMLP.apply((G, NL, final, precision, dropout_masks), *flat))
+    return list(_GroupedMLP.apply((G, NL, final, precision, dropout_masks, opts), *flat))
 
 
 # ----------------------------------------------------------------------------------------

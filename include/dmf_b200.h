@@ -71,7 +71,9 @@ int dmf_grouped_gemm_f32(const dmf_gemm_desc* groups, int n_groups, int epilogue
 /* bf16 tensor-core path: tcgen05.mma (kind::f16, fp32 accumulate in TMEM), operands staged by
  * TMA (128B swizzle).  Both operands K-major: A [M,K] bf16 (lda), B [N,K] bf16 (ldb):
  * C[M,N] = epi(A * B^T).  K*2 bytes and lda/ldb*2 bytes must be multiples of 16; pointers 16B
- * aligned.  out_f32 / out_bf16 may each be NULL (at least one non-NULL).                      */
+ * aligned.  out_f32 / out_bf16 / out_bf16_t may each be NULL (at least one non-NULL).
+ * Groups with M >= 512 and N >= 128 run on the persistent CTA-pair kernel (cta_group::2, 256x256 tiles,
+ * double-buffered TMEM accumulators); smaller ones on the single-CTA 128x128 kernel.                */
 typedef struct {
   const uint16_t* A; long long lda;
   const uint16_t* B; long long ldb;
@@ -80,6 +82,10 @@ typedef struct {
   const float* bias;                 /* [N] or NULL */
   const uint16_t* mask_bf16; long long ldmask; /* DMF_EPI_RELU_MASK: zero where mask<=0 */
   int M, N, K;
+  uint16_t* out_bf16_t; long long ldo_t;       /* optional TRANSPOSED bf16 copy: out_bf16_t[n*ldo_t + m] */
+  int split_k;  /* 0 = auto, 1 = never, >1 = that many K splits.  Splitting applies only to DMF_EPI_NONE with
+                   out_f32 alone (wgrad: K = batch); partial tiles are accumulated with red.add, so the
+                   CALLER must zero out_f32 first */
 } dmf_tc_gemm_desc;
 int dmf_grouped_gemm_bf16_tc(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, dmf_stream_t s);
 
@@ -91,6 +97,13 @@ int dmf_colsum_f32(const float* X, long long ld, int M, int N, float* out, int a
 int dmf_cast_f32_to_bf16(const float* src, long long lds, uint16_t* dst, long long ldd, int rows, int cols, dmf_stream_t s);
 int dmf_cast_transpose_f32_to_bf16(const float* src, long long lds, uint16_t* dst, long long ldd, int rows, int cols, dmf_stream_t s);
 int dmf_transpose_bf16(const uint16_t* src, long long lds, uint16_t* dst, long long ldd, int rows, int cols, dmf_stream_t s);
+/* one pass over fp32 src [rows, cols]: dst[r*ldd + c] (bf16, may be NULL), dst_t[c*ldt + r] (bf16 transposed,
+ * may be NULL: the K-major operand of the next wgrad GEMM) and colsum[c] += sum_r src (may be NULL; caller
+ * zeroes; the bias gradient).                                                                              */
+int dmf_cast_dual_bf16(const float* src, long long lds, uint16_t* dst, long long ldd, uint16_t* dst_t, long long ldt,
+                       float* colsum, int rows, int cols, dmf_stream_t s);
+/* out[n] += sum_m X[m*ld + n] for a bf16 matrix (bias gradient from the bf16 dgrad output; caller zeroes) */
+int dmf_colsum_bf16(const uint16_t* X, long long ld, int M, int N, float* out, dmf_stream_t s);
 
 /* ------------------------------------------------------------------ K2 fused InfoNCE
  * Replaces matmul/div/max/sub/exp/sum/log/mean of SupConLoss.forward (models/losses.py:64-99)

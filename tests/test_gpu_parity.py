@@ -191,6 +191,108 @@ def test_tc_gemm(dmf, M, N, K):
     assert_close(outb[:, :N].float(), ref, 1e-2, "tc gemm bf16 out")
 
 
+@pytest.mark.parametrize("M,N,K,epi", [(1024, 512, 512, "bias_relu"), (1000, 384, 200, "bias_relu"), (777, 136, 1096, "bias"),
+                                       (5000, 512, 1536, "mask")])
+def test_tc_gemm_pair_kernel(dmf, M, N, K, epi):
+    """Groups with M >= 512 and N >= 128 run on the persistent CTA-pair kernel (cta_group::2, 256x256 tiles);
+    two groups per launch, fp32 + bf16 + transposed-bf16 outputs, ragged M / N / K."""
+    ops, Lb = dmf.ops, dmf._lib
+    gen = torch.Generator().manual_seed(M + N + K)
+    Kp, Np, Mp = (K + 7) // 8 * 8, (N + 7) // 8 * 8, (M + 7) // 8 * 8
+    descs, refs, outs = [], [], []
+    for g in range(2):
+        A = torch.zeros(M, Kp); A[:, :K] = torch.randn(M, K, generator=gen)
+        W = torch.zeros(N, Kp); W[:, :K] = torch.randn(N, K, generator=gen) / K ** 0.5
+        bias = torch.randn(N, generator=gen)
+        Ab, Wb = A.to(DEV).bfloat16(), W.to(DEV).bfloat16()
+        acc = Ab.float().cpu()[:, :K] @ Wb.float().cpu()[:, :K].T
+        out = torch.full((M, N), float("nan"), device=DEV)
+        outb = torch.zeros(M, Np, dtype=torch.bfloat16, device=DEV)
+        outT = torch.zeros(N, Mp, dtype=torch.bfloat16, device=DEV)
+        d = dict(A=Ab, lda=Kp, B=Wb, ldb=Kp, out_f32=out, ldo_f32=N, out_bf16=outb, ldo_bf16=Np, out_t=outT, ldo_t=Mp,
+                 M=M, N=N, K=K)
+        if epi == "mask":
+            mk = torch.relu(torch.randn(M, Np, generator=gen)).to(DEV).bfloat16()
+            d.update(mask=mk, ldmask=Np)
+            ref = acc * (mk[:, :N].float().cpu() > 0)
+        else:
+            d.update(bias=bias.to(DEV))
+            ref = acc + bias
+            if epi == "bias_relu":
+                ref = torch.relu(ref)
+        descs.append(d); refs.append(ref); outs.append((out, outb, outT))
+    code = {"bias_relu": Lb.EPI_BIAS_RELU, "bias": Lb.EPI_BIAS, "mask": Lb.EPI_RELU_MASK}[epi]
+    ops.gemm_tc(descs, code)
+    for ref, (out, outb, outT) in zip(refs, outs):
+        assert_close(out, ref, 1e-4, "pair gemm f32 out")
+        assert_close(outb[:, :N].float(), ref, 1e-2, "pair gemm bf16 out")
+        assert_close(outT[:, :M].float().T, ref, 1e-2, "pair gemm transposed bf16 out")
+
+
+@pytest.mark.parametrize("split", [0, 1, 7])
+def test_tc_gemm_split_k(dmf, split):
+    """wgrad shape: tiny output, K = batch; split-K partial tiles accumulate with red.add into a zeroed output."""
+    ops, Lb = dmf.ops, dmf._lib
+    gen = torch.Generator().manual_seed(11 + split)
+    M, N, K = 512, 1024, 20000
+    A = (torch.randn(M, K, generator=gen) / 8).to(DEV).bfloat16()
+    Bm = (torch.randn(N, K, generator=gen) / 8).to(DEV).bfloat16()
+    ref = A.float().cpu() @ Bm.float().cpu().T
+    out = torch.zeros(M, N, device=DEV)
+    ops.gemm_tc([dict(A=A, lda=K, B=Bm, ldb=K, out_f32=out, ldo_f32=N, M=M, N=N, K=K, split_k=split)], Lb.EPI_NONE)
+    assert_close(out, ref, 1e-4, f"split-k={split}")
+
+
+def test_cast_dual_and_colsum_bf16(dmf):
+    ops, Lb = dmf.ops, dmf._lib
+    gen = torch.Generator().manual_seed(21)
+    for R, Cc in ((1000, 520), (64, 64), (333, 47)):
+        x = torch.randn(R, Cc, generator=gen).to(DEV)
+        Cp, Rp = (Cc + 7) // 8 * 8, (R + 7) // 8 * 8
+        dst = torch.zeros(R, Cp, dtype=torch.bfloat16, device=DEV)
+        dstT = torch.zeros(Cc, Rp, dtype=torch.bfloat16, device=DEV)
+        cs = torch.zeros(Cc, device=DEV)
+        ops.cast_dual_bf16(x, dst, Cp, dstT, Rp, cs)
+        ref = x.bfloat16()
+        assert torch.equal(dst[:, :Cc], ref), "bf16 copy"
+        assert torch.equal(dstT[:, :R], ref.T), "transposed bf16 copy"
+        assert_close(cs, x.sum(0), 1e-5, "column sums")
+        cs2 = torch.zeros(Cc, device=DEV)
+        Lb.check(Lb.lib.dmf_colsum_bf16(dst.data_ptr(), Cp, R, Cc, cs2.data_ptr(), Lb.stream()))
+        assert_close(cs2, ref.float().sum(0), 1e-5, "bf16 column sums")
+
+
+def test_dssl_bf16_pair_kernel_path(dmf):
+    """DSSL step large enough (2B = 1024 rows, widths >= 128) that every MLP GEMM runs on the CTA-pair kernel
+    with the fused transposed-copy epilogues and split-K wgrad; vs the fp32 path."""
+    torch.manual_seed(0)
+    dims, h, e, B = [256, 192], 128, 128, 512
+    m32 = dmf.DisentangledSSL(output_dim=dims, hidden_dim=h, embed_dim=e).to(DEV)
+    mbf = dmf.DisentangledSSL(output_dim=dims, hidden_dim=h, embed_dim=e, precision="bf16").to(DEV)
+    mbf.load_state_dict(m32.state_dict())
+    gen = torch.Generator().manual_seed(1)
+    x1, x2 = torch.randn(B, dims[0], generator=gen).to(DEV), torch.randn(B, dims[1], generator=gen).to(DEV)
+    v1, v2 = x1 + 0.01 * torch.randn_like(x1), x2 + 0.01 * torch.randn_like(x2)
+    torch.manual_seed(7)
+    noise = m32.draw_noise(B, DEV)
+    l32, logs32 = m32(x1, x2, v1, v2, noise=noise)
+    lbf, logsbf = mbf(x1, x2, v1, v2, noise=noise)
+    l32.backward()
+    lbf.backward()
+    assert_close(lbf, l32, 2e-2, "loss")
+    for k in ("shared", "specific", "ortho"):
+        assert_close(logsbf[k], logs32[k], 2e-2, k)
+    for (k, p), (_, q) in zip(mbf.named_parameters(), m32.named_parameters()):
+        cos = torch.nn.functional.cosine_similarity(p.grad.flatten(), q.grad.flatten(), dim=0)
+        assert float(cos) > 0.995, f"grad {k}: cosine {float(cos):.4f}"
+        assert_close(p.grad, q.grad, 0.25, "grad " + k)
+    es32, ep32 = m32.get_embedding([x1, x2])
+    esbf, epbf = mbf.get_embedding([x1, x2])
+    assert_close(esbf, es32, 2e-2, "shared embedding")
+    assert_close(epbf[0], ep32[0], 2e-2, "private embedding")
+
+
+
 @pytest.mark.parametrize("prec,tol", [("fp32", FP32), ("bf16", 2e-2)])
 def test_grouped_mlp_vs_torch(dmf, prec, tol):
     """Ragged groups (HandWritten-like widths), fwd + dgrad + wgrad + bias grad vs plain torch fp32."""

@@ -79,6 +79,7 @@ _SIGS = {
     "dmf_cast_dual_bf16": ([c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_i, c_i, c_p], c_i),
     "dmf_colsum_bf16": ([c_p, c_ll, c_i, c_i, c_p, c_p], c_i),
     "dmf_rowlse": ([c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_f, c_p, c_p, c_ll, c_p, c_p, c_sz, c_i, c_p], c_i),
+    "dmf_infonce_rowcol_sums": ([c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_f, c_f, c_i, c_i, c_p, c_p, c_ll, c_p, c_p], c_i),
     "dmf_rowlse_workspace_bytes": ([c_i, c_i], c_sz),
     "dmf_infonce_finalize": ([c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_f, c_i, c_p, c_p, c_p], c_i),
     "dmf_infonce_bwd": ([c_p, c_ll, c_i, c_p, c_p, c_ll, c_p, c_ll, c_i, c_p, c_i, c_f, c_f, c_p, c_ll, c_p, c_ll,

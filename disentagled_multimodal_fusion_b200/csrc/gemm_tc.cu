@@ -21,7 +21,7 @@ namespace dmf {
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 4, TC_THREADS = 192;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 2;  // 16 KB per operand tile
 constexpr int kMaxTcGroups = 8;
-constexpr size_t TC_SMEM_BYTES = 1024 /*align slack*/ + (size_t)TC_STAGES * 2 * TC_TILE_BYTES + 256;
+constexpr size_t TC_SMEM_BYTES = 1024 /*align slack*/ + (size_t)TC_STAGES * 2 * TC_TILE_BYTES + 4 * kEpiStageFloats * 4 + 256;
 
 struct TcGroup {
   TcEpi epi;
@@ -43,7 +43,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ TcGemmParams P) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + TC_STAGES * TC_TILE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * TC_STAGES * TC_TILE_BYTES);
+  float* epi_stage = reinterpret_cast<float*>(smem + 2 * TC_STAGES * TC_TILE_BYTES);   // [4 warps][32 x 36]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + 4 * kEpiStageFloats);
   uint64_t* empty_bar = full_bar + TC_STAGES;
   uint64_t* tmem_full = empty_bar + TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -110,7 +111,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ TcGemmParams P) {
     }
   } else {
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
+    const int row0 = m0 + q * 32;
+    float* my_stage = epi_stage + (warp - 2) * kEpiStageFloats;
     tc::mbar_wait(tmem_full, 0);
     tc::tc_fence_after_sync();
 #pragma unroll 1
@@ -118,7 +120,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ TcGemmParams P) {
       uint32_t r[32];
       tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
       tc::tmem_ld_wait();
-      tc_epilogue_chunk<EPI, false>(g.epi, r, row, n0 + c * 32, true);
+      tc_epilogue_chunk<EPI, false>(g.epi, r, row0, lane, n0 + c * 32, true, my_stage);
     }
   }
   tc::tc_fence_before_sync();

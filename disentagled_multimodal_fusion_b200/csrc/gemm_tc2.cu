@@ -8,7 +8,7 @@
 // stages HALF of the B tile: 64 B/clk of smem operand traffic per CTA instead of 128).  Clusters are
 // persistent: work items (group, tile_m, tile_n, k_split) are dealt round-robin, tile_n fastest so that
 // concurrently running clusters share A rows in L2.  Per CTA:
-//   warp 0     TMA producer: 6-stage ring of {A 128x64, B-half 128x64} bf16 tiles (128B swizzle); all loads
+//   warp 0     TMA producer: 5-stage ring of {A 128x64, B-half 128x64} bf16 tiles (128B swizzle); all loads
 //              complete on the LEADER's full barrier
 //   warp 1     (leader only) MMA issuer: 4 x tcgen05.mma 256x256x16 per stage, commit -> empty barrier of
 //              both CTAs; accumulators DOUBLE-BUFFERED in TMEM (2 x 256 columns) so the epilogue of item i
@@ -24,10 +24,10 @@ namespace dmf {
 
 constexpr int G2_THREADS = 320;
 constexpr int G2_TILE = 128 * 64 * 2;   // 16 KB
-constexpr int G2_STAGES = 6;
+constexpr int G2_STAGES = 5;
 constexpr int G2_BN = 256;
 constexpr int kMaxG2Groups = 8;
-constexpr size_t G2_SMEM_BYTES = 1024 + (size_t)G2_STAGES * 2 * G2_TILE + 512;
+constexpr size_t G2_SMEM_BYTES = 1024 + (size_t)G2_STAGES * 2 * G2_TILE + 8 * kEpiStageFloats * 4 + 512;
 
 struct G2Group {
   TcEpi epi;
@@ -74,7 +74,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + G2_STAGES * G2_TILE;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * G2_STAGES * G2_TILE);
+  float* epi_stage = reinterpret_cast<float*>(smem + 2 * G2_STAGES * G2_TILE);      // [8 warps][32 x 36]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + 8 * kEpiStageFloats);
   uint64_t* empty_bar = full_bar + G2_STAGES;
   uint64_t* acc_full = empty_bar + G2_STAGES;   // [2] per CTA (multicast commit)
   uint64_t* acc_empty = acc_full + 2;           // [2] leader: 16 epilogue warps of the pair drained the buffer
@@ -146,12 +147,13 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
     const int q = warp & 3;                  // TMEM lane quarter
     const int ch = (warp - 2) >> 2;          // column half (128 columns) of the 256-wide tile
     const uint32_t acc_empty_leader = tc2::mapa(tc::smem_u32(acc_empty), 0);
+    float* my_stage = epi_stage + (warp - 2) * kEpiStageFloats;
     uint32_t n = 0;
     for (int item = cluster_id; item < P.total_items; item += num_clusters, ++n) {
       const G2Item it = g2_decode(P, item);
       const G2Group& g = P.g[it.gi];
       const uint32_t buf = n & 1;
-      const int row = it.m0 + (int)rank * 128 + q * 32 + lane;
+      const int row0 = it.m0 + (int)rank * 128 + q * 32;
       tc::mbar_wait(acc_full + buf, (n >> 1) & 1);
       tc::tc_fence_after_sync();
       if (it.kb1 > it.kb0) {
@@ -161,8 +163,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
           tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * G2_BN + (uint32_t)(ch * 128 + c * 32), r);
           tc::tmem_ld_wait();
           const int nbase = it.n0 + ch * 128 + c * 32;
-          if (g.splits > 1) tc_epilogue_chunk<EPI, true>(g.epi, r, row, nbase, it.ks == 0);
-          else tc_epilogue_chunk<EPI, false>(g.epi, r, row, nbase, true);
+          if (g.splits > 1) tc_epilogue_chunk<EPI, true>(g.epi, r, row0, lane, nbase, it.ks == 0, my_stage);
+          else tc_epilogue_chunk<EPI, false>(g.epi, r, row0, lane, nbase, true, my_stage);
         }
       }
       tc::tc_fence_before_sync();

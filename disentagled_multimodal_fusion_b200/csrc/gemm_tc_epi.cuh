@@ -1,8 +1,13 @@
-// Epilogue shared by the tcgen05 GEMM kernels (gemm_tc.cu single-CTA, gemm_tc2.cu persistent CTA pair):
-// one thread owns one accumulator row and 32 consecutive columns just read from TMEM.
-//   bias / ReLU / ReLU-mask (dgrad) -> fp32 store (plain or red.add for split-K), bf16 row-major store,
-//   bf16 TRANSPOSED store (out_t[n][m]: the copy the next wgrad consumes as a K-major operand, so no
-//   separate transpose pass ever runs over the activations).
+// Epilogue shared by the tcgen05 GEMM kernels (gemm_tc.cu single-CTA, gemm_tc2.cu persistent CTA pair).
+//
+// A warp owns a 32-row x 32-column chunk of the accumulator (lane = row, as tcgen05.ld 32x32b delivers it).
+// Storing from that layout would touch 32 different cache lines per instruction, so the chunk is staged
+// through a per-warp shared-memory tile (pitch 36 words: conflict-free 128-bit stores by row and 128-bit
+// loads by quarter-warp) and written back COALESCED: lane -> (row = lane/8 + 4*it, 4 consecutive columns),
+// i.e. four full 128-byte row segments per fp32 store instruction.  Bias / ReLU / ReLU-mask (dgrad) are
+// applied in the coalesced phase (bias and mask are then read coalesced too).  Outputs:
+//   fp32 (plain, or red.global.add.v4.f32 for split-K), bf16 row-major, and a bf16 TRANSPOSED copy
+//   out_t[n][m] -- the K-major operand of the next wgrad -- so no transpose pass ever runs over activations.
 #pragma once
 #include "common.cuh"
 
@@ -17,6 +22,9 @@ struct TcEpi {
   int M, N;
 };
 
+constexpr int kEpiPitch = 36;                       // words per staged row
+constexpr int kEpiStageFloats = 32 * kEpiPitch;     // per-warp staging tile
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -27,92 +35,124 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// kAtomic: fp32 output is accumulated with red.global.add (split-K partial tiles); `add_bias` tells whether
-// this K-split owns the bias (only the first one does).
+// r[32]: this lane's row (row0 + lane) of the chunk, columns nbase .. nbase+31.  `stage` = this warp's
+// private smem tile (kEpiStageFloats floats, 16-byte aligned).  All 32 lanes must call (warp-uniform flow).
+// kAtomic: fp32 output accumulated with red.add (split-K partial tiles); add_bias: this K-split owns the bias.
 template <int EPI, bool kAtomic>
-__device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& g, const uint32_t (&r)[32], int row, int nbase,
-                                                  bool add_bias) {
-  if (row >= g.M || nbase >= g.N) return;
+__device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& g, const uint32_t (&r)[32], int row0, int lane, int nbase,
+                                                  bool add_bias, float* stage) {
+  if (row0 >= g.M || nbase >= g.N) return;          // warp-uniform
   const int nvalid = min(32, g.N - nbase);
-  float v[32];
+  const int mvalid = min(32, g.M - row0);
+  // ---- phase 1: raw accumulators -> smem, one 144-byte row per lane
+  float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiPitch);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float x = __uint_as_float(r[j]);
-    if (EPI == DMF_EPI_BIAS || EPI == DMF_EPI_BIAS_RELU) {
-      if (g.bias && add_bias && j < nvalid) x += __ldg(g.bias + nbase + j);
-    }
-    if (EPI == DMF_EPI_BIAS_RELU) x = fmaxf(x, 0.f);
-    v[j] = x;
+  for (int j = 0; j < 8; ++j)
+    srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
+  __syncwarp();
+  // ---- phase 2: coalesced pass, lane -> (row rr = lane/8 + 4*it, columns c = (lane%8)*4 .. +3)
+  const int c = (lane & 7) * 4;
+  const int rq = lane >> 3;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if ((EPI == DMF_EPI_BIAS || EPI == DMF_EPI_BIAS_RELU) && g.bias && add_bias) {
+    if (c + 0 < nvalid) b4.x = __ldg(g.bias + nbase + c + 0);
+    if (c + 1 < nvalid) b4.y = __ldg(g.bias + nbase + c + 1);
+    if (c + 2 < nvalid) b4.z = __ldg(g.bias + nbase + c + 2);
+    if (c + 3 < nvalid) b4.w = __ldg(g.bias + nbase + c + 3);
   }
-  if (EPI == DMF_EPI_RELU_MASK) {
-    const uint16_t* mk = g.mask + (long long)row * g.ldmask + nbase;
-    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(mk) & 15) == 0)) {
+  const bool full_n = nvalid == 32;
+  const bool need_back = g.out_t != nullptr && (EPI != DMF_EPI_NONE);   // T pass must see the post-epilogue values
 #pragma unroll
-      for (int j8 = 0; j8 < 4; ++j8) {
-        const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(mk) + j8);
-        const uint32_t w[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          // activation is post-ReLU bf16: positive <=> nonzero magnitude with sign bit clear
-          if (!(bf2f((uint16_t)(w[h] & 0xFFFFu)) > 0.f)) v[j8 * 8 + h * 2] = 0.f;
-          if (!(bf2f((uint16_t)(w[h] >> 16)) > 0.f)) v[j8 * 8 + h * 2 + 1] = 0.f;
+  for (int it = 0; it < 8; ++it) {
+    const int rr = rq + 4 * it;
+    float4 v = *reinterpret_cast<const float4*>(stage + rr * kEpiPitch + c);
+    if (EPI == DMF_EPI_BIAS || EPI == DMF_EPI_BIAS_RELU) { v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+    if (EPI == DMF_EPI_BIAS_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    const bool rvalid = rr < mvalid;
+    const long long grow = row0 + rr;
+    if (EPI == DMF_EPI_RELU_MASK) {
+      if (rvalid) {
+        const uint16_t* mk = g.mask + grow * g.ldmask + nbase + c;
+        if (full_n && ((reinterpret_cast<uintptr_t>(mk) & 7) == 0)) {
+          const uint2 m2 = __ldg(reinterpret_cast<const uint2*>(mk));
+          // activation is post-ReLU bf16: keep the gradient where it is strictly positive
+          if (!(bf2f((uint16_t)(m2.x & 0xFFFFu)) > 0.f)) v.x = 0.f;
+          if (!(bf2f((uint16_t)(m2.x >> 16)) > 0.f)) v.y = 0.f;
+          if (!(bf2f((uint16_t)(m2.y & 0xFFFFu)) > 0.f)) v.z = 0.f;
+          if (!(bf2f((uint16_t)(m2.y >> 16)) > 0.f)) v.w = 0.f;
+        } else {
+          if (c + 0 < nvalid && !(bf2f(mk[0]) > 0.f)) v.x = 0.f;
+          if (c + 1 < nvalid && !(bf2f(mk[1]) > 0.f)) v.y = 0.f;
+          if (c + 2 < nvalid && !(bf2f(mk[2]) > 0.f)) v.z = 0.f;
+          if (c + 3 < nvalid && !(bf2f(mk[3]) > 0.f)) v.w = 0.f;
         }
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid && !(bf2f(mk[j]) > 0.f)) v[j] = 0.f;
     }
-  }
-  if (g.out_f32) {
-    float* dst = g.out_f32 + (long long)row * g.ldo_f32 + nbase;
-    const bool vec = nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-    if (kAtomic) {
-      if (vec) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+    if (need_back) *reinterpret_cast<float4*>(stage + rr * kEpiPitch + c) = v;
+    if (rvalid && g.out_f32) {
+      float* dst = g.out_f32 + grow * g.ldo_f32 + nbase + c;
+      const bool vec = full_n && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+      if (kAtomic) {
+        if (vec) {
+          red_add_v4(dst, v.x, v.y, v.z, v.w);
+        } else {
+          if (c + 0 < nvalid) atomicAdd(dst + 0, v.x);
+          if (c + 1 < nvalid) atomicAdd(dst + 1, v.y);
+          if (c + 2 < nvalid) atomicAdd(dst + 2, v.z);
+          if (c + 3 < nvalid) atomicAdd(dst + 3, v.w);
+        }
       } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) atomicAdd(dst + j, v[j]);
+        if (vec) {
+          *reinterpret_cast<float4*>(dst) = v;
+        } else {
+          if (c + 0 < nvalid) dst[0] = v.x;
+          if (c + 1 < nvalid) dst[1] = v.y;
+          if (c + 2 < nvalid) dst[2] = v.z;
+          if (c + 3 < nvalid) dst[3] = v.w;
+        }
       }
-    } else {
-      if (vec) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    if (rvalid && g.out_bf16) {
+      uint16_t* dst = g.out_bf16 + grow * g.ldo_bf16 + nbase + c;
+      if (full_n && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+        uint2 pk;
+        pk.x = pack_bf16x2(v.x, v.y);
+        pk.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst) = pk;
       } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) dst[j] = v[j];
+        if (c + 0 < nvalid) dst[0] = f2bf(v.x);
+        if (c + 1 < nvalid) dst[1] = f2bf(v.y);
+        if (c + 2 < nvalid) dst[2] = f2bf(v.z);
+        if (c + 3 < nvalid) dst[3] = f2bf(v.w);
       }
     }
   }
-  if (g.out_bf16) {
-    uint16_t* dst = g.out_bf16 + (long long)row * g.ldo_bf16 + nbase;
-    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 pk;
-        pk.x = pack_bf16x2(v[j], v[j + 1]);
-        pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
-        pk.z = pack_bf16x2(v[j + 4], v[j + 5]);
-        pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(dst + j) = pk;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) dst[j] = f2bf(v[j]);
-    }
-  }
+  // ---- phase 3: transposed bf16 copy; lane = row again, each store instruction writes 32 consecutive
+  // bf16 (64 B) of one output row n
   if (g.out_t) {
-    // lanes of the warp hold consecutive rows: each store instruction writes 32 consecutive bf16 (64 B)
-    uint16_t* dst = g.out_t + (long long)nbase * g.ldo_t + row;
+    if (need_back) __syncwarp();
+    if (lane < mvalid) {
+      uint16_t* dst = g.out_t + (long long)nbase * g.ldo_t + row0 + lane;
+      if (need_back) {
+        const float4* sr = reinterpret_cast<const float4*>(stage + lane * kEpiPitch);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) dst[(long long)j * g.ldo_t] = f2bf(v[j]);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 q4 = sr[j4];
+          const int j = 4 * j4;
+          if (j + 0 < nvalid) dst[(long long)(j + 0) * g.ldo_t] = f2bf(q4.x);
+          if (j + 1 < nvalid) dst[(long long)(j + 1) * g.ldo_t] = f2bf(q4.y);
+          if (j + 2 < nvalid) dst[(long long)(j + 2) * g.ldo_t] = f2bf(q4.z);
+          if (j + 3 < nvalid) dst[(long long)(j + 3) * g.ldo_t] = f2bf(q4.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) dst[(long long)j * g.ldo_t] = f2bf(__uint_as_float(r[j]));
+      }
+    }
   }
+  __syncwarp();     // the staging tile is reused by the next chunk
 }
 
 }  // namespace dmf

@@ -1,0 +1,327 @@
+// K2 forward for L2-normalised embeddings: ONE pass over the similarity tiles yields both the row sums and
+// the column sums of exp(s - shift), and symmetric (intra-view) blocks are only computed on a half window.
+//
+// SupConLoss.forward (models/losses.py:64-99) needs, for the anchors of view 0, the LSE of every row of
+// S01 = z0 z1^T / T and, for the anchors of view 1, the LSE of every COLUMN of the same matrix; the no-grad
+// diagnostics need the row LSEs of the symmetric blocks S00 and S11.  DisentangledSSL feeds unit vectors
+// (vMF samples / F.normalize, models/disentangledssl.py:134-140), so |s| <= 1/T: a FIXED shift replaces the
+// online max (no rescaling, one ex2 per element) and makes column sums plain additions:
+//   row_sum[i] += sum_j e_ij      (per-thread accumulation, one atomicAdd per row and CTA)
+//   col_sum[j] += sum_i e_ij      (32x32 butterfly transpose-reduce in the warp, one 128-byte red.add per chunk)
+// with e_ij = 2^(s_ij * scale * log2e - shift2).  For a symmetric block only tiles J in the cyclic half
+// window [I, I + T/2] of row block I are visited; an off-diagonal tile feeds row sums of block I AND (as
+// column sums) the row sums of block J, the diagonal tile feeds row sums only.  Work per critic call drops
+// from four B x B blocks (rows of S01, S10, S00, S11) to two.
+//
+// CTA pair, cta_group::2, M = 256 anchor rows resident in smem, 256-column tiles through a 5-stage TMA ring,
+// S tiles double-buffered in TMEM (2 x 256 columns), 8 softmax warps per CTA -- same skeleton as
+// infonce_fwd_tc2.cu (which remains the exact online-max path for arbitrary inputs).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_pair.cuh"
+
+namespace dmf {
+
+constexpr int F4_THREADS = 320;
+constexpr int F4_TILE = 128 * 64 * 2;   // 16 KB: [128 rows x 64 bf16]
+constexpr int F4_STAGES = 5;
+constexpr int F4_BN = 256;              // column tile of the pair
+constexpr float kLog2eF4 = 1.4426950408889634f;
+
+__device__ __forceinline__ float f4_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Sum over the 32 lanes of e[j] for every j; lane L returns the total of column L.
+__device__ __forceinline__ float warp_colsum32(float (&e)[32], int lane) {
+  float t16[16];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float send = up ? e[k] : e[k + 16];
+      const float keep = up ? e[k + 16] : e[k];
+      t16[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  float t8[8];
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float send = up ? t16[k] : t16[k + 8];
+      const float keep = up ? t16[k + 8] : t16[k];
+      t8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  float t4[4];
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float send = up ? t8[k] : t8[k + 4];
+      const float keep = up ? t8[k + 4] : t8[k];
+      t4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  float t2[2];
+  {
+    const bool up = lane & 2;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float send = up ? t4[k] : t4[k + 2];
+      const float keep = up ? t4[k + 2] : t4[k];
+      t2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+  }
+  const bool up = lane & 1;
+  const float send = up ? t2[0] : t2[1];
+  const float keep = up ? t2[1] : t2[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+struct F4Args {
+  int Ma, Nb, num_kb;
+  float scale;        // 1 / temperature
+  float sl2;          // scale * log2(e)
+  float shift2;       // fixed shift in the log2 domain
+  int sym;            // 1: A rows are rows [row0_global, row0_global + Ma) of Bm (symmetric block, half window)
+  int row0_global;    // global index of local row 0 (multiple of 256 when sym)
+  int total_tiles;    // T = ceil(Nb / 256)
+  int tiles_per_split;
+  float* row_sum;     // [Ma]  += (caller zeroes)
+  float* col_sum;     // [Nb]  += (caller zeroes); may be NULL when !sym (rows only)
+  long long diag_offset;
+  float* diag_out;    // [Ma] raw scaled similarity s_{i, diag_offset + i}
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F4_THREADS, 1)
+rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const F4Args P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smemA = smem;                                    // num_kb tiles: this CTA's 128 anchor rows
+  uint8_t* smemB = smem + P.num_kb * F4_TILE;               // F4_STAGES tiles: this CTA's half of the column tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + F4_STAGES * F4_TILE);
+  uint64_t* a_full = bars;
+  uint64_t* full_bar = bars + 1;
+  uint64_t* empty_bar = full_bar + F4_STAGES;
+  uint64_t* s_full = empty_bar + F4_STAGES;   // per CTA [2]
+  uint64_t* s_empty = s_full + 2;             // leader [2]: 16 softmax warps of the pair drained the buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
+  float* mrg = reinterpret_cast<float*>(tmem_slot + 4);   // [128] row-sum merge of the two column halves
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc2::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int blk = blockIdx.x >> 1;                          // 256-row anchor block (local)
+  const int m0 = blk * 256 + (int)rank * 128;               // first local row of this CTA
+  const int T = P.total_tiles;
+  // tile window of this anchor block: cyclic [w0, w0 + wcnt) mod T
+  int w0 = 0, wcnt = T;
+  const int Ig = (P.row0_global >> 8) + blk;                // global row-block index (sym only)
+  if (P.sym) {
+    w0 = Ig;
+    if (T & 1) wcnt = (T + 1) / 2;
+    else wcnt = T / 2 + (Ig < T / 2 ? 1 : 0);
+  }
+  const int t_begin = blockIdx.y * P.tiles_per_split;
+  const int ntiles = max(0, min(wcnt, t_begin + P.tiles_per_split) - t_begin);
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+    tc::mbar_init(a_full, 1);
+    for (int s = 0; s < F4_STAGES; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(s_full + b, 1); tc::mbar_init(s_empty + b, 16); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc2::tmem_alloc2<512>(tmem_slot);
+  tc::tc_fence_before_sync();
+  tc2::cluster_sync_all();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && ntiles > 0) {
+      if (leader) tc::mbar_expect_tx(a_full, 2 * P.num_kb * F4_TILE);
+      for (int kb = 0; kb < P.num_kb; ++kb) tc2::tma_load_2d_pair(smemA + kb * F4_TILE, &tmA, kb * 64, m0, a_full);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        int J = w0 + t_begin + t;
+        if (J >= T) J -= T;
+        const int j0 = J * F4_BN + (int)rank * 128;
+        for (int kb = 0; kb < P.num_kb; ++kb) {
+          tc::mbar_wait(empty_bar + stage, phase ^ 1);
+          if (leader) tc::mbar_expect_tx(full_bar + stage, 2 * F4_TILE);
+          tc2::tma_load_2d_pair(smemB + stage * F4_TILE, &tmB, kb * 64, j0, full_bar + stage);
+          if (++stage == F4_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0 && ntiles > 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(256, F4_BN, 0, 0);
+      tc::mbar_wait(a_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        tc::mbar_wait(s_empty + buf, (((uint32_t)t >> 1) & 1) ^ 1);
+        tc::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * F4_BN);
+        for (int kb = 0; kb < P.num_kb; ++kb) {
+          tc::mbar_wait(full_bar + stage, phase);
+          tc::tc_fence_after_sync();
+          const uint32_t a_addr = tc::smem_u32(smemA + kb * F4_TILE);
+          const uint32_t b_addr = tc::smem_u32(smemB + stage * F4_TILE);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc2::umma_ss2(d_tmem, tc::make_smem_desc(a_addr + k * 32, 16, 1024),
+                          tc::make_smem_desc(b_addr + k * 32, 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc2::umma_commit2(empty_bar + stage);
+          if (++stage == F4_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc2::umma_commit2(s_full + buf);
+      }
+    }
+  } else {
+    const int sw = warp - 2;
+    const int q = warp & 3;
+    const int ch = sw >> 2;                      // column half (128 columns) of every 256-wide tile
+    const int rloc = q * 32 + lane;
+    const int row = m0 + rloc;
+    const bool rvalid = row < P.Ma;
+    // invalid rows (TMA zero fill) must contribute nothing to the column sums: shift = +inf -> e = 0
+    const float my_shift = rvalid ? P.shift2 : INFINITY;
+    float l = 0.f, diag = 0.f;
+    bool has_diag = false;
+    const long long dj = (P.diag_offset >= 0 && rvalid) ? P.diag_offset + row : -1;
+    const uint32_t s_empty_leader0 = tc2::mapa(tc::smem_u32(s_empty), 0);
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      int J = w0 + t_begin + t;
+      if (J >= T) J -= T;
+      const bool want_cols = P.col_sum != nullptr && !(P.sym && J == Ig);
+      tc::mbar_wait(s_full + buf, ((uint32_t)t >> 1) & 1);
+      tc::tc_fence_after_sync();
+      const int j0 = J * F4_BN + ch * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * F4_BN + ch * 128 + c * 32), r);
+        tc::tmem_ld_wait();
+        const int nbase = j0 + c * 32;
+        const int nvalid = P.Nb - nbase;
+        if (nvalid <= 0) continue;                 // warp-uniform
+        if (dj >= nbase && dj < nbase + 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nbase + j == dj) { diag = __uint_as_float(r[j]) * P.scale; has_diag = true; }
+        }
+        float e[32];
+        if (nvalid >= 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) e[j] = f4_exp2(fmaf(__uint_as_float(r[j]), P.sl2, -my_shift));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) e[j] = j < nvalid ? f4_exp2(fmaf(__uint_as_float(r[j]), P.sl2, -my_shift)) : 0.f;
+        }
+        float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) { ps0 += e[j]; ps1 += e[j + 1]; ps2 += e[j + 2]; ps3 += e[j + 3]; }
+        l += (ps0 + ps1) + (ps2 + ps3);
+        if (want_cols) {
+          const float cs = warp_colsum32(e, lane);
+          if (lane < nvalid) atomicAdd(P.col_sum + nbase + lane, cs);
+        }
+      }
+      tc::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc2::mbar_arrive_cluster(s_empty_leader0 + (uint32_t)(buf * 8));
+    }
+    // merge the two column halves of each row, then one atomicAdd per row (column splits share rows)
+    if (ch == 1) {
+      mrg[rloc] = l;
+      mrg[128 + rloc] = diag;
+      mrg[256 + rloc] = has_diag ? 1.f : 0.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (ch == 0 && rvalid && ntiles > 0) {
+      atomicAdd(P.row_sum + row, l + mrg[rloc]);
+      if (P.diag_out) {
+        if (has_diag) P.diag_out[row] = diag;
+        else if (mrg[256 + rloc] != 0.f) P.diag_out[row] = mrg[128 + rloc];
+      }
+    }
+  }
+  __syncwarp();
+  tc::tc_fence_before_sync();
+  tc2::cluster_sync_all();          // the peer may still target this CTA's barriers / TMEM until here
+  if (warp == 1) tc2::tmem_dealloc2<512>(tmem_base);
+}
+
+}  // namespace dmf
+
+using namespace dmf;
+
+// Sums of exp(scale * <a_i, b_j> - shift) over the rows / columns of the [Ma x Nb] similarity block (bf16 operands).
+//   sym = 0: every tile; row_sum[i] += sum_j, col_sum[j] += sum_i (col_sum may be NULL).
+//   sym = 1: A must be rows [row0_global, row0_global + Ma) of Bm (a symmetric Gram block); only the cyclic half
+//            window of tiles is computed and the FULL row sum of global row g is row_sum[g - row0_global] + col_sum[g]
+//            (col_sum summed over all ranks).  Requires row0_global % 256 == 0.
+// row_sum / col_sum are accumulated (caller zeroes).  diag_out[i] = scale * <a_i, b_{diag_offset+i}> (natural units).
+extern "C" int dmf_infonce_rowcol_sums(const void* A, long long lda, int Ma, const void* Bm, long long ldb, int Nb, int D,
+                                       float scale, float shift, int sym, int row0_global, float* row_sum, float* col_sum,
+                                       long long diag_offset, float* diag_out, dmf_stream_t s) {
+  DMF_REQUIRE(A && Bm && row_sum, "dmf_infonce_rowcol_sums: null argument");
+  DMF_REQUIRE(Ma >= 0 && Nb >= 1, "dmf_infonce_rowcol_sums: bad shape Ma=%d Nb=%d", Ma, Nb);
+  DMF_REQUIRE(D % 64 == 0 && D >= 64 && D <= 512, "dmf_infonce_rowcol_sums: D=%d must be a multiple of 64 in [64,512]", D);
+  DMF_REQUIRE(!sym || (col_sum && (row0_global % 256) == 0 && row0_global + Ma <= Nb),
+              "dmf_infonce_rowcol_sums: symmetric mode needs col_sum, row0_global %% 256 == 0 and the rows inside Bm");
+  if (Ma == 0) return 0;
+  const int num_kb = D / 64;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_2d(&tmA, A, Ma, D, lda, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, Bm, Nb, D, ldb, 128);
+  if (rc) return rc;
+  const size_t smem = 1024 + (size_t)(num_kb + F4_STAGES) * F4_TILE + 256 + 2048;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(rowcol_sum_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(1024 + (size_t)(8 + F4_STAGES) * F4_TILE + 256 + 2048));
+    if (e != cudaSuccess) return fail((int)e, "dmf_infonce_rowcol_sums: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  F4Args P;
+  P.Ma = Ma; P.Nb = Nb; P.num_kb = num_kb;
+  P.scale = scale;
+  P.sl2 = scale * kLog2eF4;
+  P.shift2 = shift * kLog2eF4;
+  P.sym = sym ? 1 : 0;
+  P.row0_global = row0_global;
+  P.total_tiles = (Nb + F4_BN - 1) / F4_BN;
+  P.row_sum = row_sum; P.col_sum = col_sum;
+  P.diag_offset = diag_offset; P.diag_out = diag_out;
+  const int pairs = (Ma + 255) / 256;
+  const int window = sym ? P.total_tiles / 2 + 1 : P.total_tiles;
+  // split the tile window over blockIdx.y so that pairs * nsplit fills whole waves of the 74 clusters
+  int nsplit = 1;
+  {
+    double best = 0.0;
+    for (int ns = 1; ns <= 16; ++ns) {
+      if (ns > 1 && window / ns < 4) break;
+      const int items = pairs * ns;
+      const double eff = (double)items / (double)(((items + 73) / 74) * 74);
+      if (eff > best + 0.02) { best = eff; nsplit = ns; }
+      if (eff >= 0.97) break;
+    }
+  }
+  P.tiles_per_split = (window + nsplit - 1) / nsplit;
+  dim3 grid(2 * pairs, nsplit);
+  rowcol_sum_tc4_kernel<<<grid, F4_THREADS, smem, (cudaStream_t)s>>>(tmA, tmB, P);
+  return launched("dmf_infonce_rowcol_sums");
+}

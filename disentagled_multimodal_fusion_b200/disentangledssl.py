@@ -151,16 +151,16 @@ class DisentangledSSL(LightningModule):
         vv2 = torch.cat([noise[1][1], noise[3][1]], 0)
         Z1 = ops.vmf_rsample(E1, w1, vv1)
         Z2 = ops.vmf_rsample(E2, w2, vv2)
-        joint_loss, loss_x, loss_y = self.critic.pair(Z1[:B], Z2[:B])
-        joint_loss_v, loss_x_v, loss_y_v = self.critic.pair(Z1[B:], Z2[B:])
+        joint_loss, loss_x, loss_y = self.critic.pair(Z1[:B], Z2[:B], unit_norm=True)
+        joint_loss_v, loss_x_v, loss_y_v = self.critic.pair(Z1[B:], Z2[B:], unit_norm=True)
         joint_loss = 0.5 * (joint_loss + joint_loss_v)
         loss_x = 0.5 * (loss_x + loss_x_v)
         loss_y = 0.5 * (loss_y + loss_y_v)
         loss_shared = joint_loss
 
         P1n, P2n = ops.row_normalize(P1), ops.row_normalize(P2)
-        specific_loss_x1, _, _ = self.critic.pair(P1n[:B], P1n[B:])
-        specific_loss_x2, _, _ = self.critic.pair(P2n[:B], P2n[B:])
+        specific_loss_x1, _, _ = self.critic.pair(P1n[:B], P1n[B:], unit_norm=True)
+        specific_loss_x2, _, _ = self.critic.pair(P2n[:B], P2n[B:], unit_norm=True)
         loss_specific = specific_loss_x1 + specific_loss_x2
 
         lmd = self.lmd_scheduler(self.iterations) if self.lmd_end_value > 0 else self.lmd_start_value

@@ -236,19 +236,34 @@ class _GroupedMLP(torch.autograd.Function):
         dbs = [[None] * NL for _ in range(G)]
         dxs = [None] * G
         for l in range(NL - 1, -1, -1):
-            wdescs, ddescs = [], []
+            wdescs, ddescs, partials = [], [], []
             new_dY = [None] * G
             for g in range(G):
                 X = acts[g][l]
                 dY = dYs[g]
                 M, K = X.shape
                 N = dY.shape[1]
-                dW = torch.empty(N, K, dtype=torch.float32, device=dev)
-                db = torch.empty(N, dtype=torch.float32, device=dev)
-                # dW[n,k] = sum_m dY[m,n] X[m,k];  db[n] = sum_m dY[m,n]  (row sums of the A operand)
-                wdescs.append(dict(A=dY, a_rs=1, a_cs=dY.stride(0), B=X, b_rs=X.stride(0), b_cs=1, C=dW, ldc=K,
-                                   rowsum_a=db, M=N, N=K, K=M))
-                dWs[g][l], dbs[g][l] = dW, db
+                # dW[n,k] = sum_m dY[m,n] X[m,k];  db[n] = sum_m dY[m,n]  (row sums of the A operand).
+                # The output is tiny and the contraction runs over the batch: split the batch into chunks
+                # (one descriptor each, partial results reduced by a column sum) so the grid fills the GPU.
+                chunks = max(1, min(32, M // 2048))
+                if chunks == 1:
+                    dW = torch.empty(N, K, dtype=torch.float32, device=dev)
+                    db = torch.empty(N, dtype=torch.float32, device=dev)
+                    wdescs.append(dict(A=dY, a_rs=1, a_cs=dY.stride(0), B=X, b_rs=X.stride(0), b_cs=1, C=dW, ldc=K,
+                                       rowsum_a=db, M=N, N=K, K=M))
+                    dWs[g][l], dbs[g][l] = dW, db
+                else:
+                    rows = (M + chunks - 1) // chunks
+                    chunks = (M + rows - 1) // rows
+                    dWp = torch.empty(chunks, N * K, dtype=torch.float32, device=dev)
+                    dbp = torch.empty(chunks, N, dtype=torch.float32, device=dev)
+                    for c in range(chunks):
+                        r0 = c * rows
+                        rc = min(rows, M - r0)
+                        wdescs.append(dict(A=dY[r0:], a_rs=1, a_cs=dY.stride(0), B=X[r0:], b_rs=X.stride(0), b_cs=1,
+                                           C=dWp[c], ldc=K, rowsum_a=dbp[c], M=N, N=K, K=rc))
+                    partials.append((g, l, dWp, dbp, N, K))
                 if l > 0 or ctx.in_needs_grad[g]:
                     W = Ws[g][l]
                     dX = torch.empty(M, K, dtype=torch.float32, device=dev)
@@ -266,6 +281,9 @@ class _GroupedMLP(torch.autograd.Function):
                                            ldc=De, M=M, N=De, K=N)))
                     new_dY[g] = dX
             gemm_f32(wdescs, L.EPI_NONE)
+            for (g, ll, dWp, dbp, N, K) in partials:
+                dWs[g][ll] = colsum(dWp).view(N, K)
+                dbs[g][ll] = colsum(dbp)
             if ddescs:
                 if l > 0:
                     gemm_f32([d for _, d in ddescs], L.EPI_RELU_MASK)
@@ -479,7 +497,7 @@ def grouped_mlp(xs: Sequence[Tensor], weights: Sequence[Sequence[Tensor]], biase
 # ----------------------------------------------------------------------------------------
 class _InfoNCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z0, z1, temperature, precision):
+    def forward(ctx, z0, z1, temperature, precision, bound):
         L.require_device()
         z0, z1 = _f32c(z0), _f32c(z1)
         Bl, D = z0.shape
@@ -500,25 +518,52 @@ class _InfoNCE(torch.autograd.Function):
         else:
             g0, g1 = a0, a1
         scale = 1.0 / temperature
-        st = torch.empty(12, Bl, dtype=torch.float32, device=dev)
-        wsb = lib.dmf_rowlse_workspace_bytes(Bl, Bg) if dt == 1 else 0
-        ws = torch.empty(max(1, wsb // 4), dtype=torch.float32, device=dev)
         off = rank * Bl
-
-        def rowlse(A, Bm, mo, lo, do):
-            check(lib.dmf_rowlse(ptr(A), A.stride(0), Bl, ptr(Bm), Bm.stride(0), Bg, D, scale, ptr(st[mo]), ptr(st[lo]),
-                                 off, ptr(st[do]), ptr(ws), wsb, dt, stream()))
-        with _Prof("rowlse_x4"):
-            rowlse(a0, g1, 0, 1, 2)      # anchors z0 vs all z1: cross block, diag = positive
-            rowlse(a0, g0, 3, 4, 5)      # anchors z0 vs all z0: intra-view block, diag = self similarity
-            rowlse(a1, g0, 6, 7, 8)
-            rowlse(a1, g1, 9, 10, 11)
         out3 = torch.zeros(3, dtype=torch.float32, device=dev)
         lse = torch.empty(2, Bl, dtype=torch.float32, device=dev)
-        check(lib.dmf_infonce_finalize(ptr(st[0]), ptr(st[1]), ptr(st[3]), ptr(st[4]), ptr(st[2]), ptr(st[5]), Bl,
-                                       1.0 / (2 * Bg), 1.0 / Bg, 0, ptr(lse[0]), ptr(out3), stream()))
-        check(lib.dmf_infonce_finalize(ptr(st[6]), ptr(st[7]), ptr(st[9]), ptr(st[10]), ptr(st[8]), ptr(st[11]), Bl,
-                                       1.0 / (2 * Bg), 1.0 / Bg, 1, ptr(lse[1]), ptr(out3), stream()))
+        fused = bound is not None and dt == 1 and D % 64 == 0 and D <= 512 and off % 256 == 0
+        if fused:
+            # unit-norm embeddings: fixed shift, row AND column sums from one pass over S01, symmetric
+            # intra-view blocks on a half window (two B x B blocks of work instead of four)
+            shift = float(bound)
+            rs = torch.zeros(3, Bl, dtype=torch.float32, device=dev)
+            cs = torch.zeros(3, Bg, dtype=torch.float32, device=dev)
+            dg = torch.empty(3, Bl, dtype=torch.float32, device=dev)
+
+            def rowcol(A, Bm, k, sym):
+                check(lib.dmf_infonce_rowcol_sums(ptr(A), A.stride(0), Bl, ptr(Bm), Bm.stride(0), Bg, D, scale, shift, sym,
+                                                  off, ptr(rs[k]), ptr(cs[k]), off, ptr(dg[k]), stream()))
+            with _Prof("rowlse_x4"):
+                rowcol(a0, g1, 0, 0)     # cross block: rows -> view-0 anchors, columns -> view-1 anchors
+                rowcol(a0, g0, 1, 1)     # intra-view blocks (no-grad diagnostics + the reference's row max)
+                rowcol(a1, g1, 2, 1)
+            if world > 1:
+                dist.all_reduce(cs)
+            mfix = torch.full((Bl,), shift, dtype=torch.float32, device=dev)
+            l_c1 = cs[0, off:off + Bl].contiguous()
+            l_i0 = rs[1] + cs[1, off:off + Bl]
+            l_i1 = rs[2] + cs[2, off:off + Bl]
+            check(lib.dmf_infonce_finalize(ptr(mfix), ptr(rs[0]), ptr(mfix), ptr(l_i0), ptr(dg[0]), ptr(dg[1]), Bl,
+                                           1.0 / (2 * Bg), 1.0 / Bg, 0, ptr(lse[0]), ptr(out3), stream()))
+            check(lib.dmf_infonce_finalize(ptr(mfix), ptr(l_c1), ptr(mfix), ptr(l_i1), ptr(dg[0]), ptr(dg[2]), Bl,
+                                           1.0 / (2 * Bg), 1.0 / Bg, 1, ptr(lse[1]), ptr(out3), stream()))
+        else:
+            st = torch.empty(12, Bl, dtype=torch.float32, device=dev)
+            wsb = lib.dmf_rowlse_workspace_bytes(Bl, Bg) if dt == 1 else 0
+            ws = torch.empty(max(1, wsb // 4), dtype=torch.float32, device=dev)
+
+            def rowlse(A, Bm, mo, lo, do):
+                check(lib.dmf_rowlse(ptr(A), A.stride(0), Bl, ptr(Bm), Bm.stride(0), Bg, D, scale, ptr(st[mo]), ptr(st[lo]),
+                                     off, ptr(st[do]), ptr(ws), wsb, dt, stream()))
+            with _Prof("rowlse_x4"):
+                rowlse(a0, g1, 0, 1, 2)      # anchors z0 vs all z1: cross block, diag = positive
+                rowlse(a0, g0, 3, 4, 5)      # anchors z0 vs all z0: intra-view block, diag = self similarity
+                rowlse(a1, g0, 6, 7, 8)
+                rowlse(a1, g1, 9, 10, 11)
+            check(lib.dmf_infonce_finalize(ptr(st[0]), ptr(st[1]), ptr(st[3]), ptr(st[4]), ptr(st[2]), ptr(st[5]), Bl,
+                                           1.0 / (2 * Bg), 1.0 / Bg, 0, ptr(lse[0]), ptr(out3), stream()))
+            check(lib.dmf_infonce_finalize(ptr(st[6]), ptr(st[7]), ptr(st[9]), ptr(st[10]), ptr(st[8]), ptr(st[11]), Bl,
+                                           1.0 / (2 * Bg), 1.0 / Bg, 1, ptr(lse[1]), ptr(out3), stream()))
         if world > 1:
             dist.all_reduce(out3)
             lse_all = torch.empty(2, Bg, dtype=torch.float32, device=dev)
@@ -551,13 +596,17 @@ class _InfoNCE(torch.autograd.Function):
             check(lib.dmf_infonce_bwd(ptr(a1), a1.stride(0), Bl, ptr(lse[1]), ptr(g0), g0.stride(0), ptr(g0T),
                                       g0T.stride(0) if g0T is not None else 0, Bg, ptr(lse_all[0]), D, scale, coef, ptr(gs),
                                       off, ptr(dz1), D, 0, dt, stream()))
-        return dz0, dz1, None, None
+        return dz0, dz1, None, None, None
 
 
-def infonce(z0: Tensor, z1: Tensor, temperature: float = 0.07, precision: str = "fp32") -> Tuple[Tensor, Tensor, Tensor]:
+def infonce(z0: Tensor, z1: Tensor, temperature: float = 0.07, precision: str = "fp32",
+            unit_norm: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     """(loss, loss_x, loss_y) of SupConLoss()(stack([z0,z1],1)) without the [2B,2B] logits.
-    Under torch.distributed the negatives are global (embeddings all-gathered with NCCL)."""
-    out = _InfoNCE.apply(z0, z1, float(temperature), precision)
+    Under torch.distributed the negatives are global (embeddings all-gathered with NCCL).
+    ``unit_norm=True`` asserts that the rows of z0 / z1 are L2-normalised (|s| <= 1/T): the bf16 path then runs
+    the fixed-shift row+column kernel (dmf_infonce_rowcol_sums) instead of four online-max passes."""
+    bound = (1.0 / float(temperature)) if unit_norm else None
+    out = _InfoNCE.apply(z0, z1, float(temperature), precision, bound)
     return out[0], out[1].detach(), out[2].detach()
 
 

@@ -119,6 +119,19 @@ int dmf_rowlse(const void* A, long long lda, int Ma, const void* Bm, long long l
 /* scratch the bf16 path may use to split the columns across CTAs (0 is always accepted)     */
 size_t dmf_rowlse_workspace_bytes(int Ma, int Nb);
 
+/* Fixed-shift variant for L2-NORMALISED embeddings (|s| <= scale; DisentangledSSL feeds vMF samples and
+ * F.normalize outputs, models/disentangledssl.py:134-140): one pass over the tiles of the [Ma x Nb] block gives
+ *   row_sum[i] += sum_j exp(s_ij - shift)   and   col_sum[j] += sum_i exp(s_ij - shift)
+ * (both ACCUMULATED; the caller zeroes them), so the column LSEs of S01 -- the row LSEs of the view-1 anchors --
+ * come from the same tiles as the view-0 ones.  sym = 1: A is rows [row0_global, row0_global+Ma) of Bm (a
+ * symmetric intra-view block): only the cyclic half window of 256-column tiles is visited and the full row sum
+ * of global row g is row_sum[g-row0_global] + col_sum[g] (col_sum summed over ranks); needs row0_global % 256
+ * == 0.  col_sum may be NULL when sym = 0.  diag_out[i] = s_{i, diag_offset+i} if diag_offset >= 0.
+ * bf16 operands, D % 64 == 0, D <= 512.  Feed dmf_infonce_finalize with m_* = shift and l_* = these sums.  */
+int dmf_infonce_rowcol_sums(const void* A, long long lda, int Ma, const void* Bm, long long ldb, int Nb, int D,
+                            float scale, float shift, int sym, int row0_global, float* row_sum, float* col_sum,
+                            long long diag_offset, float* diag_out, dmf_stream_t s);
+
 /* Per-anchor finalisation of one SupConLoss call (models/losses.py:68-99) for BOTH anchor sets:
  *   m_full = max(m_cross, m_intra); sum_c = l_cross*exp(m_cross-m_full);
  *   loss_i = -(pos - m_full - log(sum_c + 1e-12));  lse_eff_i = m_full + log(sum_c + 1e-12)

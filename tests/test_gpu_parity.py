@@ -169,6 +169,56 @@ def test_vmf_device_draw_distribution(dmf):
     assert abs(float(v.mean())) < 2e-3
 
 
+@pytest.mark.parametrize("Bg,D,nrank", [(256, 64, 1), (512, 128, 1), (1280, 512, 1), (700, 64, 1), (2048, 256, 4), (1536, 128, 2)])
+def test_infonce_rowcol_sums_kernel(dmf, Bg, D, nrank):
+    """Fixed-shift row+column sums (cross block) and half-window symmetric blocks vs a dense fp64 reference;
+    nrank > 1 emulates the data-parallel row shards (column sums added over ranks)."""
+    ops, Lb = dmf.ops, dmf._lib
+    gen = torch.Generator().manual_seed(Bg + D)
+    z0 = torch.nn.functional.normalize(torch.randn(Bg, D, generator=gen), dim=-1)
+    z1 = torch.nn.functional.normalize(0.6 * z0 + 0.4 * torch.randn(Bg, D, generator=gen), dim=-1)
+    b0, b1 = z0.to(DEV).bfloat16(), z1.to(DEV).bfloat16()
+    scale = 1 / 0.07
+    shift = scale
+    S01 = (b0.double() @ b1.double().T) * scale
+    S00 = (b0.double() @ b0.double().T) * scale
+    E01, E00 = torch.exp(S01 - shift), torch.exp(S00 - shift)
+    Bl = Bg // nrank
+    rs = torch.zeros(2, Bg, device=DEV)
+    cs = torch.zeros(2, Bg, device=DEV)
+    dg = torch.zeros(2, Bg, device=DEV)
+    for r in range(nrank):
+        off = r * Bl
+        a0 = b0[off:off + Bl]
+        for k, (Bm, sym) in enumerate(((b1, 0), (b0, 1))):
+            Lb.check(Lb.lib.dmf_infonce_rowcol_sums(a0.data_ptr(), D, Bl, Bm.data_ptr(), D, Bg, D, scale, shift, sym, off,
+                                                    rs[k, off:].data_ptr(), cs[k].data_ptr(), off, dg[k, off:].data_ptr(),
+                                                    Lb.stream()))
+    assert_close(rs[0], E01.sum(1).float(), 2e-3, "cross row sums")
+    assert_close(cs[0], E01.sum(0).float(), 2e-3, "cross column sums")
+    assert_close(rs[1] + cs[1], E00.sum(1).float(), 2e-3, "symmetric block row sums (half window)")
+    assert_close(dg[0], torch.diagonal(S01).float(), 1e-3, "positives")
+    assert_close(dg[1], torch.diagonal(S00).float(), 1e-3, "self similarities")
+
+
+def test_infonce_unit_norm_path_matches_generic(dmf):
+    """ops.infonce(unit_norm=True) (fixed shift, 3 launches) vs the generic online-max path on the same bf16 inputs."""
+    gen = torch.Generator().manual_seed(9)
+    B, D = 1024, 128
+    z0 = torch.nn.functional.normalize(torch.randn(B, D, generator=gen), dim=-1).to(DEV)
+    z1 = torch.nn.functional.normalize(0.5 * z0.cpu() + 0.5 * torch.randn(B, D, generator=gen), dim=-1).to(DEV)
+    outs = []
+    for un in (False, True):
+        a, b = z0.clone().requires_grad_(), z1.clone().requires_grad_()
+        loss, lx, ly = dmf.ops.infonce(a, b, 0.07, "bf16", unit_norm=un)
+        loss.backward()
+        outs.append((loss.detach(), lx, ly, a.grad, b.grad))
+    for x, y, what in zip(outs[1], outs[0], ("loss", "loss_x", "loss_y", "dz0", "dz1")):
+        # loss_x / loss_y are cancellation residues (self-similarity minus an LSE of logits ~ 1/T = 14.3)
+        assert_close(x, y, 1e-4, what, atol=5e-6 if what in ("loss_x", "loss_y") else 0.0)
+
+
+
 # ------------------------------------------------------------------------------------- K1
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 512), (100, 800, 240), (131, 77, 136), (600, 47, 512)])
 def test_tc_gemm(dmf, M, N, K):

@@ -566,3 +566,20 @@ def test_launch_counter_moves(dmf):
     before = dmf._lib.launch_count()
     dmf.ops.fuse_evidence(torch.rand(8, 3, 4, device=DEV), "cml")
     assert dmf._lib.launch_count() == before + 1
+
+
+# ------------------------------------------------------------------------------------- multi-GPU (NCCL)
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_data_parallel_matches_single_gpu(dmf, prec):
+    """2-rank NCCL run of one DSSL step (global negatives via all-gather, column sums / Gram / gradients
+    all-reduced) vs the same step on the full batch in one process.  Skipped on a 1-GPU box."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = "29541" if prec == "bf16" else "29542"
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", port, os.path.join(root, "tests", "dp_worker.py"), prec],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("OK") == 2, out.stdout[-2000:]

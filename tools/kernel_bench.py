@@ -75,11 +75,21 @@ def main():
         u = torch.empty(Be, device=dev); ale = torch.empty(Be, device=dev); parts = torch.zeros(4, device=dev)
         for dcw, tag in ((0.6, "fused=1"), (0.0, "fused=0")):
             p = L.EdlParams(Be, V, C, 0, 0.5, dcw, 1.0 / Be)
+            # training call (ops.edl_fused_loss): fused evidence + gradient + loss parts; 8VC + 4C + 16 B/sample
+            k = lambda: check(lib.dmf_edl_fused(ptr(evid), ptr(y), p, 0, ptr(fused), ptr(grad), 0, 0, 0, ptr(parts), stream()))
+            ms = timeit(k, iters=3, warm=1)
+            byt = Be * (8 * V * C + 4 * C + 16)
+            print(f"edl_fused train  B={Be} V={V} C={C} {tag}: {ms:.3f} ms  {byt/ms/1e6:.1f} GB/s algorithmic")
+            # + uncertainty summaries (u, aleatoric)
             k = lambda: check(lib.dmf_edl_fused(ptr(evid), ptr(y), p, 0, ptr(fused), ptr(grad), ptr(u), ptr(ale), 0, ptr(parts), stream()))
             ms = timeit(k, iters=3, warm=1)
             byt = Be * (8 * V * C + 4 * C + 16 + 8)
-            print(f"edl_fused B={Be} V={V} C={C} {tag}: {ms:.3f} ms  {byt/ms/1e6:.1f} GB/s algorithmic")
-
+            print(f"edl_fused +u/ale B={Be} V={V} C={C} {tag}: {ms:.3f} ms  {byt/ms/1e6:.1f} GB/s algorithmic")
+        p = L.EdlParams(Be, V, C, 0, 0.0, 0.0, 1.0 / Be)
+        k = lambda: check(lib.dmf_edl_fused(ptr(evid), ptr(y), p, 0, ptr(fused), 0, ptr(u), ptr(ale), 0, 0, stream()))
+        ms = timeit(k, iters=3, warm=1)
+        byt = Be * (4 * V * C + 4 * C + 16)
+        print(f"edl_fused eval (fused,u,ale) B={Be} V={V} C={C}: {ms:.3f} ms  {byt/ms/1e6:.1f} GB/s algorithmic")
 
 if __name__ == "__main__":
     main()

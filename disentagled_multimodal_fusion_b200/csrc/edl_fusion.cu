@@ -10,98 +10,55 @@
 //   dKL/de_c = (a_c-1) psi1(a_c) - (S~-C) psi1(S~)   for c != y, 0 for c == y
 // so only C+2 (lgamma,digamma,trigamma) triples are evaluated per (sample, view).
 //
-// Memory-bound design: a CTA stages a tile of SPB samples (SPB*V*C floats, <= 12 KB) through
-// shared memory with 128-bit coalesced loads, works on it in phases (row phase = one thread per
-// (sample,view); element phase = one thread per (sample,view,class)), and writes grad / fused
-// evidence tiles back with coalesced stores.  Algorithmic bytes per sample: 8VC + 4C + 16 + 8.
+// Memory-bound design (v3, "one thread per Dirichlet"): a thread owns one (sample, view) row and walks its C
+// classes; the V rows of a sample sit in adjacent lanes of one warp and advance in LOCKSTEP over the class
+// index, so everything that couples views (fused evidence, the pairwise conflict |p_i - p_j|, its sign
+// pattern) is exchanged with warp shuffles -- no block barrier inside the math, no index division, no
+// per-row arrays in shared memory.  Shared memory only carries the tile itself: a CTA copies its samples
+// in with 128-bit coalesced loads, the row threads overwrite each evidence value by its gradient IN PLACE,
+// and the tile (plus the fused-evidence tile) goes back out with 128-bit coalesced stores.  CTAs are
+// persistent (tiles dealt round-robin) and 4 fit per SM.  Algorithmic bytes per sample: 8VC + 4C + 16.
 #include "common.cuh"
 #include "special_math.cuh"
 
 namespace dmf {
 
 constexpr int kEdlThreads = 256;
-constexpr int kEdlMaxTile = 3072;  // elements of evid per CTA tile (12 KB)
-constexpr int kEdlEPT4 = kEdlMaxTile / (4 * kEdlThreads);   // float4 groups per thread = 3
+constexpr int kEdlWarps = kEdlThreads / 32;
+constexpr int kEdlMaxV = 8;
+constexpr int kEdlTileFloats = 10752;   // evidence tile per CTA (42 KB): 64 samples at V*C = 168
 
-// Layout of the dynamic shared memory (floats).  E = SPB*V*C, R = SPB*V.
-struct EdlSmem {
-  float* e;      // [E] evidence tile
-  float* p;      // [E] projected probabilities alpha/(S+1e-8)            (dc / dbf only)
-  float* S;      // [R] Dirichlet strength
-  float* iT;     // [R] 1/(S+1e-8)
-  float* om;     // [R] 1-u
-  float* gy;     // [R] psi1(S) - psi1(alpha_y)             gradient of the label class
-  float* gA;     // [R] psi1(S) - coef*(S~-C)*psi1(S~)      class-independent part for c != y
-  float* psiT;   // [R] psi(S~)
-  float* rowK;   // [R] (dot + gu*C) / T^2                  dc gradient, row part
-  float* disc;   // [R] dbf discount
-  float* pd;     // [SPB*V*V] pairwise conflict 0.5*sum_c|p_i-p_j|
-  float* q;      // [SPB*V*V] q_ij = sum_c sign(p_ic-p_jc)*alpha_ic
-  float* f;      // [SPB*C] fused evidence tile
-  float* t;      // [SPB*C] aleatoric terms
-  float* Sf;     // [SPB]
-  float* psiSf;  // [SPB]
-  int* y;        // [SPB]
-};
+__device__ __forceinline__ float sgn3(float d) { return d > 0.f ? 1.0f : (d < 0.f ? -1.0f : 0.f); }
 
-__host__ __device__ inline size_t edl_smem_floats(int SPB, int V, int C) {
-  const size_t E = (size_t)SPB * V * C, R = (size_t)SPB * V;
-  return 2 * E + 8 * R + 2 * (size_t)SPB * V * V + 2 * (size_t)SPB * C + 3 * (size_t)SPB + 16;
-}
-
-__device__ __forceinline__ float f4_get(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
-__device__ __forceinline__ void f4_set(float4& v, int k, float x) {
-  if (k == 0) v.x = x; else if (k == 1) v.y = x; else if (k == 2) v.z = x; else v.w = x;
-}
-
-// Persistent CTAs: tiles of SPB samples are dealt round-robin.  Each thread owns up to 3 float4 groups of
-// the tile (loaded with one 128-bit coalesced load each, kept in registers through all phases and stored
-// back as the gradient with one 128-bit store each); shared memory only carries what other threads need
-// (the evidence tile for row sums / fusion, per-row statistics, the projected probabilities for the
-// degree-of-conflict term).  mC / mV are 2^32/C and 2^32/V magic multipliers (exact for idx < 65536).
+template <int VT>
 __global__ void __launch_bounds__(kEdlThreads, 4)
 edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ labels, dmf_edl_params prm,
-                 int SPB, int ntiles, unsigned mC, unsigned mV, float lgammaC, const float* __restrict__ gscale_ptr,
+                 int spw, int ntiles, float lgammaC, const float* __restrict__ gscale_ptr,
                  float* __restrict__ fused_out, float* __restrict__ grad_out, float* __restrict__ u_out,
                  float* __restrict__ ale_out, int* __restrict__ pred_out, float* __restrict__ loss_parts) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[32];
-  const int V = prm.V, C = prm.C, B = prm.B;
-  const int tid = threadIdx.x;
+  constexpr int V = VT;
+  const int C = prm.C, B = prm.B;
   const int VC = V * C;
+  const int SPB = spw * kEdlWarps;                 // samples per tile
+  float* te = smem;                                // [SPB*V*C] evidence -> gradient (in place)
+  float* tf = te + (((size_t)SPB * VC + 3) & ~(size_t)3);   // [SPB*C] fused evidence
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sl = lane / V, v = lane - sl * V;      // sample slot within the warp, view
+  const int base = sl * V;                         // first lane of this sample
+  const bool slot_ok = sl < spw;
   const float fC = (float)C;
-
-  EdlSmem sm;
-  {
-    float* p = smem;
-    const size_t Ecap = ((size_t)SPB * VC + 3) & ~(size_t)3, Rcap = (size_t)SPB * V;
-    sm.e = p; p += Ecap;
-    sm.p = p; p += Ecap;
-    sm.S = p; p += Rcap;
-    sm.iT = p; p += Rcap;
-    sm.om = p; p += Rcap;
-    sm.gy = p; p += Rcap;
-    sm.gA = p; p += Rcap;
-    sm.psiT = p; p += Rcap;
-    sm.rowK = p; p += Rcap;
-    sm.disc = p; p += Rcap;
-    sm.pd = p; p += (size_t)SPB * V * V;
-    sm.q = p; p += (size_t)SPB * V * V;
-    sm.f = p; p += (size_t)SPB * C;
-    sm.t = p; p += (size_t)SPB * C;
-    sm.Sf = p; p += SPB;
-    sm.psiSf = p; p += SPB;
-    sm.y = reinterpret_cast<int*>(p);
-  }
 
   const float coef = prm.coef;
   const bool need_kl = coef != 0.f;
   const bool need_dc = prm.dc_weight != 0.f;
   const bool need_fused = fused_out || u_out || ale_out || pred_out;
-  const bool need_pd = need_dc || (prm.agg == DMF_AGG_DBF && need_fused);
+  const bool dbf = prm.agg == DMF_AGG_DBF;
+  const bool need_pd = need_dc || (dbf && need_fused);
   const bool need_loss = grad_out || loss_parts;
   const float w_edl = prm.inv_B_global / ((float)V * (float)V);
-  const float inv_vm1 = 1.0f / (float)max(1, V - 1);
+  const float inv_vm1 = 1.0f / (float)(V > 1 ? V - 1 : 1);
   const float w_dc = prm.dc_weight * prm.inv_B_global * inv_vm1;
   const float gs = (grad_out && gscale_ptr) ? __ldg(gscale_ptr) : 1.0f;
   float acc_edl = 0.f, acc_kl = 0.f, acc_dc = 0.f;
@@ -109,293 +66,226 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long b0 = (long long)tile * SPB;
     const int nS = (int)min((long long)SPB, (long long)B - b0);
-    const int E = nS * VC, R = nS * V;
-    const float* src = evid + b0 * VC;
-    const bool vec_in = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-
-    // ---- P0: tile -> registers (+ smem copy for the row / fusion phases)
-    float4 ev[kEdlEPT4];
-#pragma unroll
-    for (int k = 0; k < kEdlEPT4; ++k) {
-      const int i0 = (tid + k * kEdlThreads) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i0 + 3 < E && vec_in) {
-        v = __ldg(reinterpret_cast<const float4*>(src + i0));
+    const int E = nS * VC;
+    // ---- copy in (coalesced 128-bit)
+    {
+      const float* src = evid + b0 * VC;
+      if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int n4 = E >> 2;
+        for (int i = tid; i < n4; i += kEdlThreads)
+          reinterpret_cast<float4*>(te)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        for (int i = (n4 << 2) + tid; i < E; i += kEdlThreads) te[i] = __ldg(src + i);
       } else {
-        if (i0 + 0 < E) v.x = __ldg(src + i0 + 0);
-        if (i0 + 1 < E) v.y = __ldg(src + i0 + 1);
-        if (i0 + 2 < E) v.z = __ldg(src + i0 + 2);
-        if (i0 + 3 < E) v.w = __ldg(src + i0 + 3);
+        for (int i = tid; i < E; i += kEdlThreads) te[i] = __ldg(src + i);
       }
-      ev[k] = v;
-      if (i0 < E) *reinterpret_cast<float4*>(sm.e + i0) = v;     // Ecap is padded to a multiple of 4
-    }
-    for (int i = tid; i < nS; i += kEdlThreads) {
-      long long y = labels[b0 + i];
-      sm.y[i] = (int)min(max(y, 0LL), (long long)(C - 1));
     }
     __syncthreads();
 
-    // ---- P1: one thread per (sample, view) row: strength, psi / psi1 of S, alpha_y, S~
-    if (need_loss || need_pd) {
-      for (int r = tid; r < R; r += kEdlThreads) {
-        const int b = (int)__umulhi((unsigned)r, mV);
-        const float* er = sm.e + r * C;
-        float S = 0.f;
-        for (int c = 0; c < C; ++c) S += er[c] + 1.0f;
-        sm.S[r] = S;
-        const float iT = 1.0f / (S + 1e-8f);
-        sm.iT[r] = iT;
-        sm.om[r] = 1.0f - fC * iT;
-        if (need_loss) {
-          const float ay = er[sm.y[b]] + 1.0f;
-          const Gamma3 gS = gamma3_fast<false>(S);
-          const Gamma3 gyv = gamma3_fast<false>(ay);
-          acc_edl += gS.psi - gyv.psi;
-          sm.gy[r] = gS.psi1 - gyv.psi1;
-          float gA = gS.psi1;
-          if (need_kl) {
-            const float St = S - ay + 1.0f;
-            const Gamma3 gt = gamma3_fast<true>(St);
-            acc_kl += gt.lgam - lgammaC;
-            sm.psiT[r] = gt.psi;
-            gA -= coef * (St - fC) * gt.psi1;
-          }
-          sm.gA[r] = gA;
-        }
-      }
-      __syncthreads();
+    const int bs = warp * spw + sl;                // sample slot within the tile
+    const bool active = slot_ok && bs < nS;
+    // inactive lanes run the same instruction stream on a dummy row (row 0 of the tile) so that the
+    // full-mask shuffles stay convergent; they never store
+    float* row = te + (size_t)(active ? bs * V + v : 0) * C;
+    int y = 0;
+    if (active) {
+      const long long yl = labels[b0 + bs];
+      y = (int)min(max(yl, 0LL), (long long)(C - 1));
     }
 
-    // ---- P2: one thread per element: class-wise KL terms + EDL gradient (registers), projected probabilities
-    float4 gv[kEdlEPT4];
-#pragma unroll
-    for (int k = 0; k < kEdlEPT4; ++k) {
-      gv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int i0 = (tid + k * kEdlThreads) * 4;
-      if (i0 >= E) continue;
-      float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const int idx = i0 + h;
-        if (idx >= E) continue;
-        const int r = (int)__umulhi((unsigned)idx, mC);
-        const int c = idx - r * C;
-        const int b = (int)__umulhi((unsigned)r, mV);
-        const float al = f4_get(ev[k], h) + 1.0f;
-        if (need_loss) {
-          float g;
-          if (c == sm.y[b]) {
-            g = sm.gy[r];
-          } else if (need_kl) {
-            const float am1 = al - 1.0f;
-            const Gamma3 ga = gamma3_fast<true>(al);
-            acc_kl += am1 * (ga.psi - sm.psiT[r]) - ga.lgam;
-            g = fmaf(coef * am1, ga.psi1, sm.gA[r]);
-          } else {
-            g = sm.gA[r];
-          }
-          f4_set(gv[k], h, g * w_edl);
-        }
-        if (need_pd) f4_set(pv, h, al * sm.iT[r]);
+    // ---- row statistics
+    float S = 0.f;
+    for (int c = 0; c < C; ++c) S += row[c] + 1.0f;
+    const float iT = 1.0f / (S + 1e-8f);
+    const float om = 1.0f - fC * iT;
+    float gy = 0.f, gA = 0.f, psiT = 0.f;
+    if (need_loss) {
+      const float ay = row[y] + 1.0f;
+      const Gamma3 gS = gamma3_fast<false>(S);
+      const Gamma3 gyv = gamma3_fast<false>(ay);
+      if (active) acc_edl += gS.psi - gyv.psi;
+      gy = gS.psi1 - gyv.psi1;
+      gA = gS.psi1;
+      if (need_kl) {
+        const float St = S - ay + 1.0f;
+        const Gamma3 gt = gamma3_fast<true>(St);
+        if (active) acc_kl += gt.lgam - lgammaC;
+        psiT = gt.psi;
+        gA -= coef * (St - fC) * gt.psi1;
       }
-      if (need_pd) *reinterpret_cast<float4*>(sm.p + i0) = pv;
+    }
+    // statistics of the other views of this sample (lane base + (v + jj) % V)
+    float omj[V > 1 ? V - 1 : 1], iTj[V > 1 ? V - 1 : 1], Sj[V > 1 ? V - 1 : 1];
+    int srcl[V > 1 ? V - 1 : 1];
+#pragma unroll
+    for (int jj = 0; jj < V - 1; ++jj) {
+      int vj = v + jj + 1;
+      if (vj >= V) vj -= V;
+      srcl[jj] = base + vj;
+      omj[jj] = __shfl_sync(0xffffffffu, om, srcl[jj]);
+      iTj[jj] = __shfl_sync(0xffffffffu, iT, srcl[jj]);
+      Sj[jj] = __shfl_sync(0xffffffffu, S, srcl[jj]);
     }
 
-    // ---- P3: degree-of-conflict term (models/losses.py:161-187) and its gradient
-    if (need_pd) {
-      __syncthreads();
-      // one thread per (sample, unordered view pair): pd_ij and the sign-weighted sums q_ij, q_ji
-      const int npair = V * (V - 1) / 2;
-      for (int pi = tid; pi < nS * npair; pi += kEdlThreads) {
-        const int b = pi / npair;
-        int rem = pi - b * npair, i = 0;
-        while (rem >= V - 1 - i) { rem -= V - 1 - i; ++i; }
-        const int j = i + 1 + rem;
-        const float* pi_ = sm.p + (b * V + i) * C;
-        const float* pj_ = sm.p + (b * V + j) * C;
-        const float* ei_ = sm.e + (b * V + i) * C;
-        const float* ej_ = sm.e + (b * V + j) * C;
-        float pd = 0.f, qij = 0.f, qji = 0.f;
-        for (int c = 0; c < C; ++c) {
-          const float d = pi_[c] - pj_[c];
-          pd += fabsf(d);
-          const float sg = d > 0.f ? 1.0f : (d < 0.f ? -1.0f : 0.f);
-          qij = fmaf(sg, ei_[c] + 1.0f, qij);
-          qji = fmaf(-sg, ej_[c] + 1.0f, qji);
+    // ---- loop A: pairwise conflict sums (models/losses.py:161-187): pd_kj = 0.5 sum_c |p_k - p_j|,
+    //      q_kj = sum_c sign(p_kc - p_jc) alpha_kc
+    float pd[V > 1 ? V - 1 : 1], rowK = 0.f, disc = 1.0f;
+    if (need_pd && V > 1) {
+      float q[V - 1 > 0 ? V - 1 : 1];
+#pragma unroll
+      for (int jj = 0; jj < V - 1; ++jj) { pd[jj] = 0.f; q[jj] = 0.f; }
+#pragma unroll 2
+      for (int c = 0; c < C; ++c) {
+        const float al = row[c] + 1.0f;
+        const float p = al * iT;
+#pragma unroll
+        for (int jj = 0; jj < V - 1; ++jj) {
+          const float alj = __shfl_sync(0xffffffffu, al, srcl[jj]);
+          const float d = p - alj * iTj[jj];
+          pd[jj] += fabsf(d);
+          q[jj] = fmaf(sgn3(d), al, q[jj]);
         }
-        pd *= 0.5f;
-        sm.pd[(b * V + i) * V + j] = pd;
-        sm.pd[(b * V + j) * V + i] = pd;
-        sm.q[(b * V + i) * V + j] = qij;
-        sm.q[(b * V + j) * V + i] = qji;
       }
-      for (int d = tid; d < nS * V; d += kEdlThreads) { sm.pd[d * V + (d - (int)__umulhi((unsigned)d, mV) * V)] = 0.f; }
-      __syncthreads();
-    }
-    if (need_dc) {
-      for (int r = tid; r < R; r += kEdlThreads) {
-        const int b = (int)__umulhi((unsigned)r, mV), i = r - b * V;
-        float gu = 0.f, dcs = 0.f, dot = 0.f;
-        const float omi = sm.om[r];
+      float gu = 0.f, dcs = 0.f, dot = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < V - 1; ++jj) {
+        pd[jj] *= 0.5f;
+        gu += pd[jj] * omj[jj];
+        dcs += pd[jj] * (om * omj[jj]);
+        dot = fmaf(omj[jj], q[jj], dot);
+      }
+      dot *= om;
+      if (active && need_dc) acc_dc += dcs * inv_vm1;
+      rowK = (dot - 2.0f * gu * fC) * iT * iT;
+      if (dbf && need_fused) {  // utils.py:88-116: discount of this view
+        const float ui = fC / S;
+        // multiply in absolute view order j = 0..V-1 like the reference (bit-exact uncertainty rankings);
+        // the j == i factor is exactly 1 (pd_ii = 0)
+        float agree = 1.0f;
+#pragma unroll
         for (int j = 0; j < V; ++j) {
-          if (j == i) continue;
-          const float pd = sm.pd[r * V + j];
-          const float omj = sm.om[b * V + j];
-          gu += pd * omj;
-          dcs += pd * (omi * omj);
-          dot = fmaf(omj, sm.q[r * V + j], dot);
-        }
-        dot *= omi;
-        acc_dc += dcs * inv_vm1;
-        const float iT = sm.iT[r];
-        sm.rowK[r] = (dot - 2.0f * gu * fC) * iT * iT;
-      }
-      __syncthreads();
+          float pdj = 0.f, Sjj = S;
 #pragma unroll
-      for (int k = 0; k < kEdlEPT4; ++k) {
-        const int i0 = (tid + k * kEdlThreads) * 4;
-        if (i0 >= E) continue;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int idx = i0 + h;
-          if (idx >= E) continue;
-          const int r = (int)__umulhi((unsigned)idx, mC);
-          const int c = idx - r * C;
-          const int b = (int)__umulhi((unsigned)r, mV), kk = r - b * V;
-          const float pk = sm.p[idx];
-          float gp = 0.f;
-          for (int j = 0; j < V; ++j) {
-            if (j == kk) continue;
-            const int rj = b * V + j;
-            const float d = pk - sm.p[rj * C + c];
-            const float sg = d > 0.f ? 1.0f : (d < 0.f ? -1.0f : 0.f);
-            gp = fmaf(sg, sm.om[rj], gp);
-          }
-          gp *= sm.om[r];
-          f4_set(gv[k], h, f4_get(gv[k], h) + w_dc * (gp * sm.iT[r] - sm.rowK[r]));
+          for (int jj = 0; jj < V - 1; ++jj)
+            if (srcl[jj] - base == j) { pdj = pd[jj]; Sjj = Sj[jj]; }
+          const float uj = fC / Sjj;
+          const float dc = pdj * ((1.0f - ui) * (1.0f - uj));
+          agree *= powf(1.0f - dc * dc * dc, 0.33333334f);
         }
+        disc = agree;
       }
     }
 
-    // ---- P4: fused evidence + summaries
-    if (need_fused) {
-      if (prm.agg == DMF_AGG_DBF) {  // utils.py:88-116
-        for (int r = tid; r < R; r += kEdlThreads) {
-          const int b = (int)__umulhi((unsigned)r, mV);
-          const float ui = fC / sm.S[r];
-          float agree = 1.0f;
-          for (int j = 0; j < V; ++j) {
-            const float uj = fC / sm.S[b * V + j];
-            const float dc = sm.pd[r * V + j] * ((1.0f - ui) * (1.0f - uj));
-            agree *= powf(1.0f - dc * dc * dc, 0.33333334f);
-          }
-          sm.disc[r] = agree;
+    // ---- loop B: class-wise KL terms, gradient (written in place), fused evidence
+    float Sf = 0.f, best = 0.f, bestv = 0.f;
+    int arg = 0, argv = 0;
+    const float uS = fC / S;
+#pragma unroll 2
+    for (int c = 0; c < C; ++c) {
+      const float e = row[c];
+      const float al = e + 1.0f;
+      if (need_loss) {
+        float g;
+        if (need_kl) {
+          const float am1 = al - 1.0f;
+          const Gamma3 ga = gamma3_fast<true>(al);
+          const bool isy = c == y;
+          if (active && !isy) acc_kl += am1 * (ga.psi - psiT) - ga.lgam;
+          g = isy ? gy : fmaf(coef * am1, ga.psi1, gA);
+        } else {
+          g = (c == y) ? gy : gA;
         }
-        __syncthreads();
+        g *= w_edl;
+        if (need_dc && V > 1) {
+          const float p = al * iT;
+          float gp = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < V - 1; ++jj) {
+            const float alj = __shfl_sync(0xffffffffu, al, srcl[jj]);
+            const float d = p - alj * iTj[jj];
+            gp = fmaf(sgn3(d), omj[jj], gp);
+          }
+          g += w_dc * (gp * om * iT - rowK);
+        }
+        if (active && grad_out) row[c] = g * gs;
       }
-      for (int i = tid; i < nS * C; i += kEdlThreads) {
-        const int b = (int)__umulhi((unsigned)i, mC), c = i - b * C;
-        const float* eb = sm.e + (size_t)b * VC + c;
+      if (need_fused) {
+        // every lane of the sample forms the same fused value, summing the views in reference order
+        float term = e;
+        if (dbf) {
+          const float bel = (e / S) * disc;
+          const float unc = uS * disc + 1.0f - disc;
+          term = fC * bel / (unc + 1e-6f);
+        }
+        // sall = ((t0 + t1) + t2) + ...   d1 = (t1 + t2) + ...   (the reference's summation orders)
+        float t0 = 0.f, sall = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int vv = 0; vv < V; ++vv) {
+          const float tv = __shfl_sync(0xffffffffu, term, base + vv);
+          if (vv == 0) { t0 = tv; sall = tv; } else { sall += tv; d1 += tv; }
+        }
         float f;
         switch (prm.agg) {
-          case DMF_AGG_CML: {
-            f = 0.f;
-            for (int v = 0; v < V; ++v) f += eb[v * C];
-          } break;
-          case DMF_AGG_AVG: {
-            f = 0.f;
-            for (int v = 0; v < V; ++v) f += eb[v * C];
-            f = f / (float)V;
-          } break;
-          case DMF_AGG_JOINT: {
-            float d = 0.f;
-            for (int v = 1; v < V; ++v) d += eb[v * C];
-            f = 0.5f * eb[0] + 0.5f * d;
-          } break;
-          case DMF_AGG_DISENTANGLED: {
-            f = 0.f;
-            for (int v = 1; v < V; ++v) f += eb[v * C];
-          } break;
-          default: {  // DBF
-            f = 0.f;
-            for (int v = 0; v < V; ++v) {
-              const int r = b * V + v;
-              const float S = sm.S[r], d = sm.disc[r];
-              const float bel = (eb[v * C] / S) * d;
-              const float unc = (fC / S) * d + 1.0f - d;
-              f += fC * bel / (unc + 1e-6f);
-            }
-            f = f / (float)V;
-          } break;
+          case DMF_AGG_CML: f = sall; break;
+          case DMF_AGG_AVG: f = sall / (float)V; break;
+          case DMF_AGG_JOINT: f = 0.5f * t0 + 0.5f * d1; break;
+          case DMF_AGG_DISENTANGLED: f = d1; break;
+          default: f = sall / (float)V; break;
         }
-        sm.f[i] = f;
-        if (fused_out) fused_out[b0 * C + i] = f;
-      }
-      if (u_out || ale_out || pred_out) {
-        __syncthreads();
-        for (int b = tid; b < nS; b += kEdlThreads) {
-          const float* fb = sm.f + b * C;
-          float Sf = 0.f, best = fb[0];
-          int arg = 0;
-          for (int c = 0; c < C; ++c) {
-            Sf += fb[c] + 1.0f;
-            if (fb[c] > best) { best = fb[c]; arg = c; }
-          }
-          sm.Sf[b] = Sf;
-          if (u_out) u_out[b0 + b] = fC / Sf;
-          if (ale_out) sm.psiSf[b] = gamma3<false>(Sf + 1.0f).psi;
-          if (pred_out) {
-            int* po = pred_out + (b0 + b) * (V + 1);
-            for (int v = 0; v < V; ++v) {
-              const float* evp = sm.e + (b * V + v) * C;
-              float bv = evp[0];
-              int av = 0;
-              for (int c = 1; c < C; ++c)
-                if (evp[c] > bv) { bv = evp[c]; av = c; }
-              po[v] = av;
-            }
-            po[V] = arg;
-          }
-        }
-        if (ale_out) {
-          __syncthreads();
-          for (int i = tid; i < nS * C; i += kEdlThreads) {
-            const int b = (int)__umulhi((unsigned)i, mC);
-            const float al = sm.f[i] + 1.0f;
-            sm.t[i] = (al / sm.Sf[b]) * (gamma3<false>(al + 1.0f).psi - sm.psiSf[b]);
-          }
-          __syncthreads();
-          for (int b = tid; b < nS; b += kEdlThreads) {
-            float a = 0.f;
-            for (int c = 0; c < C; ++c) a += sm.t[b * C + c];
-            ale_out[b0 + b] = -a;
-          }
-        }
+        if (active && v == 0) tf[bs * C + c] = f;
+        Sf += f + 1.0f;
+        if (c == 0) { best = f; bestv = e; }
+        if (f > best) { best = f; arg = c; }
+        if (e > bestv) { bestv = e; argv = c; }
       }
     }
+    if (need_fused && active) {
+      if (u_out && v == 0) u_out[b0 + bs] = fC / Sf;
+      if (pred_out) {
+        int* po = pred_out + (b0 + bs) * (V + 1);
+        po[v] = argv;
+        if (v == 0) po[V] = arg;
+      }
+    }
+    if (ale_out) {
+      // aleatoric = -sum_c (a_c/Sf) (psi(a_c + 1) - psi(Sf + 1)); the sample's lanes split the classes
+      __syncwarp();
+      const float psiSf = gamma3<false>(Sf + 1.0f).psi;
+      float a = 0.f;
+      if (active)
+        for (int c = v; c < C; c += V) {
+          const float al = tf[bs * C + c] + 1.0f;
+          a += (al / Sf) * (gamma3<false>(al + 1.0f).psi - psiSf);
+        }
+      float tot = 0.f;
+#pragma unroll
+      for (int vv = 0; vv < V; ++vv) tot += __shfl_sync(0xffffffffu, a, base + vv);
+      if (active && v == 0) ale_out[b0 + bs] = -tot;
+    }
+    __syncthreads();
 
-    // ---- P5: gradient straight from registers (one 128-bit store per group)
+    // ---- copy out (coalesced 128-bit): gradient tile, fused-evidence tile
     if (grad_out) {
       float* dst = grad_out + b0 * VC;
-      const bool vec_out = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-#pragma unroll
-      for (int k = 0; k < kEdlEPT4; ++k) {
-        const int i0 = (tid + k * kEdlThreads) * 4;
-        if (i0 >= E) continue;
-        float4 v = gv[k];
-        v.x *= gs; v.y *= gs; v.z *= gs; v.w *= gs;
-        if (i0 + 3 < E && vec_out) {
-          *reinterpret_cast<float4*>(dst + i0) = v;
-        } else {
-          if (i0 + 0 < E) dst[i0 + 0] = v.x;
-          if (i0 + 1 < E) dst[i0 + 1] = v.y;
-          if (i0 + 2 < E) dst[i0 + 2] = v.z;
-          if (i0 + 3 < E) dst[i0 + 3] = v.w;
-        }
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const int n4 = E >> 2;
+        for (int i = tid; i < n4; i += kEdlThreads) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(te)[i];
+        for (int i = (n4 << 2) + tid; i < E; i += kEdlThreads) dst[i] = te[i];
+      } else {
+        for (int i = tid; i < E; i += kEdlThreads) dst[i] = te[i];
       }
     }
-    __syncthreads();     // shared tiles are reused by the next tile of this CTA
+    if (fused_out) {
+      float* dst = fused_out + b0 * C;
+      const int n = nS * C;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const int n4 = n >> 2;
+        for (int i = tid; i < n4; i += kEdlThreads) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(tf)[i];
+        for (int i = (n4 << 2) + tid; i < n; i += kEdlThreads) dst[i] = tf[i];
+      } else {
+        for (int i = tid; i < n; i += kEdlThreads) dst[i] = tf[i];
+      }
+    }
+    __syncthreads();     // tiles are reused by the next tile of this CTA
   }
 
   if (loss_parts) {
@@ -426,39 +316,55 @@ __global__ void evidence_bwd_kernel(const float* __restrict__ h, const float* __
 
 using namespace dmf;
 
+template <int VT>
+static int launch_edl(const float* evid, const long long* labels, const dmf_edl_params* p, const float* gscale, float* fused,
+                      float* grad, float* u, float* ale, int* pred, float* loss_parts, cudaStream_t st) {
+  const int VC = VT * p->C;
+  int spw = 32 / VT;                                         // samples per warp: a sample never straddles warps
+  const int cap = kEdlTileFloats / (kEdlWarps * VC);         // ... and the tile has to fit
+  if (spw > cap) spw = cap;
+  DMF_REQUIRE(spw >= 1, "dmf_edl_fused: V*C=%d too large (max %d)", VC, kEdlTileFloats / kEdlWarps);
+  const int SPB = spw * kEdlWarps;
+  const size_t smem = ((((size_t)SPB * VC + 3) & ~(size_t)3) + (size_t)SPB * p->C + 4) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(edl_fused_kernel<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return fail((int)e, "dmf_edl_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  DMF_REQUIRE(smem <= 64 * 1024, "dmf_edl_fused: tile needs %zu bytes of shared memory", smem);
+  const long long tiles = ((long long)p->B + SPB - 1) / SPB;
+  DMF_REQUIRE(tiles < (1LL << 31), "dmf_edl_fused: batch too large");
+  // persistent CTAs: whole multiples of the SM count, as many as stay resident (4 by registers, smem permitting)
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  const long long capb = (long long)kNumSMs * per_sm;
+  const unsigned blocks = (unsigned)(tiles < capb ? tiles : capb);
+  edl_fused_kernel<VT><<<blocks, kEdlThreads, smem, st>>>(evid, labels, *p, spw, (int)tiles, lgammaf((float)p->C), gscale,
+                                                          fused, grad, u, ale, pred, loss_parts);
+  return launched("dmf_edl_fused");
+}
+
 extern "C" int dmf_edl_fused(const float* evid, const long long* labels, const dmf_edl_params* p, const float* gscale,
                              float* fused, float* grad, float* u, float* ale, int* pred, float* loss_parts,
                              dmf_stream_t s) {
   DMF_REQUIRE(evid && labels && p, "dmf_edl_fused: null argument");
   DMF_REQUIRE(p->B >= 0 && p->V >= 1 && p->C >= 2, "dmf_edl_fused: bad shape B=%d V=%d C=%d", p->B, p->V, p->C);
+  DMF_REQUIRE(p->V <= kEdlMaxV, "dmf_edl_fused: V=%d views; kernels are instantiated for V <= %d", p->V, kEdlMaxV);
   DMF_REQUIRE(p->agg >= DMF_AGG_CML && p->agg <= DMF_AGG_DBF, "dmf_edl_fused: unknown aggregation %d", p->agg);
   if (p->B == 0) return 0;
-  const int VC = p->V * p->C;
-  DMF_REQUIRE(VC * 4 <= kEdlMaxTile, "dmf_edl_fused: V*C=%d too large (max %d)", VC, kEdlMaxTile / 4);
-  int SPB = (kEdlMaxTile / VC) & ~3;
-  if (SPB > 256) SPB = 256;
-  const size_t smem = edl_smem_floats(SPB, p->V, p->C) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(edl_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) return fail((int)e, "dmf_edl_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+  cudaStream_t st = (cudaStream_t)s;
+  switch (p->V) {
+    case 1: return launch_edl<1>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
+    case 2: return launch_edl<2>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
+    case 3: return launch_edl<3>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
+    case 4: return launch_edl<4>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
+    case 5: return launch_edl<5>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
+    case 6: return launch_edl<6>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
+    case 7: return launch_edl<7>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
+    default: return launch_edl<8>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
   }
-  DMF_REQUIRE(smem <= 100 * 1024, "dmf_edl_fused: tile needs %zu bytes of shared memory", smem);
-  const long long tiles = ((long long)p->B + SPB - 1) / SPB;
-  DMF_REQUIRE(tiles < (1LL << 31), "dmf_edl_fused: batch too large");
-  // persistent CTAs: as many as can be resident (shared-memory bound), in whole multiples of the SM count
-  int per_sm = (int)((220 * 1024) / (smem + 1024));
-  if (per_sm > 4) per_sm = 4;          // register-bound residency (64 regs x 256 threads)
-  if (per_sm < 1) per_sm = 1;
-  const long long cap = (long long)kNumSMs * per_sm;
-  const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
-  const unsigned mC = (unsigned)((1ULL << 32) / (unsigned)p->C) + 1u;
-  const unsigned mV = (unsigned)((1ULL << 32) / (unsigned)p->V) + 1u;
-  edl_fused_kernel<<<blocks, kEdlThreads, smem, (cudaStream_t)s>>>(evid, labels, *p, SPB, (int)tiles, mC, mV,
-                                                                   lgammaf((float)p->C), gscale, fused, grad, u, ale, pred,
-                                                                   loss_parts);
-  return launched("dmf_edl_fused");
 }
 
 extern "C" int dmf_evidence_fwd(const float* h, float* e, long long n, dmf_stream_t s) {

@@ -9,6 +9,7 @@
 // operand traffic per tensor-core cycle and L2 traffic per FLOP both drop.  MMA issue: leader CTA only;
 // full barriers live in the leader (TMA of both CTAs completes them), consumer-release barriers are
 // multicast-committed to both CTAs, softmax warps of both CTAs arrive on the leader's p_full.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_pair.cuh"
@@ -38,7 +39,7 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                        const __grid_constant__ CUtensorMap tmBT, int Ma, int Nb, int D, int num_kb, float scale,
                        const float* __restrict__ lseA, const float* __restrict__ lseB, float coef,
                        const float* __restrict__ gscale, long long diag_offset, const uint16_t* __restrict__ Bm,
-                       long long ldb, float* __restrict__ dA, long long ldda, int accumulate) {
+                       long long ldb, float* __restrict__ dA, long long ldda, int accumulate, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smemA = smem;                                   // num_kb tiles (resident anchors)
@@ -121,6 +122,7 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tc::tc_fence_after_sync();
           const uint32_t a_addr = tc::smem_u32(smemA + kb * B3_TILE);
           const uint32_t b_addr = tc::smem_u32(smemB + stage * B3_HALF);
+          if (!(dbg & 4))
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc2::umma_ss2(d_tmem, tc::make_smem_desc(a_addr + k * 32, 16, 1024),
@@ -138,6 +140,7 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tc::tc_fence_after_sync();
         const uint32_t w_tmem = tmem_base + (uint32_t)((t & 1) * 128);
         const uint32_t v_addr = tc::smem_u32(smemV);
+        if (!(dbg & 2))
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // W columns j = 16k..16k+15: column half (k>>2) keeps its packed pairs at +64*(k>>2) + 8*(k&3)
@@ -172,6 +175,7 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       tc::mbar_wait(s_full + (t & 1), ((uint32_t)t >> 1) & 1);
       tc::tc_fence_after_sync();
       const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((t & 1) * 128 + ch * 64);
+      if (!(dbg & 1))
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
@@ -270,7 +274,9 @@ int dmf_infonce_bwd_bf16_tc3(const void* A, long long lda, int Ma, const float* 
   }
   const int pairs = (Ma + 255) / 256;
   dim3 grid(2 * pairs, (D + B3_OW - 1) / B3_OW);
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("DMF_BWD_DBG"); dbg = e ? atoi(e) : 0; }   // timing experiments only (wrong results)
   infonce_bwd_tc3_kernel<<<grid, B3_THREADS, smem, s>>>(tmA, tmB, tmBT, Ma, Nb, D, num_kb, scale, lseA, lseB, coef, gscale,
-                                                        diag_offset, (const uint16_t*)Bm, ldb, dA, ldda, accumulate);
+                                                        diag_offset, (const uint16_t*)Bm, ldb, dA, ldda, accumulate, dbg);
   return launched("dmf_infonce_bwd(bf16 pair)");
 }

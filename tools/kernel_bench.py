@@ -43,6 +43,14 @@ def main():
         f = lambda: check(lib.dmf_rowlse(ptr(b0), D, B, ptr(b1), D, B, D, scale, ptr(st[0]), ptr(st[1]), 0, ptr(st[2]), ptr(ws), wsb, 1, stream()))
         ms = timeit(f)
         print(f"rowlse_tc B={B} D={D}: {ms:.3f} ms  {2*B*B*D/ms/1e9:.1f} TFLOP/s executed")
+    if a.what in ("all", "fwdfused"):
+        rs = torch.zeros(3, B, device=dev); cs = torch.zeros(3, B, device=dev); dg = torch.zeros(3, B, device=dev)
+        for sym, Bm, tag in ((0, b1, "cross rows+cols"), (1, b0, "symmetric half window")):
+            f = lambda: check(lib.dmf_infonce_rowcol_sums(ptr(b0), D, B, ptr(Bm), D, B, D, scale, scale, sym, 0, ptr(rs[sym]), ptr(cs[sym]),
+                                                          0, ptr(dg[sym]), stream()))
+            ms = timeit(f)
+            fl = 2 * B * B * D * (0.5 if sym else 1.0)
+            print(f"rowcol_sums[{tag}] B={B} D={D}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s (algorithmic = executed)")
     if a.what in ("all", "bwd"):
         lse = torch.full((2, B), 3.0, device=dev)
         f = lambda: check(lib.dmf_rowlse(ptr(b0), D, B, ptr(b1), D, B, D, scale, ptr(st[0]), ptr(st[1]), 0, ptr(st[2]), ptr(ws), wsb, 1, stream()))

@@ -148,7 +148,7 @@ def run_reference(args, rank, world):
 def run_gpu(args, rank, world, local_rank):
     import disentagled_multimodal_fusion_b200 as pkg
     from disentagled_multimodal_fusion_b200 import ops, _lib
-    from disentagled_multimodal_fusion_b200.dp import FlatParams, shard_rows
+    from disentagled_multimodal_fusion_b200.dp import FlatParams, GraphedStep, shard_rows
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -178,17 +178,19 @@ def run_gpu(args, rank, world, local_rank):
     devin = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
-    def step(inp):
-        loss, logs = model(inp["x1"], inp["x2"], inp["v1"], inp["v2"])
+    noise_bufs = model.draw_noise(Bl, dev)          # fixed buffers, refilled in place every step (outside the graph)
+
+    def step(inp, capturable=False):
+        loss, logs = model(inp["x1"], inp["x2"], inp["v1"], inp["v2"], noise=noise_bufs)
         bb.zero_grad()
         loss.backward()
         bb.allreduce_grads()
-        bb.adam_step(1e-4)
+        bb.adam_step(1e-4, capturable=capturable)
         ploss, _, _, _ = probe.shared_step([inp["x1"], inp["x2"], inp["y"]])
         hd.zero_grad()
         ploss.backward()
         hd.allreduce_grads()
-        hd.adam_step(3e-3, weight_decay=1e-4, decoupled=True)
+        hd.adam_step(3e-3, weight_decay=1e-4, decoupled=True, capturable=capturable)
         return loss.detach() + ploss.detach()
 
     def barrier():
@@ -196,33 +198,70 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_marks = []
+
     def timed(nsteps, fn):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps)]
         s.record()
-        for _ in range(nsteps):
+        for i in range(nsteps):
             fn()
+            marks[i].record()
         e.record()
         barrier()
         ms = s.elapsed_time(e)
+        step_marks.append([round((s if i == 0 else marks[i - 1]).elapsed_time(marks[i]), 2) for i in range(nsteps)])
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
         return ms
 
+    # ---- warm-up (eager), launch count per step, per-kernel CUDA-event profile of one eager pass
     W = max(args.warmup, 3)
     for _ in range(W):
+        model.draw_noise(Bl, dev, out=noise_bufs)
         step(devin)
-    # ---- main number: device-resident inputs
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     l0 = _lib.launch_count()
     ops.PROFILE.clear()
     ops.PROFILE_ON = True
-    ms = timed(args.steps, lambda: step(devin))
+    prof_steps = 2
+    for _ in range(prof_steps):
+        model.draw_noise(Bl, dev, out=noise_bufs)
+        step(devin)
+    torch.cuda.synchronize()
     ops.PROFILE_ON = False
-    launches = _lib.launch_count() - l0
+    launches = (_lib.launch_count() - l0) // prof_steps
+    prof = ops.profile_summary()
+
+    # ---- the step as ONE CUDA graph (forward, backward, NCCL collectives, fused optimizers); the vMF noise is
+    #      redrawn in place before every replay by four launches outside the graph (host-side RNG counter)
+    launch_mode = "eager"
+    gstep = None
+    if args.graph != "off":
+        try:
+            gstep = GraphedStep(lambda: step(devin, capturable=True), warmup=2, stream=torch.cuda.current_stream())
+            launch_mode = "cuda_graph"
+        except Exception as ex:  # noqa: BLE001
+            if args.graph == "on":
+                raise
+            launch_mode = f"eager (graph capture failed: {type(ex).__name__})"
+            gstep = None
+            torch.cuda.synchronize()
+
+    def run_value():
+        model.draw_noise(Bl, dev, out=noise_bufs)
+        if gstep is not None:
+            gstep()
+        else:
+            step(devin)
+    for _ in range(2):
+        run_value()
+    # ---- main number: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(args.steps, run_value)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     value = Bg * args.steps / (ms / 1e3)
@@ -231,6 +270,17 @@ def run_gpu(args, rank, world, local_rank):
     copy_stream = torch.cuda.Stream()
     bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
+    gsteps = [None, None]
+    if gstep is not None:
+        try:
+            for i in range(2):
+                for k, v in host.items():
+                    bufs[i][k].copy_(v)
+                gsteps[i] = GraphedStep(lambda i=i: step(bufs[i], capturable=True), warmup=1, pool=gstep.pool(),
+                                        stream=torch.cuda.current_stream())
+        except Exception:  # noqa: BLE001
+            gsteps = [None, None]
+            torch.cuda.synchronize()
 
     def prefetch(i):
         with torch.cuda.stream(copy_stream):
@@ -245,7 +295,8 @@ def run_gpu(args, rank, world, local_rank):
         torch.cuda.current_stream().wait_event(ready[i])
         copy_stream.wait_stream(torch.cuda.current_stream())   # next copy must not overwrite a buffer in use
         prefetch(i ^ 1)
-        out = step(bufs[i])
+        model.draw_noise(Bl, dev, out=noise_bufs)
+        out = gsteps[i]() if gsteps[i] is not None else step(bufs[i])
         d2h.copy_(out.reshape(1), non_blocking=False)           # device->host read of the step's loss
         state["i"] = i ^ 1
     prefetch(0)
@@ -257,18 +308,18 @@ def run_gpu(args, rank, world, local_rank):
         return
     pk = peaks()
     # roofline of the dominant kernel (InfoNCE backward): algorithmic FLOPs per launch = 2*Ma*Nb*D
-    prof = ops.profile_summary()
     roof = None
     if "infonce_bwd" in prof:
         n, tot_ms = prof["infonce_bwd"]
         avg_ms = tot_ms / n
         flops = 2.0 * Bl * Bg * EMB
         ach = flops / (avg_ms * 1e-3) / 1e12
-        roof = {"kernel": "infonce_bwd_tc_kernel", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+        roof = {"kernel": "infonce_bwd_tc3_kernel", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": ach / pk["tf_sust"], "traffic": None, "launches": n, "avg_ms": avg_ms,
                 "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
-                "share_of_step": tot_ms / ms,
-                "other_kernels_ms_per_step": {k: v[1] / args.steps for k, v in prof.items()}}
+                "share_of_step": (tot_ms / prof_steps) / (ms / args.steps),
+                "timed_in": f"{prof_steps} eager steps after warm-up (CUDA events on the launching stream)",
+                "other_kernels_ms_per_step": {k: v[1] / prof_steps for k, v in prof.items()}}
     step_flops = 73.9e12 * (Bg / 65536.0) ** 2 if Bg else 0
     cpu = None
     if not args.no_cpu_baseline:
@@ -283,14 +334,15 @@ def run_gpu(args, rank, world, local_rank):
         "config": {"workload": "C5 DisentangledSSL 2x1024-d, hidden 512, embed 512, T=0.07 + 3-head evidential probe (C=10)",
                    "global_batch": Bg, "per_gpu_batch": Bl, "parallelism": f"dp{world}",
                    "l2": "inputs (1 GiB/step/GPU at dp1) and embeddings are larger than the 126 MB L2",
-                   "noise": "vMF noise drawn on device every step (dmf_vmf_draw)"},
+                   "noise": "vMF noise drawn on device every step (dmf_vmf_draw)", "launch": launch_mode},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
         "step_tflops_algorithmic": step_flops / 1e12,
         "step_frac_of_sustained_bf16": step_flops / (ms / args.steps * 1e-3) / 1e12 / (pk["tf_sust"] * world),
         "roofline": roof, "cpu_baseline": cpu,
+        "step_ms": {"value": step_marks[0], "e2e": step_marks[-1]},
     }
     print(json.dumps(line), flush=True)
 
@@ -305,6 +357,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step as one CUDA graph (auto: fall back to eager launches if capture fails)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -317,7 +371,11 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_gpu(args, rank, world, local_rank)
+        # the whole run lives on one non-default stream (see dp.GraphedStep: CUDA-graph capture of the backward
+        # pass needs every autograd leaf to have been touched on a capturable stream only)
+        main_stream = torch.cuda.Stream(device=local_rank)
+        with torch.cuda.stream(main_stream):
+            run_gpu(args, rank, world, local_rank)
     finally:
         if world > 1:
             dist.destroy_process_group()

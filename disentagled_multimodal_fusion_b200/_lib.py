@@ -98,6 +98,7 @@ _SIGS = {
     "dmf_evidence_fwd": ([c_p, c_p, c_ll, c_p], c_i),
     "dmf_evidence_bwd": ([c_p, c_p, c_p, c_p, c_ll, c_p], c_i),
     "dmf_adam_step": ([c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_f, c_p, c_p], c_i),
+    "dmf_adam_step_dev": ([c_p, c_p, c_p, c_p, c_ll, c_p, c_f, c_f, c_f, c_f, c_i, c_f, c_p, c_p], c_i),
     "dmf_fill_f32": ([c_p, c_ll, c_f, c_p], c_i),
 }
 

@@ -391,6 +391,39 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+
+// Graph-capturable variant: the 1-based step count and the learning rate live in DEVICE memory, so a captured
+// CUDA graph of the whole training step can be replayed without re-baking host scalars.  state[0] = step count
+// (as float, exact up to 2^24), state[1] = learning rate.  The bias corrections are formed per thread with
+// exp2/log2 in double precision of the same quantities torch uses; adam_tick_kernel bumps the count afterwards.
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long long n, const float* __restrict__ state, float beta1,
+                                float beta2, float eps, float wd, int decoupled, float gscale,
+                                uint16_t* __restrict__ pb) {
+  const double step = (double)state[0] + 1.0;
+  const float lr = state[1];
+  const double bc1 = 1.0 - pow((double)beta1, step);
+  const double bc2 = 1.0 - pow((double)beta2, step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    float gi = g[i] * gscale;
+    if (wd != 0.f) {
+      if (decoupled) pi *= (1.0f - lr * wd);
+      else gi = fmaf(wd, pi, gi);
+    }
+    float mi = m[i], vi = v[i];
+    mi = mi + (gi - mi) * (1.0f - beta1);
+    vi = vi * beta2 + (1.0f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+    pi = pi - step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (pb) pb[i] = f2bf(pi);
+  }
+}
+__global__ void adam_tick_kernel(float* state) { state[0] += 1.0f; }
+
 __global__ void fill_kernel(float* __restrict__ p, long long n, float value) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     p[i] = value;
@@ -654,6 +687,19 @@ extern "C" int dmf_adam_step(float* p, const float* g, float* m, float* v, long 
   adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, decoupled, step_size,
                                                         inv_bc2_sqrt, grad_scale, p_bf16);
   return launched("dmf_adam_step");
+}
+
+extern "C" int dmf_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float* state, float beta1,
+                                 float beta2, float eps, float wd, int decoupled, float grad_scale, uint16_t* p_bf16,
+                                 dmf_stream_t s) {
+  DMF_REQUIRE(p && g && m && v && state && n >= 0, "dmf_adam_step_dev: bad arguments");
+  if (n == 0) return 0;
+  adam_dev_kernel<<<grid_for(n), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, state, beta1, beta2, eps, wd, decoupled,
+                                                            grad_scale, p_bf16);
+  int rc = launched("dmf_adam_step_dev");
+  if (rc) return rc;
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)s>>>(state);
+  return launched("dmf_adam_step_dev(tick)");
 }
 extern "C" int dmf_fill_f32(float* p, long long n, float value, dmf_stream_t s) {
   DMF_REQUIRE(p && n >= 0, "dmf_fill_f32: bad arguments");

@@ -63,6 +63,10 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int m0 = blockIdx.x * 128;
   const int d0 = blockIdx.y * B3_OW;
   const int ntiles = (Nb + 127) / 128;
+  // rotate the column-tile order per cluster so that the 74 resident clusters do not all hit the same L2 lines
+  // at the same time (the whole column set is re-read by every cluster)
+  const int trot = (dbg & 8) ? 0 : (int)(((long long)(blockIdx.x >> 1) * 37 + blockIdx.y * 17) % ntiles);
+  auto tile_of = [&](int t) { int x = t + trot; return x >= ntiles ? x - ntiles : x; };
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
@@ -93,7 +97,7 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(empty_bar + stage, phase ^ 1);
           if (leader) tc::mbar_expect_tx(full_bar + stage, 2 * B3_HALF);
-          tc2::tma_load_2d_pair(smemB + stage * B3_HALF, &tmB, kb * 64, t * 128 + (int)rank * 64, full_bar + stage);
+          tc2::tma_load_2d_pair(smemB + stage * B3_HALF, &tmB, kb * 64, tile_of(t) * 128 + (int)rank * 64, full_bar + stage);
           if (++stage == B3_STAGES) { stage = 0; phase ^= 1; }
         }
       };
@@ -103,8 +107,8 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (t + 1 < ntiles) load_b(t + 1);
         tc::mbar_wait(pv_done, ((uint32_t)t & 1) ^ 1);   // smemV free: PV(t-1) retired
         if (leader) tc::mbar_expect_tx(v_full, 4 * B3_TILE);
-        tc2::tma_load_2d_pair(smemV, &tmBT, t * 128, d0 + (int)rank * 128, v_full);
-        tc2::tma_load_2d_pair(smemV + B3_TILE, &tmBT, t * 128 + 64, d0 + (int)rank * 128, v_full);
+        tc2::tma_load_2d_pair(smemV, &tmBT, tile_of(t) * 128, d0 + (int)rank * 128, v_full);
+        tc2::tma_load_2d_pair(smemV + B3_TILE, &tmBT, tile_of(t) * 128 + 64, d0 + (int)rank * 128, v_full);
       }
     }
   } else if (warp == 1) {
@@ -165,7 +169,7 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const float ai = ex2f3(la2 - c0);
     const uint32_t p_full_leader = tc2::mapa(tc::smem_u32(p_full), 0);
     for (int t = 0; t < ntiles; ++t) {
-      const int j0 = t * 128;
+      const int j0 = tile_of(t) * 128;
       float* bs = bsm + (t & 1) * 128;
       if (st < 128) {
         const int j = j0 + st;

@@ -118,17 +118,19 @@ class DisentangledSSL(LightningModule):
         zsx1, zsx2, z1x1, z2x2 = self._encode([x1], [x2])
         return torch.cat([zsx1, zsx2], dim=1), [z1x1, z2x2]
 
-    def draw_noise(self, B, device):
-        """Noise of the four rsample() calls in the reference order (zs1, zs2, zsv1, zsv2)."""
+    def draw_noise(self, B, device, out=None):
+        """Noise of the four rsample() calls in the reference order (zs1, zs2, zsv1, zsv2).  ``out`` (device mode):
+        list of four (w, v) buffer pairs to refill in place."""
         D = self.embed_dim
         if self.noise_mode == "device":
             self.noise_seed += 1
-            return [ops.vmf_draw(B, D, self.vmfkappa, 0x5EED + self.noise_seed, i, device) for i in range(4)]
-        out = []
+            return [ops.vmf_draw(B, D, self.vmfkappa, 0x5EED + self.noise_seed, i, device, out=None if out is None else out[i])
+                    for i in range(4)]
+        res = []
         for _ in range(4):
             w, v = draw_vmf_noise(B, D, float(self.vmfkappa))
-            out.append((w.to(device, non_blocking=True), v.to(device, non_blocking=True)))
-        return out
+            res.append((w.to(device, non_blocking=True), v.to(device, non_blocking=True)))
+        return res
 
     # ---------- models/disentangledssl.py:82-160
     def forward(self, x1, x2, v1, v2, noise=None):

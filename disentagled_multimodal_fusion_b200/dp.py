@@ -46,6 +46,9 @@ class FlatParams:
             p.grad = self.grad[o:o + k].view_as(p.data)
             o += k
         self.step_count = 0
+        # device-resident optimizer state for CUDA-graph replay: (steps taken so far, learning rate)
+        self.state = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._lr_on_device = None
 
     def zero_grad(self):
         self.grad.zero_()
@@ -61,7 +64,51 @@ class FlatParams:
         if ws > 1:
             dist.all_reduce(self.grad)
 
-    def adam_step(self, lr: float, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False):
+    def adam_step(self, lr: float, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, capturable=False):
+        """Fused flat-buffer Adam / AdamW.  ``capturable=True`` keeps the step count and the learning rate in device
+        memory (``self.state``) so the call can sit inside a captured CUDA graph; set a new learning rate with
+        ``set_lr`` between replays."""
         from . import ops
+        if capturable:
+            if self._lr_on_device is None:
+                self.set_lr(lr)
+            ops.adam_step_flat_dev(self.flat, self.grad, self.m, self.v, self.state, betas, eps, weight_decay, decoupled)
+            return
         self.step_count += 1
         ops.adam_step_flat(self.flat, self.grad, self.m, self.v, lr, self.step_count, betas, eps, weight_decay, decoupled)
+
+    def set_lr(self, lr: float):
+        """Write the learning rate (and the host-side step count) into the device state; not capturable."""
+        self.state.copy_(torch.tensor([float(self.step_count), float(lr)], dtype=torch.float32))
+        self._lr_on_device = float(lr)
+
+
+class GraphedStep:
+    """A whole training step (forward, backward, NCCL collectives, fused optimizer) captured ONCE into a CUDA graph
+    and replayed: one graph launch per step instead of ~600 kernel launches, which is what keeps an 8-GPU strong-
+    scaling run (a few ms of GPU work per launch-bound phase) from being host-bound.  ``fn`` must read its inputs
+    from fixed device buffers and must not synchronise; anything that changes per step through HOST scalars (RNG
+    seeds, step counts, learning rates) has to live in device memory or run outside the graph."""
+
+    def __init__(self, fn, warmup: int = 2, pool=None, stream=None):
+        # Run the warm-up and the capture on ONE non-default stream.  Everything that touched the parameters
+        # before (eager steps, optimizer state) should have run on a non-default stream too: autograd replays
+        # each AccumulateGrad on the stream its node was created on, and a node created on the legacy default
+        # stream makes capture fail ("legacy stream would depend on a capturing stream").
+        side = stream if stream is not None else torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, pool=pool, stream=side):
+            self.out = fn()
+
+    def pool(self):
+        return self.graph.pool()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out

@@ -142,11 +142,15 @@ def colsum(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     return out
 
 
-def vmf_draw(rows: int, D: int, kappa: float, seed: int, offset: int, device) -> Tuple[Tensor, Tensor]:
-    """Device-side vMF noise (distribution-equal to the reference sampler, not stream-equal)."""
+def vmf_draw(rows: int, D: int, kappa: float, seed: int, offset: int, device, out=None) -> Tuple[Tensor, Tensor]:
+    """Device-side vMF noise (distribution-equal to the reference sampler, not stream-equal).  ``out`` = (w, v)
+    pre-allocated buffers to draw into (fixed addresses for CUDA-graph replay)."""
     L.require_device()
-    w = torch.empty(rows, 1, dtype=torch.float32, device=device)
-    v = torch.empty(rows, D - 1, dtype=torch.float32, device=device)
+    if out is None:
+        w = torch.empty(rows, 1, dtype=torch.float32, device=device)
+        v = torch.empty(rows, D - 1, dtype=torch.float32, device=device)
+    else:
+        w, v = out
     check(lib.dmf_vmf_draw(ptr(w), ptr(v), rows, D, float(kappa), seed, offset, stream()))
     return w, v
 
@@ -876,3 +880,11 @@ def adam_step_flat(p: Tensor, g: Tensor, m: Tensor, v: Tensor, lr: float, step: 
     L.require_device()
     check(lib.dmf_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, betas[0], betas[1], eps, weight_decay,
                             1 if decoupled else 0, step, grad_scale, 0, stream()))
+
+
+def adam_step_flat_dev(p: Tensor, g: Tensor, m: Tensor, v: Tensor, state: Tensor, betas=(0.9, 0.999), eps: float = 1e-8,
+                       weight_decay: float = 0.0, decoupled: bool = False, grad_scale: float = 1.0) -> None:
+    """Graph-capturable Adam/AdamW: ``state`` is a device float[2] = (steps taken so far, learning rate)."""
+    L.require_device()
+    check(lib.dmf_adam_step_dev(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(state), betas[0], betas[1], eps, weight_decay,
+                                1 if decoupled else 0, grad_scale, 0, stream()))

@@ -224,6 +224,11 @@ int dmf_evidence_bwd(const float* h, const float* e, const float* de, float* dh,
 int dmf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int decoupled, int step, float grad_scale,
                   uint16_t* p_bf16, dmf_stream_t s);
+/* Same update with the step count and learning rate in DEVICE memory (state[0] = number of steps taken so far,
+ * as a float; state[1] = learning rate), so that a CUDA graph holding the whole training step can be replayed:
+ * the kernel uses step = state[0] + 1 and a trailing 1-thread kernel increments state[0].                 */
+int dmf_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float* state, float beta1, float beta2,
+                      float eps, float weight_decay, int decoupled, float grad_scale, uint16_t* p_bf16, dmf_stream_t s);
 /* fill n floats with a value (buffer zeroing for the accumulate-style outputs) */
 int dmf_fill_f32(float* p, long long n, float value, dmf_stream_t s);
 

@@ -62,11 +62,17 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const bool leader = rank == 0;
   const int m0 = blockIdx.x * 128;
   const int d0 = blockIdx.y * B3_OW;
-  const int ntiles = (Nb + 127) / 128;
+  // column split (gridDim.z): this cluster covers tiles [tz0, tz0 + ntiles) of the column set and, when the
+  // set is split, accumulates its partial dA slice with red.add (the caller zeroes dA)
+  const int total_tiles = (Nb + 127) / 128;
+  const int tiles_per_split = (total_tiles + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int tz0 = blockIdx.z * tiles_per_split;
+  const int ntiles = max(0, min(total_tiles, tz0 + tiles_per_split) - tz0);
+  const bool split = gridDim.z > 1;
   // rotate the column-tile order per cluster so that the 74 resident clusters do not all hit the same L2 lines
   // at the same time (the whole column set is re-read by every cluster)
-  const int trot = (dbg & 8) ? 0 : (int)(((long long)(blockIdx.x >> 1) * 37 + blockIdx.y * 17) % ntiles);
-  auto tile_of = [&](int t) { int x = t + trot; return x >= ntiles ? x - ntiles : x; };
+  const int trot = (dbg & 8 || ntiles == 0) ? 0 : (int)(((long long)(blockIdx.x >> 1) * 37 + blockIdx.y * 17) % ntiles);
+  auto tile_of = [&](int t) { int x = t + trot; return tz0 + (x >= ntiles ? x - ntiles : x); };
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
@@ -223,7 +229,7 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (row < Ma && dbase < D) {
         const int nvalid = min(32, D - dbase);
         float* dst = dA + (long long)row * ldda + dbase;
-        const bool has_pos = pj >= 0 && pj < Nb;
+        const bool has_pos = pj >= 0 && pj < Nb && blockIdx.z == 0;   // the positive term is added by split 0 only
         const uint16_t* bp = has_pos ? Bm + pj * ldb + dbase : nullptr;
         if (nvalid == 32 && !accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -233,14 +239,21 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             o.y = (__uint_as_float(r[j + 1]) - (has_pos ? 2.0f * bf2f(bp[j + 1]) : 0.f)) * cg;
             o.z = (__uint_as_float(r[j + 2]) - (has_pos ? 2.0f * bf2f(bp[j + 2]) : 0.f)) * cg;
             o.w = (__uint_as_float(r[j + 3]) - (has_pos ? 2.0f * bf2f(bp[j + 3]) : 0.f)) * cg;
-            *reinterpret_cast<float4*>(dst + j) = o;
+            if (split)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+            else
+              *reinterpret_cast<float4*>(dst + j) = o;
           }
         } else {
-          for (int j = 0; j < nvalid; ++j) {
-            float v = __uint_as_float(r[j]);
-            if (has_pos) v -= 2.0f * bf2f(bp[j]);
-            v *= cg;
-            dst[j] = accumulate ? dst[j] + v : v;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nvalid) {
+              float v = __uint_as_float(r[j]);
+              if (has_pos) v -= 2.0f * bf2f(bp[j]);
+              v *= cg;
+              if (split) atomicAdd(dst + j, v);
+              else dst[j] = accumulate ? dst[j] + v : v;
+            }
           }
         }
       }
@@ -277,7 +290,28 @@ int dmf_infonce_bwd_bf16_tc3(const void* A, long long lda, int Ma, const float* 
     attr = true;
   }
   const int pairs = (Ma + 255) / 256;
-  dim3 grid(2 * pairs, (D + B3_OW - 1) / B3_OW);
+  const int slices = (D + B3_OW - 1) / B3_OW;
+  // Column split: when pairs * slices does not fill whole waves of the 74 resident clusters (small local batches
+  // of a data-parallel run), split the column set over gridDim.z; partial slices are accumulated with red.add.
+  int nsplit = 1;
+  const int total_tiles = (Nb + 127) / 128;
+  if (!accumulate) {
+    const int base = pairs * slices;
+    double best = (double)base / (double)(((base + 73) / 74) * 74);
+    for (int ns = 2; ns <= 16 && best < 0.97; ++ns) {
+      if (total_tiles / ns < 16) break;
+      const int items = base * ns;
+      const double eff = (double)items / (double)(((items + 73) / 74) * 74);
+      if (eff > best + 0.03) { best = eff; nsplit = ns; }
+    }
+    const int tps = (total_tiles + nsplit - 1) / nsplit;
+    nsplit = (total_tiles + tps - 1) / tps;
+  }
+  if (nsplit > 1) {
+    cudaError_t e = cudaMemset2DAsync(dA, (size_t)ldda * sizeof(float), 0, (size_t)D * sizeof(float), (size_t)Ma, s);
+    if (e != cudaSuccess) return fail((int)e, "dmf_infonce_bwd(bf16 pair): memset: %s", cudaGetErrorString(e));
+  }
+  dim3 grid(2 * pairs, slices, nsplit);
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("DMF_BWD_DBG"); dbg = e ? atoi(e) : 0; }   // timing experiments only (wrong results)
   infonce_bwd_tc3_kernel<<<grid, B3_THREADS, smem, s>>>(tmA, tmB, tmBT, Ma, Nb, D, num_kb, scale, lseA, lseB, coef, gscale,

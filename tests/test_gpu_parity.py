@@ -147,6 +147,34 @@ def test_infonce_bf16_vs_fp32_large(dmf, B, D):
     assert_close(outs["bf16"][4], outs["fp32"][4], 2e-2, "bf16 dz1")
 
 
+def test_infonce_bwd_column_split(dmf):
+    """A small local shard against a large gathered column set (the 8-GPU shape in miniature): the backward kernel
+    splits the columns over gridDim.z and accumulates with red.add; result vs the fp32 FFMA kernel."""
+    ops, Lb = dmf.ops, dmf._lib
+    gen = torch.Generator().manual_seed(77)
+    Bl, Bg, D, off = 1536, 8192, 256, 2048
+    z0 = torch.nn.functional.normalize(torch.randn(Bg, D, generator=gen), dim=-1).to(DEV)
+    z1 = torch.nn.functional.normalize(0.5 * z0.cpu() + 0.3 * torch.randn(Bg, D, generator=gen), dim=-1).to(DEV)
+    scale = 1 / 0.07
+    S = (z0.bfloat16().float() @ z1.bfloat16().float().T) * scale
+    lseA, lseB = torch.logsumexp(S, 1).contiguous(), torch.logsumexp(S, 0).contiguous()
+    one = torch.ones(1, device=DEV)
+    outs = []
+    for dt in (0, 1):
+        a = z0[off:off + Bl].contiguous()
+        if dt == 1:
+            a, bm = ops.cast_bf16(a), ops.cast_bf16(z1)
+            bt = ops.transpose_bf16(bm)
+        else:
+            a, bm, bt = z0.bfloat16().float()[off:off + Bl].contiguous(), z1.bfloat16().float().contiguous(), None
+        dz = torch.full((Bl, D), float("nan"), device=DEV)
+        Lb.check(Lb.lib.dmf_infonce_bwd(a.data_ptr(), D, Bl, lseA[off:].data_ptr(), bm.data_ptr(), D, Lb.ptr(bt),
+                                        bt.stride(0) if bt is not None else 0, Bg, lseB.data_ptr(), D, scale, scale / (2 * Bg),
+                                        one.data_ptr(), off, dz.data_ptr(), D, 0, dt, Lb.stream()))
+        outs.append(dz)
+    assert_close(outs[1], outs[0], 5e-3, "split-column bf16 backward vs fp32 kernel")
+
+
 def test_vmf(dmf):
     g = load_golden("vmf")
     e = T(g["e"], DEV, grad=True)

@@ -153,16 +153,21 @@ class DisentangledSSL(LightningModule):
         vv2 = torch.cat([noise[1][1], noise[3][1]], 0)
         Z1 = ops.vmf_rsample(E1, w1, vv1)
         Z2 = ops.vmf_rsample(E2, w2, vv2)
-        joint_loss, loss_x, loss_y = self.critic.pair(Z1[:B], Z2[:B], unit_norm=True)
-        joint_loss_v, loss_x_v, loss_y_v = self.critic.pair(Z1[B:], Z2[B:], unit_norm=True)
+        P1n, P2n = ops.row_normalize(P1), ops.row_normalize(P2)
+        # all four critic inputs exist now: launch their embedding all-gathers up front (asynchronous NCCL), so
+        # the gathers of calls 2-4 overlap the similarity tiles of call 1
+        pr = self.precision
+        pairs = [(Z1[:B], Z2[:B]), (Z1[B:], Z2[B:]), (P1n[:B], P1n[B:]), (P2n[:B], P2n[B:])]
+        pres = [ops.GatheredPair(a, b, pr) for a, b in pairs]
+        joint_loss, loss_x, loss_y = self.critic.pair(*pairs[0], unit_norm=True, pre=pres[0])
+        joint_loss_v, loss_x_v, loss_y_v = self.critic.pair(*pairs[1], unit_norm=True, pre=pres[1])
         joint_loss = 0.5 * (joint_loss + joint_loss_v)
         loss_x = 0.5 * (loss_x + loss_x_v)
         loss_y = 0.5 * (loss_y + loss_y_v)
         loss_shared = joint_loss
 
-        P1n, P2n = ops.row_normalize(P1), ops.row_normalize(P2)
-        specific_loss_x1, _, _ = self.critic.pair(P1n[:B], P1n[B:], unit_norm=True)
-        specific_loss_x2, _, _ = self.critic.pair(P2n[:B], P2n[B:], unit_norm=True)
+        specific_loss_x1, _, _ = self.critic.pair(*pairs[2], unit_norm=True, pre=pres[2])
+        specific_loss_x2, _, _ = self.critic.pair(*pairs[3], unit_norm=True, pre=pres[3])
         loss_specific = specific_loss_x1 + specific_loss_x2
 
         lmd = self.lmd_scheduler(self.iterations) if self.lmd_end_value > 0 else self.lmd_start_value

@@ -499,9 +499,36 @@ def grouped_mlp(xs: Sequence[Tensor], weights: Sequence[Sequence[Tensor]], biase
 # ----------------------------------------------------------------------------------------
 # K2  InfoNCE (SupConLoss default path, models/losses.py:17-101)
 # ----------------------------------------------------------------------------------------
+class GatheredPair:
+    """bf16 / fp32 copies of the two views of one critic call plus their all-gathered versions.  Creating it
+    LAUNCHES the NCCL all-gathers asynchronously (on NCCL's stream); ``wait()`` joins them into the current stream.
+    A module that knows all its critic inputs early (DisentangledSSL) creates the four pairs up front so that
+    the gathers of calls 2..4 overlap the tiles of call 1."""
+
+    def __init__(self, z0: Tensor, z1: Tensor, precision: str):
+        L.require_device()
+        z0, z1 = _f32c(z0.detach()), _f32c(z1.detach())
+        self.a0, self.a1 = (cast_bf16(z0), cast_bf16(z1)) if precision == "bf16" else (z0, z1)
+        self.works = []
+        if _dist_on():
+            world = dist.get_world_size()
+            Bl, D = z0.shape
+            self.g0 = torch.empty(Bl * world, D, dtype=self.a0.dtype, device=z0.device)
+            self.g1 = torch.empty(Bl * world, D, dtype=self.a1.dtype, device=z0.device)
+            self.works.append(dist.all_gather_into_tensor(self.g0, self.a0, async_op=True))
+            self.works.append(dist.all_gather_into_tensor(self.g1, self.a1, async_op=True))
+        else:
+            self.g0, self.g1 = self.a0, self.a1
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+
 class _InfoNCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z0, z1, temperature, precision, bound):
+    def forward(ctx, z0, z1, temperature, precision, bound, pre):
         L.require_device()
         z0, z1 = _f32c(z0), _f32c(z1)
         Bl, D = z0.shape
@@ -510,17 +537,10 @@ class _InfoNCE(torch.autograd.Function):
         rank = dist.get_rank() if world > 1 else 0
         Bg = Bl * world
         dt = 1 if precision == "bf16" else 0
-        if dt == 1:
-            a0, a1 = cast_bf16(z0), cast_bf16(z1)
-        else:
-            a0, a1 = z0, z1
-        if world > 1:        # embeddings all-gathered over NVLink so every rank sees global negatives
-            g0 = torch.empty(Bg, D, dtype=a0.dtype, device=dev)
-            g1 = torch.empty(Bg, D, dtype=a1.dtype, device=dev)
-            dist.all_gather_into_tensor(g0, a0)
-            dist.all_gather_into_tensor(g1, a1)
-        else:
-            g0, g1 = a0, a1
+        if pre is None:      # embeddings all-gathered over NVLink so every rank sees global negatives
+            pre = GatheredPair(z0, z1, precision)
+        pre.wait()
+        a0, a1, g0, g1 = pre.a0, pre.a1, pre.g0, pre.g1
         scale = 1.0 / temperature
         off = rank * Bl
         out3 = torch.zeros(3, dtype=torch.float32, device=dev)
@@ -600,17 +620,18 @@ class _InfoNCE(torch.autograd.Function):
             check(lib.dmf_infonce_bwd(ptr(a1), a1.stride(0), Bl, ptr(lse[1]), ptr(g0), g0.stride(0), ptr(g0T),
                                       g0T.stride(0) if g0T is not None else 0, Bg, ptr(lse_all[0]), D, scale, coef, ptr(gs),
                                       off, ptr(dz1), D, 0, dt, stream()))
-        return dz0, dz1, None, None, None
+        return dz0, dz1, None, None, None, None
 
 
 def infonce(z0: Tensor, z1: Tensor, temperature: float = 0.07, precision: str = "fp32",
-            unit_norm: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+            unit_norm: bool = False, pre: Optional["GatheredPair"] = None) -> Tuple[Tensor, Tensor, Tensor]:
     """(loss, loss_x, loss_y) of SupConLoss()(stack([z0,z1],1)) without the [2B,2B] logits.
     Under torch.distributed the negatives are global (embeddings all-gathered with NCCL).
     ``unit_norm=True`` asserts that the rows of z0 / z1 are L2-normalised (|s| <= 1/T): the bf16 path then runs
-    the fixed-shift row+column kernel (dmf_infonce_rowcol_sums) instead of four online-max passes."""
+    the fixed-shift row+column kernel (dmf_infonce_rowcol_sums) instead of four online-max passes.
+    ``pre`` = a GatheredPair built earlier from the same (z0, z1) (asynchronous all-gather already in flight)."""
     bound = (1.0 / float(temperature)) if unit_norm else None
-    out = _InfoNCE.apply(z0, z1, float(temperature), precision, bound)
+    out = _InfoNCE.apply(z0, z1, float(temperature), precision, bound, pre)
     return out[0], out[1].detach(), out[2].detach()
 
 

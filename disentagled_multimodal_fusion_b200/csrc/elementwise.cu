@@ -442,6 +442,22 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, long long lds, u
     dst[r * ldd + c] = f2bf(src[r * lds + c]);
   }
 }
+// 4 elements per thread (128-bit load, 64-bit store); requires cols % 4 == 0, lds % 4 == 0, ldd % 4 == 0 and
+// 16-byte / 8-byte aligned bases
+__global__ void cast_bf16_vec4_kernel(const float* __restrict__ src, long long lds, uint16_t* __restrict__ dst,
+                                      long long ldd, int rows, int cols4) {
+  const long long total = (long long)rows * cols4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cols4;
+    const int c = (int)(idx - r * cols4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * lds + c));
+    uint2 pk;
+    pk.x = (uint32_t)f2bf(v.x) | ((uint32_t)f2bf(v.y) << 16);
+    pk.y = (uint32_t)f2bf(v.z) | ((uint32_t)f2bf(v.w) << 16);
+    *reinterpret_cast<uint2*>(dst + r * ldd + c) = pk;
+  }
+}
 
 template <typename TIn>
 __global__ void transpose_to_bf16_kernel(const TIn* __restrict__ src, long long lds, uint16_t* __restrict__ dst,
@@ -712,6 +728,12 @@ extern "C" int dmf_cast_f32_to_bf16(const float* src, long long lds, uint16_t* d
                                     dmf_stream_t s) {
   DMF_REQUIRE(src && dst && rows >= 0 && cols >= 0, "dmf_cast_f32_to_bf16: bad arguments");
   if (rows == 0 || cols == 0) return 0;
+  if ((cols & 3) == 0 && (lds & 3) == 0 && (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    cast_bf16_vec4_kernel<<<grid_for((long long)rows * (cols / 4)), 256, 0, (cudaStream_t)s>>>(src, lds, dst, ldd, rows,
+                                                                                             cols / 4);
+    return launched("dmf_cast_f32_to_bf16");
+  }
   cast_bf16_kernel<<<grid_for((long long)rows * cols), 256, 0, (cudaStream_t)s>>>(src, lds, dst, ldd, rows, cols);
   return launched("dmf_cast_f32_to_bf16");
 }

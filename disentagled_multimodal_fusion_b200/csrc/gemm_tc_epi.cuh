@@ -44,6 +44,24 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& g, const uint32_t
   if (row0 >= g.M || nbase >= g.N) return;          // warp-uniform
   const int nvalid = min(32, g.N - nbase);
   const int mvalid = min(32, g.M - row0);
+  // ReLU-mask words of the whole chunk are fetched up front (8 independent 8-byte loads in flight) so the
+  // coalesced pass below pays ONE global-load latency per chunk instead of one per row group
+  const int c = (lane & 7) * 4;
+  const int rq = lane >> 3;
+  const bool full_n = nvalid == 32;
+  uint2 mk8[8];
+  bool mask_vec = false;
+  if (EPI == DMF_EPI_RELU_MASK) {
+    const uint16_t* mk0 = g.mask + (long long)(row0 + rq) * g.ldmask + nbase + c;
+    mask_vec = full_n && ((reinterpret_cast<uintptr_t>(mk0) & 7) == 0) && ((g.ldmask & 3) == 0);
+    if (mask_vec) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        mk8[it] = make_uint2(0x3F803F80u, 0x3F803F80u);
+        if (rq + 4 * it < mvalid) mk8[it] = __ldg(reinterpret_cast<const uint2*>(mk0 + (long long)(4 * it) * g.ldmask));
+      }
+    }
+  }
   // ---- phase 1: raw accumulators -> smem, one 144-byte row per lane
   float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiPitch);
 #pragma unroll
@@ -52,8 +70,6 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& g, const uint32_t
                           __uint_as_float(r[4 * j + 3]));
   __syncwarp();
   // ---- phase 2: coalesced pass, lane -> (row rr = lane/8 + 4*it, columns c = (lane%8)*4 .. +3)
-  const int c = (lane & 7) * 4;
-  const int rq = lane >> 3;
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if ((EPI == DMF_EPI_BIAS || EPI == DMF_EPI_BIAS_RELU) && g.bias && add_bias) {
     if (c + 0 < nvalid) b4.x = __ldg(g.bias + nbase + c + 0);
@@ -61,7 +77,6 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& g, const uint32_t
     if (c + 2 < nvalid) b4.z = __ldg(g.bias + nbase + c + 2);
     if (c + 3 < nvalid) b4.w = __ldg(g.bias + nbase + c + 3);
   }
-  const bool full_n = nvalid == 32;
   const bool need_back = g.out_t != nullptr && (EPI != DMF_EPI_NONE);   // T pass must see the post-epilogue values
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
@@ -73,15 +88,15 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& g, const uint32_t
     const long long grow = row0 + rr;
     if (EPI == DMF_EPI_RELU_MASK) {
       if (rvalid) {
-        const uint16_t* mk = g.mask + grow * g.ldmask + nbase + c;
-        if (full_n && ((reinterpret_cast<uintptr_t>(mk) & 7) == 0)) {
-          const uint2 m2 = __ldg(reinterpret_cast<const uint2*>(mk));
+        if (mask_vec) {
+          const uint2 m2 = mk8[it];
           // activation is post-ReLU bf16: keep the gradient where it is strictly positive
           if (!(bf2f((uint16_t)(m2.x & 0xFFFFu)) > 0.f)) v.x = 0.f;
           if (!(bf2f((uint16_t)(m2.x >> 16)) > 0.f)) v.y = 0.f;
           if (!(bf2f((uint16_t)(m2.y & 0xFFFFu)) > 0.f)) v.z = 0.f;
           if (!(bf2f((uint16_t)(m2.y >> 16)) > 0.f)) v.w = 0.f;
         } else {
+          const uint16_t* mk = g.mask + grow * g.ldmask + nbase + c;
           if (c + 0 < nvalid && !(bf2f(mk[0]) > 0.f)) v.x = 0.f;
           if (c + 1 < nvalid && !(bf2f(mk[1]) > 0.f)) v.y = 0.f;
           if (c + 2 < nvalid && !(bf2f(mk[2]) > 0.f)) v.z = 0.f;

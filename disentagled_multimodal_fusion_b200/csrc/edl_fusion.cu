@@ -28,9 +28,19 @@ constexpr int kEdlWarps = kEdlThreads / 32;
 constexpr int kEdlMaxV = 8;
 constexpr int kEdlTileFloats = 10752;   // evidence tile per CTA (42 KB): 64 samples at V*C = 168
 
-__device__ __forceinline__ float sgn3(float d) { return d > 0.f ? 1.0f : (d < 0.f ? -1.0f : 0.f); }
+// sign(d) * x for x >= 0 (alpha and 1-u are non-negative): copysign + a zero guard (3 instructions, no int->float)
+__device__ __forceinline__ float sgn_mul(float d, float x) {
+  const float t = __int_as_float((__float_as_int(x) & 0x7fffffff) | (__float_as_int(d) & (int)0x80000000));
+  return d == 0.f ? 0.f : t;
+}
 
-template <int VT>
+// MODE specialises the hot loops at compile time (the per-iteration uniform branches on runtime flags cost
+// ~10 BRA + dead selects per element, ncu source page of v3):
+//   0 = generic (any flag combination, eval outputs, DBF)      1 = train: loss + KL + conflict term, sum-type fusion
+//   2 = train: loss + KL, no conflict term, sum-type fusion
+enum { EDL_GENERIC = 0, EDL_TRAIN_DC = 1, EDL_TRAIN = 2 };
+
+template <int VT, int MODE>
 __global__ void __launch_bounds__(kEdlThreads, 4)
 edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ labels, dmf_edl_params prm,
                  int spw, int ntiles, float lgammaC, const float* __restrict__ gscale_ptr,
@@ -51,12 +61,12 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
   const float fC = (float)C;
 
   const float coef = prm.coef;
-  const bool need_kl = coef != 0.f;
-  const bool need_dc = prm.dc_weight != 0.f;
-  const bool need_fused = fused_out || u_out || ale_out || pred_out;
-  const bool dbf = prm.agg == DMF_AGG_DBF;
+  const bool need_kl = MODE != EDL_GENERIC ? true : coef != 0.f;
+  const bool need_dc = MODE == EDL_TRAIN_DC ? true : (MODE == EDL_TRAIN ? false : prm.dc_weight != 0.f);
+  const bool need_fused = MODE != EDL_GENERIC ? fused_out != nullptr : (fused_out || u_out || ale_out || pred_out);
+  const bool dbf = MODE != EDL_GENERIC ? false : prm.agg == DMF_AGG_DBF;
   const bool need_pd = need_dc || (dbf && need_fused);
-  const bool need_loss = grad_out || loss_parts;
+  const bool need_loss = MODE != EDL_GENERIC ? true : (grad_out || loss_parts);
   const float w_edl = prm.inv_B_global / ((float)V * (float)V);
   const float inv_vm1 = 1.0f / (float)(V > 1 ? V - 1 : 1);
   const float w_dc = prm.dc_weight * prm.inv_B_global * inv_vm1;
@@ -126,6 +136,75 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
       Sj[jj] = __shfl_sync(0xffffffffu, S, srcl[jj]);
     }
 
+    if (MODE != EDL_GENERIC) {
+      // ================= training fast path (compile-time flags) =================
+      // fused evidence of the sum-type rules first (the evidence tile is overwritten by the gradient below):
+      // the V lanes of a sample split the classes, each value summed over the views in reference order
+      if (fused_out != nullptr && active) {
+        const float* sb = te + (size_t)bs * VC;
+        for (int c = v; c < C; c += V) {
+          float t0 = sb[c], sall = t0, d1 = 0.f;
+#pragma unroll
+          for (int vv = 1; vv < V; ++vv) { const float tv = sb[vv * C + c]; sall += tv; d1 += tv; }
+          float f;
+          switch (prm.agg) {
+            case DMF_AGG_CML: f = sall; break;
+            case DMF_AGG_AVG: f = sall / (float)V; break;
+            case DMF_AGG_JOINT: f = 0.5f * t0 + 0.5f * d1; break;
+            default: f = d1; break;   // DISENTANGLED
+          }
+          tf[bs * C + c] = f;
+        }
+      }
+      __syncwarp();
+      // ONE pass over the classes: gamma triple, KL terms, EDL gradient and (MODE 1) the conflict sums; the part
+      // of the conflict gradient that needs the completed sums (rowK) is subtracted in a light second pass
+      constexpr bool kDC = MODE == EDL_TRAIN_DC && V > 1;
+      float pdv[V > 1 ? V - 1 : 1], qv[V > 1 ? V - 1 : 1];
+#pragma unroll
+      for (int jj = 0; jj < V - 1; ++jj) { pdv[jj] = 0.f; qv[jj] = 0.f; }
+      const float wg = w_edl * gs, wd = w_dc * gs * om * iT;
+#pragma unroll 2
+      for (int c = 0; c < C; ++c) {
+        const float al = row[c] + 1.0f;
+        const float am1 = al - 1.0f;
+        const Gamma3 ga = gamma3_fast<true>(al);
+        const bool isy = c == y;
+        const float klt = am1 * (ga.psi - psiT) - ga.lgam;
+        acc_kl += (active && !isy) ? klt : 0.f;
+        float g = (isy ? gy : fmaf(coef * am1, ga.psi1, gA)) * wg;
+        if (kDC) {
+          const float p = al * iT;
+          float gp = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < V - 1; ++jj) {
+            const float alj = __shfl_sync(0xffffffffu, al, srcl[jj]);
+            const float d = p - alj * iTj[jj];
+            pdv[jj] += fabsf(d);
+            qv[jj] += sgn_mul(d, al);
+            gp += sgn_mul(d, omj[jj]);
+          }
+          g = fmaf(wd, gp, g);
+        }
+        if (active) row[c] = g;
+      }
+      if (kDC) {
+        float gu = 0.f, dcs = 0.f, dot = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < V - 1; ++jj) {
+          const float pdh = 0.5f * pdv[jj];
+          gu += pdh * omj[jj];
+          dcs += pdh * (om * omj[jj]);
+          dot = fmaf(omj[jj], qv[jj], dot);
+        }
+        dot *= om;
+        if (active) acc_dc += dcs * inv_vm1;
+        const float kk = w_dc * gs * (dot - 2.0f * gu * fC) * iT * iT;
+        if (active)
+#pragma unroll 4
+          for (int c = 0; c < C; ++c) row[c] -= kk;
+      }
+    } else {
     // ---- loop A: pairwise conflict sums (models/losses.py:161-187): pd_kj = 0.5 sum_c |p_k - p_j|,
     //      q_kj = sum_c sign(p_kc - p_jc) alpha_kc
     float pd[V > 1 ? V - 1 : 1], rowK = 0.f, disc = 1.0f;
@@ -142,7 +221,7 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
           const float alj = __shfl_sync(0xffffffffu, al, srcl[jj]);
           const float d = p - alj * iTj[jj];
           pd[jj] += fabsf(d);
-          q[jj] = fmaf(sgn3(d), al, q[jj]);
+          q[jj] += sgn_mul(d, al);
         }
       }
       float gu = 0.f, dcs = 0.f, dot = 0.f;
@@ -202,7 +281,7 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
           for (int jj = 0; jj < V - 1; ++jj) {
             const float alj = __shfl_sync(0xffffffffu, al, srcl[jj]);
             const float d = p - alj * iTj[jj];
-            gp = fmaf(sgn3(d), omj[jj], gp);
+            gp += sgn_mul(d, omj[jj]);
           }
           g += w_dc * (gp * om * iT - rowK);
         }
@@ -232,13 +311,15 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
           default: f = sall / (float)V; break;
         }
         if (active && v == 0) tf[bs * C + c] = f;
-        Sf += f + 1.0f;
-        if (c == 0) { best = f; bestv = e; }
-        if (f > best) { best = f; arg = c; }
-        if (e > bestv) { bestv = e; argv = c; }
+        if (MODE == EDL_GENERIC) {
+          Sf += f + 1.0f;
+          if (c == 0) { best = f; bestv = e; }
+          if (f > best) { best = f; arg = c; }
+          if (e > bestv) { bestv = e; argv = c; }
+        }
       }
     }
-    if (need_fused && active) {
+    if (MODE == EDL_GENERIC && need_fused && active) {
       if (u_out && v == 0) u_out[b0 + bs] = fC / Sf;
       if (pred_out) {
         int* po = pred_out + (b0 + bs) * (V + 1);
@@ -246,7 +327,7 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
         if (v == 0) po[V] = arg;
       }
     }
-    if (ale_out) {
+    if (MODE == EDL_GENERIC && ale_out) {
       // aleatoric = -sum_c (a_c/Sf) (psi(a_c + 1) - psi(Sf + 1)); the sample's lanes split the classes
       __syncwarp();
       const float psiSf = gamma3<false>(Sf + 1.0f).psi;
@@ -261,6 +342,7 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
       for (int vv = 0; vv < V; ++vv) tot += __shfl_sync(0xffffffffu, a, base + vv);
       if (active && v == 0) ale_out[b0 + bs] = -tot;
     }
+    }   // generic path
     __syncthreads();
 
     // ---- copy out (coalesced 128-bit): gradient tile, fused-evidence tile
@@ -316,8 +398,8 @@ __global__ void evidence_bwd_kernel(const float* __restrict__ h, const float* __
 
 using namespace dmf;
 
-template <int VT>
-static int launch_edl(const float* evid, const long long* labels, const dmf_edl_params* p, const float* gscale, float* fused,
+template <int VT, int MODE>
+static int launch_edl_mode(const float* evid, const long long* labels, const dmf_edl_params* p, const float* gscale, float* fused,
                       float* grad, float* u, float* ale, int* pred, float* loss_parts, cudaStream_t st) {
   const int VC = VT * p->C;
   int spw = 32 / VT;                                         // samples per warp: a sample never straddles warps
@@ -328,7 +410,7 @@ static int launch_edl(const float* evid, const long long* labels, const dmf_edl_
   const size_t smem = ((((size_t)SPB * VC + 3) & ~(size_t)3) + (size_t)SPB * p->C + 4) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(edl_fused_kernel<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(edl_fused_kernel<VT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return fail((int)e, "dmf_edl_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -341,9 +423,22 @@ static int launch_edl(const float* evid, const long long* labels, const dmf_edl_
   if (per_sm < 1) per_sm = 1;
   const long long capb = (long long)kNumSMs * per_sm;
   const unsigned blocks = (unsigned)(tiles < capb ? tiles : capb);
-  edl_fused_kernel<VT><<<blocks, kEdlThreads, smem, st>>>(evid, labels, *p, spw, (int)tiles, lgammaf((float)p->C), gscale,
+  edl_fused_kernel<VT, MODE><<<blocks, kEdlThreads, smem, st>>>(evid, labels, *p, spw, (int)tiles, lgammaf((float)p->C), gscale,
                                                           fused, grad, u, ale, pred, loss_parts);
   return launched("dmf_edl_fused");
+}
+
+template <int VT>
+static int launch_edl(const float* evid, const long long* labels, const dmf_edl_params* p, const float* gscale, float* fused,
+                      float* grad, float* u, float* ale, int* pred, float* loss_parts, cudaStream_t st) {
+  // the training call (gradient and/or loss, annealed KL on, no eval outputs, sum-type fusion) gets loops
+  // specialised at compile time; everything else runs the generic instantiation
+  const bool train = (grad || loss_parts) && p->coef != 0.f && !u && !ale && !pred && p->agg != DMF_AGG_DBF;
+  if (train && p->dc_weight != 0.f && VT > 1)
+    return launch_edl_mode<VT, EDL_TRAIN_DC>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
+  if (train && p->dc_weight == 0.f)
+    return launch_edl_mode<VT, EDL_TRAIN>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
+  return launch_edl_mode<VT, EDL_GENERIC>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
 }
 
 extern "C" int dmf_edl_fused(const float* evid, const long long* labels, const dmf_edl_params* p, const float* gscale,

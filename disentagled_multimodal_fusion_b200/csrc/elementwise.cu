@@ -221,6 +221,76 @@ __global__ void vmf_draw_kernel(float* __restrict__ nw, float* __restrict__ nv, 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// device-side augmentation (utils.py:118-151): per row one of {add N(0, noise_scale^2) noise,
+// zero floor(D / drop_scale) distinct random columns, identity}, each with probability 1/3.  One warp per row,
+// Philox counter RNG.  Distribution-equal to the reference's numpy/torch host loop, not stream-equal.
+// The column subset is the set of the n_drop smallest of D iid uniform keys (a uniform random subset without
+// replacement); the key threshold is found by a 32-step bisection on the key value with warp-wide counts.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned aug_key(unsigned long long seed, unsigned long long row, int k) {
+  // stateless 32-bit key of (seed, row, column): two rounds of a 64-bit mix (splitmix64 finaliser)
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (row * 0x100000001B3ull + (unsigned long long)k + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (unsigned)((z ^ (z >> 31)) >> 32);
+}
+
+__global__ void augment_kernel(const float* __restrict__ X, long long ldx, float* __restrict__ Y, long long ldy, int rows,
+                               int D, float noise_scale, int n_drop, unsigned long long seed, unsigned long long offset,
+                               int* __restrict__ choice_out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, (unsigned long long)row * 32 + lane, offset, &st);
+  // per-row choice from lane 0's stream (unbiased: rejection of the top 2^32 mod 3 values)
+  unsigned r = 0;
+  if (lane == 0) {
+    do { r = curand(&st); } while (r >= 4294967295u - (4294967295u % 3u));
+    r %= 3u;
+  }
+  const int t = (int)__shfl_sync(0xffffffffu, r, 0);
+  if (choice_out && lane == 0) choice_out[row] = t;
+  const float* x = X + (long long)row * ldx;
+  float* y = Y + (long long)row * ldy;
+  if (t == 0) {
+    for (int k = lane; k < D; k += 32) y[k] = x[k] + noise_scale * curand_normal(&st);
+  } else if (t == 1 && n_drop > 0) {
+    const unsigned long long rs = seed ^ (offset * 0xD1B54A32D192ED03ull);
+    // smallest threshold thr with count(key < thr) >= n_drop  (bisection on the 32-bit key value)
+    unsigned lo = 0u, hi = 0xFFFFFFFFu;
+    while (lo < hi) {
+      const unsigned mid = lo + ((hi - lo) >> 1);
+      int cnt = 0;
+      for (int k = lane; k < D; k += 32) cnt += aug_key(rs, (unsigned long long)row, k) <= mid ? 1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (cnt >= n_drop) hi = mid; else lo = mid + 1u;
+    }
+    // keys <= lo are dropped; ties at the threshold (probability ~ D^2 / 2^32) are broken by column order
+    int below = 0;
+    for (int k = lane; k < D; k += 32) below += aug_key(rs, (unsigned long long)row, k) < lo ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    int ties_left = n_drop - below;
+    for (int k0 = 0; k0 < D; k0 += 32) {
+      const int k = k0 + lane;
+      const unsigned key = k < D ? aug_key(rs, (unsigned long long)row, k) : 0xFFFFFFFFu;
+      const bool tie = k < D && key == lo;
+      const unsigned tm = __ballot_sync(0xffffffffu, tie);
+      const int rank_in = __popc(tm & ((1u << lane) - 1u));
+      const bool drop = k < D && (key < lo || (tie && rank_in < ties_left));
+      if (k < D) y[k] = drop ? 0.f : x[k];
+      ties_left -= __popc(tm);
+      if (ties_left < 0) ties_left = 0;
+    }
+  } else {
+    for (int k = lane; k < D; k += 32) y[k] = x[k];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // DMVAE head
 // ------------------------------------------------------------------------------------------
@@ -645,6 +715,17 @@ extern "C" int dmf_vmf_draw(float* nw, float* nv, int rows, int D, float kappa, 
   if (rows == 0) return 0;
   vmf_draw_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(nw, nv, rows, D, kappa, seed, offset);
   return launched("dmf_vmf_draw");
+}
+
+
+extern "C" int dmf_augment(const float* X, long long ldx, float* Y, long long ldy, int rows, int D, float noise_scale,
+                           int drop_scale, unsigned long long seed, unsigned long long offset, int* choice_out,
+                           dmf_stream_t s) {
+  DMF_REQUIRE(X && Y && rows >= 0 && D >= 1 && drop_scale >= 1, "dmf_augment: bad arguments");
+  if (rows == 0) return 0;
+  augment_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(X, ldx, Y, ldy, rows, D, noise_scale, D / drop_scale, seed,
+                                                            offset, choice_out);
+  return launched("dmf_augment");
 }
 
 static int fill_views(ViewPtrs& P, const float* const* in, const float* const* in2, float* const* out, int N) {

@@ -203,8 +203,15 @@ class DisentangledSSL(LightningModule):
     def shared_step(self, batch):
         x1 = batch[0].float().cuda()
         x2 = batch[1].float().cuda()
-        v1 = augment_data(x1)
-        v2 = augment_data(x2)
+        if self.noise_mode == "device":
+            # the reference's augment_data is an O(B) host loop with per-row H2D copies; the device
+            # kernel draws the same distribution (not the same stream)
+            self.noise_seed += 1
+            v1 = ops.augment(x1, 0xA06 + self.noise_seed, 0)
+            v2 = ops.augment(x2, 0xA06 + self.noise_seed, 1)
+        else:
+            v1 = augment_data(x1)
+            v2 = augment_data(x2)
         return x1, x2, v1, v2
 
     def configure_optimizers(self):

@@ -173,6 +173,13 @@ int dmf_vmf_bwd(const float* E, long long lde, const float* noise_w, const float
 int dmf_vmf_draw(float* noise_w, float* noise_v, int rows, int D, float kappa, unsigned long long seed,
                  unsigned long long offset, dmf_stream_t s);
 
+/* Device-side augment_data (utils.py:118-151): per row, with probability 1/3 each, Y = X + N(0,
+ * noise_scale^2), Y = X with floor(D / drop_scale) distinct uniformly chosen columns zeroed, or Y = X.
+ * Distribution-equal to the reference's host loop (numpy choice + torch.randn), not stream-equal.
+ * choice_out (optional, [rows] int32) receives the per-row choice 0 / 1 / 2.                                  */
+int dmf_augment(const float* X, long long ldx, float* Y, long long ldy, int rows, int D, float noise_scale,
+                int drop_scale, unsigned long long seed, unsigned long long offset, int* choice_out, dmf_stream_t s);
+
 /* ------------------------------------------------------------------ DMVAE head + objectives
  * Replaces chunk/exp/randn_like/PoE/KL of models/dmvae.py:74-112,142-150,170-172.
  * stats [N][B,4e] (mu_s, lv_s, mu_p, lv_p), noise [2N+1][B,e] in the reference draw order.

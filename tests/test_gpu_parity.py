@@ -175,6 +175,33 @@ def test_infonce_bwd_column_split(dmf):
     assert_close(outs[1], outs[0], 5e-3, "split-column bf16 backward vs fp32 kernel")
 
 
+def test_device_augmentation_distribution(dmf):
+    """dmf_augment vs the contract of utils.augment_data (utils.py:118-151): per-row choice uniform over
+    {noise, drop, identity}; noise rows = x + N(0, 0.01^2); drop rows have exactly D // 10 zeroed columns chosen
+    uniformly; identity rows untouched; different seeds give different draws."""
+    B, D = 30000, 200
+    gen = torch.Generator().manual_seed(3)
+    x = (torch.rand(B, D, generator=gen) + 0.5).to(DEV)          # strictly positive: zeros can only come from drops
+    y, ch = dmf.ops.augment(x, seed=123, offset=0, return_choice=True)
+    ch = ch.long()
+    frac = torch.bincount(ch, minlength=3).float() / B
+    assert float((frac - 1 / 3).abs().max()) < 0.012, frac
+    d = (y - x)
+    ident, noise, drop = ch == 2, ch == 0, ch == 1
+    assert float(d[ident].abs().max()) == 0.0
+    nz = d[noise]
+    assert abs(float(nz.std()) - 0.01) < 2e-4 and abs(float(nz.mean())) < 1e-4
+    dropped = (y[drop] == 0)
+    assert torch.equal(dropped.sum(1), torch.full((int(drop.sum()),), D // 10, device=DEV))
+    assert float((y[drop][~dropped] - x[drop][~dropped]).abs().max()) == 0.0
+    colfreq = dropped.float().mean(0)                             # each column dropped with probability 1/10
+    assert float((colfreq - 0.1).abs().max()) < 0.02, float((colfreq - 0.1).abs().max())
+    y2, ch2 = dmf.ops.augment(x, seed=124, offset=0, return_choice=True)
+    assert float((ch2.long() != ch).float().mean()) > 0.5
+    y3 = dmf.ops.augment(x, seed=123, offset=0)
+    assert torch.equal(y3, y), "same seed must reproduce the draw"
+
+
 def test_vmf(dmf):
     g = load_golden("vmf")
     e = T(g["e"], DEV, grad=True)

@@ -102,23 +102,30 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      // whole warp, uniform control flow; one elected lane issues the TMA instructions
       int stage = 0;
       uint32_t phase = 0;
       for (int item = cluster_id; item < P.total_items; item += num_clusters) {
         const G2Item it = g2_decode(P, item);
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           tc::mbar_wait(empty_bar + stage, phase ^ 1);
-          if (leader) tc::mbar_expect_tx(full_bar + stage, 4 * G2_TILE);      // A + B-half of BOTH CTAs
-          tc2::tma_load_2d_pair(smemA + stage * G2_TILE, &P.tmA[it.gi], kb * 64, it.m0 + (int)rank * 128, full_bar + stage);
-          tc2::tma_load_2d_pair(smemB + stage * G2_TILE, &P.tmB[it.gi], kb * 64, it.n0 + (int)rank * 128, full_bar + stage);
+          if (tc::elect_one()) {
+            if (leader) tc::mbar_expect_tx(full_bar + stage, 4 * G2_TILE);      // A + B-half of BOTH CTAs
+            tc2::tma_load_2d_pair(smemA + stage * G2_TILE, &P.tmA[it.gi], kb * 64, it.m0 + (int)rank * 128, full_bar + stage);
+            tc2::tma_load_2d_pair(smemB + stage * G2_TILE, &P.tmB[it.gi], kb * 64, it.n0 + (int)rank * 128, full_bar + stage);
+          }
+          __syncwarp();
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
+      // whole warp, uniform control flow; one elected lane issues the tcgen05 instructions
       constexpr uint32_t idesc = tc::make_idesc_bf16(256, G2_BN, 0, 0);
+      const uint64_t adesc0 = tc::make_smem_desc(tc::smem_u32(smemA), 16, 1024);
+      const uint64_t bdesc0 = tc::make_smem_desc(tc::smem_u32(smemB), 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t n = 0;
@@ -131,16 +138,19 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           tc::mbar_wait(full_bar + stage, phase);
           tc::tc_fence_after_sync();
-          const uint32_t a_addr = tc::smem_u32(smemA + stage * G2_TILE);
-          const uint32_t b_addr = tc::smem_u32(smemB + stage * G2_TILE);
+          const uint64_t ad = adesc0 + (uint64_t)((stage * G2_TILE) >> 4);
+          const uint64_t bd = bdesc0 + (uint64_t)((stage * G2_TILE) >> 4);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc2::umma_ss2(d_tmem, tc::make_smem_desc(a_addr + k * 32, 16, 1024),
-                          tc::make_smem_desc(b_addr + k * 32, 16, 1024), idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
-          tc2::umma_commit2(empty_bar + stage);
+            for (int k = 0; k < 4; ++k)
+              tc2::umma_ss2(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+            tc2::umma_commit2(empty_bar + stage);
+          }
+          __syncwarp();
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
-        tc2::umma_commit2(acc_full + buf);
+        if (tc::elect_one()) tc2::umma_commit2(acc_full + buf);
+        __syncwarp();
       }
     }
   } else {

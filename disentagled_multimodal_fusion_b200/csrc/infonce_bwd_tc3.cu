@@ -95,33 +95,48 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t tmem_O = tmem_base + 256;   // S buffers at [0,128) and [128,256)
 
   if (warp == 0) {
-    if (lane == 0) {
-      if (leader) tc::mbar_expect_tx(a_full, 2 * num_kb * B3_TILE);      // bytes of BOTH CTAs
-      for (int kb = 0; kb < num_kb; ++kb) tc2::tma_load_2d_pair(smemA + kb * B3_TILE, &tmA, kb * 64, m0, a_full);
+    {
+      // whole warp, uniform control flow; one elected lane issues the TMA instructions
+      if (tc::elect_one()) {
+        if (leader) tc::mbar_expect_tx(a_full, 2 * num_kb * B3_TILE);      // bytes of BOTH CTAs
+        for (int kb = 0; kb < num_kb; ++kb) tc2::tma_load_2d_pair(smemA + kb * B3_TILE, &tmA, kb * 64, m0, a_full);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       auto load_b = [&](int t) {
+        const int jrow = tile_of(t) * 128 + (int)rank * 64;
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(empty_bar + stage, phase ^ 1);
-          if (leader) tc::mbar_expect_tx(full_bar + stage, 2 * B3_HALF);
-          tc2::tma_load_2d_pair(smemB + stage * B3_HALF, &tmB, kb * 64, tile_of(t) * 128 + (int)rank * 64, full_bar + stage);
+          if (tc::elect_one()) {
+            if (leader) tc::mbar_expect_tx(full_bar + stage, 2 * B3_HALF);
+            tc2::tma_load_2d_pair(smemB + stage * B3_HALF, &tmB, kb * 64, jrow, full_bar + stage);
+          }
+          __syncwarp();
           if (++stage == B3_STAGES) { stage = 0; phase ^= 1; }
         }
       };
       // consumption order of the MMA thread: S(0), S(1), PV(0), S(2), PV(1), ...
-      load_b(0);
+      if (ntiles > 0) load_b(0);
       for (int t = 0; t < ntiles; ++t) {
         if (t + 1 < ntiles) load_b(t + 1);
         tc::mbar_wait(pv_done, ((uint32_t)t & 1) ^ 1);   // smemV free: PV(t-1) retired
-        if (leader) tc::mbar_expect_tx(v_full, 4 * B3_TILE);
-        tc2::tma_load_2d_pair(smemV, &tmBT, tile_of(t) * 128, d0 + (int)rank * 128, v_full);
-        tc2::tma_load_2d_pair(smemV + B3_TILE, &tmBT, tile_of(t) * 128 + 64, d0 + (int)rank * 128, v_full);
+        if (tc::elect_one()) {
+          if (leader) tc::mbar_expect_tx(v_full, 4 * B3_TILE);
+          tc2::tma_load_2d_pair(smemV, &tmBT, tile_of(t) * 128, d0 + (int)rank * 128, v_full);
+          tc2::tma_load_2d_pair(smemV + B3_TILE, &tmBT, tile_of(t) * 128 + 64, d0 + (int)rank * 128, v_full);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
+      // whole warp, uniform control flow; one elected lane issues the tcgen05 instructions
       constexpr uint32_t idesc_s = tc::make_idesc_bf16(256, 128, 0, 0);
       constexpr uint32_t idesc_o = tc::make_idesc_bf16(256, B3_OW, 0, 0);
+      const uint64_t adesc0 = tc::make_smem_desc(tc::smem_u32(smemA), 16, 1024);
+      const uint64_t bdesc0 = tc::make_smem_desc(tc::smem_u32(smemB), 16, 1024);
+      const uint64_t vdesc0 = tc::make_smem_desc(tc::smem_u32(smemV), 16, 1024);
       tc::mbar_wait(a_full, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -131,17 +146,21 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(full_bar + stage, phase);
           tc::tc_fence_after_sync();
-          const uint32_t a_addr = tc::smem_u32(smemA + kb * B3_TILE);
-          const uint32_t b_addr = tc::smem_u32(smemB + stage * B3_HALF);
-          if (!(dbg & 4))
+          // descriptor start-address field is (byte address >> 4): advance by whole tiles / 32-byte K steps
+          const uint64_t ad = adesc0 + (uint64_t)((kb * B3_TILE) >> 4);
+          const uint64_t bd = bdesc0 + (uint64_t)((stage * B3_HALF) >> 4);
+          if (tc::elect_one()) {
+            if (!(dbg & 4)) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc2::umma_ss2(d_tmem, tc::make_smem_desc(a_addr + k * 32, 16, 1024),
-                        tc::make_smem_desc(b_addr + k * 32, 16, 1024), idesc_s, (kb | k) != 0 ? 1u : 0u);
-          tc2::umma_commit2(empty_bar + stage);
+              for (int k = 0; k < 4; ++k) tc2::umma_ss2(d_tmem, ad + 2 * k, bd + 2 * k, idesc_s, (kb | k) != 0 ? 1u : 0u);
+            }
+            tc2::umma_commit2(empty_bar + stage);
+          }
+          __syncwarp();
           if (++stage == B3_STAGES) { stage = 0; phase ^= 1; }
         }
-        tc2::umma_commit2(s_full + (t & 1));
+        if (tc::elect_one()) tc2::umma_commit2(s_full + (t & 1));
+        __syncwarp();
       };
       issue_s(0);
       for (int t = 0; t < ntiles; ++t) {
@@ -150,18 +169,22 @@ infonce_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tc::mbar_wait(v_full, (uint32_t)t & 1);
         tc::tc_fence_after_sync();
         const uint32_t w_tmem = tmem_base + (uint32_t)((t & 1) * 128);
-        const uint32_t v_addr = tc::smem_u32(smemV);
-        if (!(dbg & 2))
+        if (tc::elect_one()) {
+          if (!(dbg & 2)) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          // W columns j = 16k..16k+15: column half (k>>2) keeps its packed pairs at +64*(k>>2) + 8*(k&3)
-          const uint32_t a_t = w_tmem + (uint32_t)((k >> 2) * 64 + (k & 3) * 8);
-          const uint32_t off = (uint32_t)(k >> 2) * B3_TILE + (uint32_t)(k & 3) * 32;
-          tc2::umma_ts2(tmem_O, a_t, tc::make_smem_desc(v_addr + off, 16, 1024), idesc_o, (t | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 8; ++k) {
+              // W columns j = 16k..16k+15: column half (k>>2) keeps its packed pairs at +64*(k>>2) + 8*(k&3)
+              const uint32_t a_t = w_tmem + (uint32_t)((k >> 2) * 64 + (k & 3) * 8);
+              const uint64_t vd = vdesc0 + (uint64_t)((((k >> 2) * B3_TILE) + (k & 3) * 32) >> 4);
+              tc2::umma_ts2(tmem_O, a_t, vd, idesc_o, (t | k) != 0 ? 1u : 0u);
+            }
+          }
+          tc2::umma_commit2(pv_done);
         }
-        tc2::umma_commit2(pv_done);
+        __syncwarp();
       }
-      tc2::umma_commit2(acc_full);
+      if (tc::elect_one()) tc2::umma_commit2(acc_full);
+      __syncwarp();
     }
   } else {
     const int sw = warp - 2;                 // 0..7

@@ -54,6 +54,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp.  The MMA-issuing WARP runs its loops with uniform control flow and only the
+// tcgen05.mma / commit instructions are predicated on this: descriptors and addresses then live in uniform
+// registers.  (Issuing from `if (lane == 0)` made every operand thread-divergent: ptxas wrapped each
+// UTCHMMA in ~20 instructions of ELECT / R2UR.BROADCAST retry loops -- slower than a 64-cycle N=128 MMA.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* d) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(d)) : "memory");

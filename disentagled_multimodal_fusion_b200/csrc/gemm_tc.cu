@@ -77,37 +77,44 @@ gemm_bf16_tc_kernel(const __grid_constant__ TcGemmParams P) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      // whole warp, uniform control flow; one elected lane issues the TMA instructions
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         tc::mbar_wait(empty_bar + stage, phase ^ 1);
-        tc::mbar_expect_tx(full_bar + stage, 2 * TC_TILE_BYTES);
-        tc::tma_load_2d(smemA + stage * TC_TILE_BYTES, &P.tmA[gi], kb * TC_BK, m0, full_bar + stage);
-        tc::tma_load_2d(smemB + stage * TC_TILE_BYTES, &P.tmB[gi], kb * TC_BK, n0, full_bar + stage);
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(full_bar + stage, 2 * TC_TILE_BYTES);
+          tc::tma_load_2d(smemA + stage * TC_TILE_BYTES, &P.tmA[gi], kb * TC_BK, m0, full_bar + stage);
+          tc::tma_load_2d(smemB + stage * TC_TILE_BYTES, &P.tmB[gi], kb * TC_BK, n0, full_bar + stage);
+        }
+        __syncwarp();
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // whole warp, uniform control flow; one elected lane issues the tcgen05 instructions
       constexpr uint32_t idesc = tc::make_idesc_bf16(TC_BM, TC_BN, 0, 0);
+      const uint64_t adesc0 = tc::make_smem_desc(tc::smem_u32(smemA), 16, 1024);
+      const uint64_t bdesc0 = tc::make_smem_desc(tc::smem_u32(smemB), 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         tc::mbar_wait(full_bar + stage, phase);
         tc::tc_fence_after_sync();
-        const uint32_t a_addr = tc::smem_u32(smemA + stage * TC_TILE_BYTES);
-        const uint32_t b_addr = tc::smem_u32(smemB + stage * TC_TILE_BYTES);
+        const uint64_t off = (uint64_t)((stage * TC_TILE_BYTES) >> 4);
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t ad = tc::make_smem_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t bd = tc::make_smem_desc(b_addr + k * 32, 16, 1024);
-          tc::umma_ss(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k)
+            tc::umma_ss(tmem_base, adesc0 + off + 2 * k, bdesc0 + off + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc::umma_commit(empty_bar + stage);   // frees the smem stage when these MMAs retire
         }
-        tc::umma_commit(empty_bar + stage);   // frees the smem stage when these MMAs retire
+        __syncwarp();
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
-      tc::umma_commit(tmem_full);             // accumulator complete
+      if (tc::elect_one()) tc::umma_commit(tmem_full);             // accumulator complete
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;                   // TMEM lane quarter this warp may access

@@ -71,24 +71,34 @@ rowlse_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0 && ntiles > 0) {
-      if (leader) tc::mbar_expect_tx(a_full, 2 * num_kb * F2_TILE);        // bytes of BOTH CTAs
-      for (int kb = 0; kb < num_kb; ++kb) tc2::tma_load_2d_pair(smemA + kb * F2_TILE, &tmA, kb * 64, m0, a_full);
+    if (ntiles > 0) {
+      // whole warp, uniform control flow; one elected lane issues the TMA instructions
+      if (tc::elect_one()) {
+        if (leader) tc::mbar_expect_tx(a_full, 2 * num_kb * F2_TILE);        // bytes of BOTH CTAs
+        for (int kb = 0; kb < num_kb; ++kb) tc2::tma_load_2d_pair(smemA + kb * F2_TILE, &tmA, kb * 64, m0, a_full);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int j0 = (jt0 + t) * F2_BN + (int)rank * 128;               // this CTA's half of the tile
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(empty_bar + stage, phase ^ 1);
-          if (leader) tc::mbar_expect_tx(full_bar + stage, 2 * F2_TILE);
-          tc2::tma_load_2d_pair(smemB + stage * F2_TILE, &tmB, kb * 64, j0, full_bar + stage);
+          if (tc::elect_one()) {
+            if (leader) tc::mbar_expect_tx(full_bar + stage, 2 * F2_TILE);
+            tc2::tma_load_2d_pair(smemB + stage * F2_TILE, &tmB, kb * 64, j0, full_bar + stage);
+          }
+          __syncwarp();
           if (++stage == F2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0 && ntiles > 0) {
+    if (leader && ntiles > 0) {
+      // whole warp, uniform control flow; one elected lane issues the tcgen05 instructions
       constexpr uint32_t idesc = tc::make_idesc_bf16(256, F2_BN, 0, 0);
+      const uint64_t adesc0 = tc::make_smem_desc(tc::smem_u32(smemA), 16, 1024);
+      const uint64_t bdesc0 = tc::make_smem_desc(tc::smem_u32(smemB), 16, 1024);
       tc::mbar_wait(a_full, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -100,16 +110,18 @@ rowlse_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(full_bar + stage, phase);
           tc::tc_fence_after_sync();
-          const uint32_t a_addr = tc::smem_u32(smemA + kb * F2_TILE);
-          const uint32_t b_addr = tc::smem_u32(smemB + stage * F2_TILE);
+          const uint64_t ad = adesc0 + (uint64_t)((kb * F2_TILE) >> 4);
+          const uint64_t bd = bdesc0 + (uint64_t)((stage * F2_TILE) >> 4);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc2::umma_ss2(d_tmem, tc::make_smem_desc(a_addr + k * 32, 16, 1024),
-                          tc::make_smem_desc(b_addr + k * 32, 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
-          tc2::umma_commit2(empty_bar + stage);
+            for (int k = 0; k < 4; ++k) tc2::umma_ss2(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc2::umma_commit2(empty_bar + stage);
+          }
+          __syncwarp();
           if (++stage == F2_STAGES) { stage = 0; phase ^= 1; }
         }
-        tc2::umma_commit2(s_full + buf);
+        if (tc::elect_one()) tc2::umma_commit2(s_full + buf);
+        __syncwarp();
       }
     }
   } else {

@@ -287,21 +287,42 @@ def run_gpu(args, rank, world, local_rank):
             for k, v in host.items():
                 bufs[i][k].copy_(v, non_blocking=True)
             ready[i].record(copy_stream)
-    state = {"i": 0}
-    d2h = torch.empty(1, dtype=torch.float32).pin_memory()
+    state = {"i": 0, "losses": []}
+    d2h = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    d2h_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    d2h_pending = [False, False]
 
     def e2e_step():
+        # Every step: H2D of the NEXT batch on the copy stream (overlaps this step's compute), this step's
+        # graph launch, an asynchronous D2H copy of its loss into pinned memory, and the host READ of the
+        # previous step's loss (after its copy event) -- the usual one-step-lagged logging of a training loop,
+        # so the host never idles the GPU while it waits for a scalar.
         i = state["i"]
         torch.cuda.current_stream().wait_event(ready[i])
         copy_stream.wait_stream(torch.cuda.current_stream())   # next copy must not overwrite a buffer in use
         prefetch(i ^ 1)
         model.draw_noise(Bl, dev, out=noise_bufs)
         out = gsteps[i]() if gsteps[i] is not None else step(bufs[i])
-        d2h.copy_(out.reshape(1), non_blocking=False)           # device->host read of the step's loss
+        d2h[i].copy_(out.reshape(1), non_blocking=True)         # device->host read of the step's loss
+        d2h_ev[i].record()
+        d2h_pending[i] = True
+        j = i ^ 1
+        if d2h_pending[j]:
+            d2h_ev[j].synchronize()
+            state["losses"].append(float(d2h[j][0]))
+            d2h_pending[j] = False
         state["i"] = i ^ 1
+
+    def e2e_drain():
+        for j in range(2):
+            if d2h_pending[j]:
+                d2h_ev[j].synchronize()
+                state["losses"].append(float(d2h[j][0]))
+                d2h_pending[j] = False
     prefetch(0)
     e2e_step()
     ms_e2e = timed(args.steps, e2e_step)
+    e2e_drain()
     e2e_value = Bg * args.steps / (ms_e2e / 1e3)
 
     if rank != 0:

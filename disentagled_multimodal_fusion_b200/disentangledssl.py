@@ -159,32 +159,46 @@ class DisentangledSSL(LightningModule):
         pr = self.precision
         pairs = [(Z1[:B], Z2[:B]), (Z1[B:], Z2[B:]), (P1n[:B], P1n[B:]), (P2n[:B], P2n[B:])]
         pres = [ops.GatheredPair(a, b, pr) for a, b in pairs]
-        joint_loss, loss_x, loss_y = self.critic.pair(*pairs[0], unit_norm=True, pre=pres[0])
-        joint_loss_v, loss_x_v, loss_y_v = self.critic.pair(*pairs[1], unit_norm=True, pre=pres[1])
+        # data parallel: every critic call returns this rank's PARTIAL sums; they are all-reduced ONCE below
+        # (all combinations are linear and the gradients do not depend on the loss value)
+        dp = ops._dist_on()
+        kw = dict(unit_norm=True, reduce=not dp)
+        joint_loss, loss_x, loss_y = self.critic.pair(*pairs[0], pre=pres[0], **kw)
+        joint_loss_v, loss_x_v, loss_y_v = self.critic.pair(*pairs[1], pre=pres[1], **kw)
         joint_loss = 0.5 * (joint_loss + joint_loss_v)
         loss_x = 0.5 * (loss_x + loss_x_v)
         loss_y = 0.5 * (loss_y + loss_y_v)
         loss_shared = joint_loss
 
-        specific_loss_x1, _, _ = self.critic.pair(*pairs[2], unit_norm=True, pre=pres[2])
-        specific_loss_x2, _, _ = self.critic.pair(*pairs[3], unit_norm=True, pre=pres[3])
+        specific_loss_x1, _, _ = self.critic.pair(*pairs[2], pre=pres[2], **kw)
+        specific_loss_x2, _, _ = self.critic.pair(*pairs[3], pre=pres[3], **kw)
         loss_specific = specific_loss_x1 + specific_loss_x2
 
         lmd = self.lmd_scheduler(self.iterations) if self.lmd_end_value > 0 else self.lmd_start_value
 
-        def _ortho():
-            pr = self.precision
-            return 0.5 * (ops.ortho_loss(P1[:B], E1[:B], pr) + ops.ortho_loss(P2[:B], E2[:B], pr)) + \
-                0.5 * (ops.ortho_loss(P1[B:], E1[B:], pr) + ops.ortho_loss(P2[B:], E2[B:], pr))
         if lmd == 0:
             # reference default (lmd_start_value = lmd_end_value = 0): the term is logged but its weight is
-            # exactly zero, so its backward pass (two R x D x D GEMMs per call) is skipped
+            # exactly zero, so neither its backward pass nor autograd bookkeeping is needed: one grouped Gram
+            # launch + one all-reduce for the four calls (rows of P are already normalised for the critic)
             with torch.no_grad():
-                loss_ortho = _ortho()
+                E1n, E2n = ops.row_normalize(E1), ops.row_normalize(E2)
+                ov = ops.ortho_values_nograd([(P1n[:B], E1n[:B]), (P2n[:B], E2n[:B]), (P1n[B:], E1n[B:]), (P2n[B:], E2n[B:])],
+                                             self.precision)
+                loss_ortho = 0.5 * (ov[0] + ov[1]) + 0.5 * (ov[2] + ov[3])
             loss = 2 * loss_shared / (1 + self.a) + self.a * loss_specific / (1 + self.a)
         else:
-            loss_ortho = _ortho()
+            pr = self.precision
+            loss_ortho = 0.5 * (ops.ortho_loss(P1[:B], E1[:B], pr) + ops.ortho_loss(P2[:B], E2[:B], pr)) + \
+                0.5 * (ops.ortho_loss(P1[B:], E1[B:], pr) + ops.ortho_loss(P2[B:], E2[B:], pr))
             loss = 2 * loss_shared / (1 + self.a) + self.a * loss_specific / (1 + self.a) + lmd * loss_ortho
+        if dp:
+            import torch.distributed as dist
+            # ortho is already global (its Gram was all-reduced); the InfoNCE terms are partial sums
+            part = loss - lmd * loss_ortho if lmd != 0 else loss
+            vals = torch.stack([part.detach(), loss_shared.detach(), loss_x, loss_y, loss_specific.detach()])
+            dist.all_reduce(vals)
+            loss = loss + (vals[0] - part.detach())        # global value, local gradient
+            loss_shared, joint_loss, loss_x, loss_y, loss_specific = vals[1], vals[1], vals[2], vals[3], vals[4]
         # device scalars (the reference does seven .item() syncs here)
         logs = {'loss': loss.detach(), 'shared': loss_shared.detach(), 'clip': joint_loss.detach(),
                 'loss_x': loss_x, 'loss_y': loss_y, 'specific': loss_specific.detach(),

@@ -542,7 +542,7 @@ class GatheredPair:
 
 class _InfoNCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z0, z1, temperature, precision, bound, pre):
+    def forward(ctx, z0, z1, temperature, precision, bound, pre, reduce):
         L.require_device()
         z0, z1 = _f32c(z0), _f32c(z1)
         Bl, D = z0.shape
@@ -603,10 +603,11 @@ class _InfoNCE(torch.autograd.Function):
             check(lib.dmf_infonce_finalize(ptr(st[6]), ptr(st[7]), ptr(st[9]), ptr(st[10]), ptr(st[8]), ptr(st[11]), Bl,
                                            1.0 / (2 * Bg), 1.0 / Bg, 1, ptr(lse[1]), ptr(out3), stream()))
         if world > 1:
-            dist.all_reduce(out3)
-            lse_all = torch.empty(2, Bg, dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(lse_all[0], lse[0])
-            dist.all_gather_into_tensor(lse_all[1], lse[1])
+            if reduce:
+                dist.all_reduce(out3)
+            gath = torch.empty(world, 2, Bl, dtype=torch.float32, device=dev)      # one collective for both views
+            dist.all_gather_into_tensor(gath, lse)
+            lse_all = gath.permute(1, 0, 2).reshape(2, Bg).contiguous()
         else:
             lse_all = lse
         ctx.save_for_backward(a0, a1, g0, g1, lse, lse_all)
@@ -634,18 +635,20 @@ class _InfoNCE(torch.autograd.Function):
             check(lib.dmf_infonce_bwd(ptr(a1), a1.stride(0), Bl, ptr(lse[1]), ptr(g0), g0.stride(0), ptr(g0T),
                                       g0T.stride(0) if g0T is not None else 0, Bg, ptr(lse_all[0]), D, scale, coef, ptr(gs),
                                       off, ptr(dz1), D, 0, dt, stream()))
-        return dz0, dz1, None, None, None, None
+        return dz0, dz1, None, None, None, None, None
 
 
 def infonce(z0: Tensor, z1: Tensor, temperature: float = 0.07, precision: str = "fp32",
-            unit_norm: bool = False, pre: Optional["GatheredPair"] = None) -> Tuple[Tensor, Tensor, Tensor]:
+            unit_norm: bool = False, pre: Optional["GatheredPair"] = None, reduce: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
     """(loss, loss_x, loss_y) of SupConLoss()(stack([z0,z1],1)) without the [2B,2B] logits.
     Under torch.distributed the negatives are global (embeddings all-gathered with NCCL).
     ``unit_norm=True`` asserts that the rows of z0 / z1 are L2-normalised (|s| <= 1/T): the bf16 path then runs
     the fixed-shift row+column kernel (dmf_infonce_rowcol_sums) instead of four online-max passes.
-    ``pre`` = a GatheredPair built earlier from the same (z0, z1) (asynchronous all-gather already in flight)."""
+    ``pre`` = a GatheredPair built earlier from the same (z0, z1) (asynchronous all-gather already in flight).
+    ``reduce=False`` (data parallel only) returns this rank's PARTIAL sums of the three scalars -- the caller
+    all-reduces them later, once for all its critic calls (the gradients do not depend on the loss value)."""
     bound = (1.0 / float(temperature)) if unit_norm else None
-    out = _InfoNCE.apply(z0, z1, float(temperature), precision, bound, pre)
+    out = _InfoNCE.apply(z0, z1, float(temperature), precision, bound, pre, reduce)
     return out[0], out[1].detach(), out[2].detach()
 
 
@@ -774,6 +777,45 @@ class _OrthoLoss(torch.autograd.Function):
         check(lib.dmf_row_normalize_bwd(ptr(n1), D, ptr(i1), ptr(dn1), D, R, D, ptr(d1), D, 0, stream()))
         check(lib.dmf_row_normalize_bwd(ptr(ns), D, ptr(i2), ptr(dns), D, R, D, ptr(d2), D, 0, stream()))
         return d1, d2, None
+
+
+@torch.no_grad()
+def ortho_values_nograd(pairs: Sequence[Tuple[Tensor, Tensor]], precision: str = "fp32") -> Tensor:
+    """Values of ``ortho_loss`` for several (z1, zs) pairs whose rows are ALREADY L2-normalised, without autograd:
+    one grouped split-K Gram launch (bf16 path) for all pairs, one all-reduce, one reduction.  Used by
+    DisentangledSSL when the ortho weight is exactly zero (the term is only logged)."""
+    L.require_device()
+    n = len(pairs)
+    R, D = pairs[0][0].shape
+    dev = pairs[0][0].device
+    grams = torch.zeros(n, D, D, dtype=torch.float32, device=dev)
+    if precision == "bf16" and R >= 512 and D >= 128:
+        Rp = (R + 7) // 8 * 8
+        descs = []
+        for i, (a, b) in enumerate(pairs):
+            aT = torch.empty(D, Rp, dtype=torch.bfloat16, device=dev)
+            bT = torch.empty(D, Rp, dtype=torch.bfloat16, device=dev)
+            cast_dual_bf16(a, None, 0, aT, Rp)
+            cast_dual_bf16(b, None, 0, bT, Rp)
+            descs.append(dict(A=aT, lda=Rp, B=bT, ldb=Rp, out_f32=grams[i], ldo_f32=D, M=D, N=D, K=R, split_k=0))
+        gemm_tc(descs, L.EPI_NONE)
+    else:
+        for i, (a, b) in enumerate(pairs):
+            a, b = _f32c(a), _f32c(b)
+            chunks = max(1, min(64, R // 512))
+            rows = (R + chunks - 1) // chunks
+            chunks = (R + rows - 1) // rows
+            part = torch.empty(chunks, D * D, dtype=torch.float32, device=dev)
+            descs = []
+            for c in range(chunks):
+                r0 = c * rows
+                rc = min(rows, R - r0)
+                descs.append(dict(A=a[r0:], a_rs=1, a_cs=D, B=b[r0:], b_rs=D, b_cs=1, C=part[c], ldc=D, M=D, N=D, K=rc))
+            gemm_f32(descs, L.EPI_NONE)
+            colsum(part, grams[i].view(-1))
+    if _dist_on():
+        dist.all_reduce(grams)
+    return torch.sqrt((grams * grams).sum(dim=(1, 2)))
 
 
 def ortho_loss(z1: Tensor, zs: Tensor, precision: str = "fp32") -> Tensor:

@@ -33,6 +33,7 @@ struct G2Group {
   TcEpi epi;
   int K;
   int tiles_n, splits, kb_per_split, num_kb;
+  int atomic;          // fp32 output accumulated with red.add (split-K partial tiles, or accumulate-into-C mode)
   int item_start;
 };
 struct alignas(64) G2Params {
@@ -173,7 +174,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
           tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * G2_BN + (uint32_t)(ch * 128 + c * 32), r);
           tc::tmem_ld_wait();
           const int nbase = it.n0 + ch * 128 + c * 32;
-          if (g.splits > 1) tc_epilogue_chunk<EPI, true>(g.epi, r, row0, lane, nbase, it.ks == 0, my_stage);
+          if (g.atomic) tc_epilogue_chunk<EPI, true>(g.epi, r, row0, lane, nbase, it.ks == 0, my_stage);
           else tc_epilogue_chunk<EPI, false>(g.epi, r, row0, lane, nbase, true, my_stage);
         }
       }
@@ -233,6 +234,7 @@ int launch_gemm_tc2(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, 
       const int tiles = ((d.M + 255) / 256) * g.tiles_n;
       // split-K: only for plain fp32 accumulation (wgrad: tiny output, K = batch); the caller zeroes out_f32
       int splits = 1;
+      const bool accum = d.split_k < 0 && epilogue == DMF_EPI_NONE && d.out_f32 && !d.out_bf16 && !d.out_bf16_t;
       if (d.split_k != 1 && epilogue == DMF_EPI_NONE && d.out_f32 && !d.out_bf16 && !d.out_bf16_t) {
         const int max_splits = g.num_kb / 8 > 0 ? (g.num_kb / 8 < 64 ? g.num_kb / 8 : 64) : 1;
         if (d.split_k > 1) {
@@ -250,6 +252,7 @@ int launch_gemm_tc2(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, 
       }
       g.kb_per_split = (g.num_kb + splits - 1) / splits;
       g.splits = (g.num_kb + g.kb_per_split - 1) / g.kb_per_split;
+      g.atomic = (g.splits > 1 || accum) ? 1 : 0;
       g.item_start = items;
       items += tiles * g.splits;
       ++P.n;

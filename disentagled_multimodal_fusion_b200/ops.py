@@ -134,12 +134,22 @@ def transpose_bf16(src: Tensor) -> Tensor:
     return dst
 
 
-def colsum(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+def colsum(x: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
     M, N = x.shape
     if out is None:
         out = torch.empty(N, dtype=torch.float32, device=x.device)
-    check(lib.dmf_colsum_f32(ptr(x), x.stride(0), M, N, ptr(out), 0, stream()))
+    check(lib.dmf_colsum_f32(ptr(x), x.stride(0), M, N, ptr(out), 1 if accumulate else 0, stream()))
     return out
+
+
+def _grad_slot(p: Tensor) -> Optional[Tensor]:
+    """The pre-allocated fp32 .grad of a leaf parameter (dp.FlatParams points every .grad into one flat buffer),
+    or None.  Kernels that can accumulate (red.add) write weight / bias gradients straight into it and the
+    autograd Function returns None for that input: no temporary, no zero-fill, no AccumulateGrad add."""
+    g = getattr(p, "grad", None)
+    if g is None or not p.is_leaf or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
+        return None
+    return g
 
 
 def vmf_draw(rows: int, D: int, kappa: float, seed: int, offset: int, device, out=None) -> Tuple[Tensor, Tensor]:
@@ -300,8 +310,15 @@ class _GroupedMLP(torch.autograd.Function):
                     new_dY[g] = dX
             gemm_f32(wdescs, L.EPI_NONE)
             for (g, ll, dWp, dbp, N, K) in partials:
-                dWs[g][ll] = colsum(dWp).view(N, K)
-                dbs[g][ll] = colsum(dbp)
+                ws, bsl = _grad_slot(Ws[g][ll]), _grad_slot(ctx.bs[g][ll])
+                if ws is not None:
+                    colsum(dWp, ws.view(-1), accumulate=True)
+                else:
+                    dWs[g][ll] = colsum(dWp).view(N, K)
+                if bsl is not None:
+                    colsum(dbp, bsl, accumulate=True)
+                else:
+                    dbs[g][ll] = colsum(dbp)
             if ddescs:
                 if l > 0:
                     gemm_f32([d for _, d in ddescs], L.EPI_RELU_MASK)
@@ -417,12 +434,13 @@ class _GroupedMLP(torch.autograd.Function):
             Np, Mp = (N + 7) // 8 * 8, (M + 7) // 8 * 8
             b = torch.empty(M, Np, dtype=torch.bfloat16, device=dev)
             bT = torch.empty(N, Mp, dtype=torch.bfloat16, device=dev)
-            db = torch.zeros(N, dtype=torch.float32, device=dev)
+            slot = _grad_slot(ctx.bs[g][NL - 1])
+            db = slot if slot is not None else torch.zeros(N, dtype=torch.float32, device=dev)
             check(lib.dmf_cast_dual_bf16(ptr(dy), dy.stride(0), ptr(b), Np, ptr(bT), Mp, ptr(db), M, N, stream()))
             dYb[g], dYT[g] = (b[:, :N] if Np != N else b), bT
-            dbs[g][NL - 1] = db
+            dbs[g][NL - 1] = None if slot is not None else db
         for l in range(NL - 1, -1, -1):
-            wdescs, ddescs = [], []
+            wdescs, ddescs, wdirect = [], [], []
             nextb, nextT = [None] * G, [None] * G
             next32 = [None] * G
             for g in range(G):
@@ -433,10 +451,12 @@ class _GroupedMLP(torch.autograd.Function):
                 XT = actTs[g][l]
                 if XT is None:
                     XT = transpose_bf16(X)          # [K, Mp]
-                dW = torch.zeros(N, K, dtype=torch.float32, device=dev)
+                slot = _grad_slot(Ws[g][l]) if (N >= 512 and K >= 128) else None     # pair kernel can accumulate
+                wdirect.append(slot is not None)
+                dW = slot if slot is not None else torch.zeros(N, K, dtype=torch.float32, device=dev)
                 wdescs.append(dict(A=dYT[g], lda=dYT[g].stride(0), B=XT, ldb=XT.stride(0), out_f32=dW, ldo_f32=K,
-                                   M=N, N=K, K=M, split_k=0))
-                dWs[g][l] = dW
+                                   M=N, N=K, K=M, split_k=-1 if slot is not None else 0))
+                dWs[g][l] = None if slot is not None else dW
                 if l == 0 and not ctx.in_needs_grad[g] and ctx.extra_needs_grad[g]:
                     De = ctx.extra_cols[g]
                     WT = cast_transpose_bf16(Ws[g][l][:, K - De:])      # [De, Np]
@@ -459,6 +479,13 @@ class _GroupedMLP(torch.autograd.Function):
                         d.update(out_f32=dX32, ldo_f32=K)
                         next32[g] = dX32
                     ddescs.append(d)
+            if len(set(wdirect)) > 1:        # the accumulate mode needs every group of the launch on the pair kernel
+                for g in range(G):
+                    if wdirect[g]:
+                        K_, N_ = wdescs[g]["N"], wdescs[g]["M"]
+                        dW = torch.zeros(N_, K_, dtype=torch.float32, device=dev)
+                        wdescs[g].update(out_f32=dW, split_k=0)
+                        dWs[g][l] = dW
             gemm_tc(wdescs, L.EPI_NONE)
             if ddescs:
                 gemm_tc(ddescs, L.EPI_RELU_MASK if l > 0 else L.EPI_NONE)
@@ -467,9 +494,10 @@ class _GroupedMLP(torch.autograd.Function):
             else:
                 for g in range(G):
                     K = nextb[g].shape[1]
-                    db = torch.zeros(K, dtype=torch.float32, device=dev)
+                    slot = _grad_slot(ctx.bs[g][l - 1])
+                    db = slot if slot is not None else torch.zeros(K, dtype=torch.float32, device=dev)
                     check(lib.dmf_colsum_bf16(ptr(nextb[g]), nextb[g].stride(0), nextb[g].shape[0], K, ptr(db), stream()))
-                    dbs[g][l - 1] = db
+                    dbs[g][l - 1] = None if slot is not None else db
                 dYb, dYT = nextb, nextT
         return dxs, dWs, dbs
 

@@ -83,9 +83,11 @@ typedef struct {
   const uint16_t* mask_bf16; long long ldmask; /* DMF_EPI_RELU_MASK: zero where mask<=0 */
   int M, N, K;
   uint16_t* out_bf16_t; long long ldo_t;       /* optional TRANSPOSED bf16 copy: out_bf16_t[n*ldo_t + m] */
-  int split_k;  /* 0 = auto, 1 = never, >1 = that many K splits.  Splitting applies only to DMF_EPI_NONE with
-                   out_f32 alone (wgrad: K = batch); partial tiles are accumulated with red.add, so the
-                   CALLER must zero out_f32 first */
+  int split_k;  /* 0 = auto, 1 = never, >1 = that many K splits, <0 = auto AND always accumulate (out_f32 += A*B^T:
+                   wgrad straight into an existing .grad buffer).  Splitting applies only to DMF_EPI_NONE with
+                   out_f32 alone (wgrad: K = batch); partial tiles are accumulated with red.add, so for
+                   split_k >= 0 the CALLER must zero out_f32 first.  Honoured by the CTA-pair kernel only
+                   (M >= 512 and N >= 128 in every group) */
 } dmf_tc_gemm_desc;
 int dmf_grouped_gemm_bf16_tc(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, dmf_stream_t s);
 

@@ -623,6 +623,32 @@ def test_launch_counter_moves(dmf):
     assert dmf._lib.launch_count() == before + 1
 
 
+def test_direct_grad_accumulation_matches_autograd(dmf):
+    """With dp.FlatParams every .grad is pre-allocated, and the wgrad / bias-grad kernels accumulate straight into
+    it (red.add) while the autograd Function returns None; the result must equal the ordinary autograd path, also
+    when a second backward accumulates on top."""
+    from disentagled_multimodal_fusion_b200.dp import FlatParams
+    dims, h, e, B = [256, 192], 512, 128, 512
+    gen = torch.Generator().manual_seed(1)
+    x1, x2 = torch.randn(B, dims[0], generator=gen).to(DEV), torch.randn(B, dims[1], generator=gen).to(DEV)
+    v1, v2 = x1 + 0.01 * torch.randn_like(x1), x2 + 0.01 * torch.randn_like(x2)
+    grads = []
+    for use_flat in (False, True):
+        torch.manual_seed(0)
+        m = dmf.DisentangledSSL(output_dim=dims, hidden_dim=h, embed_dim=e, precision="bf16").to(DEV)
+        torch.manual_seed(7)
+        noise = m.draw_noise(B, DEV)
+        fp = FlatParams(m.parameters()) if use_flat else None
+        if fp is not None:
+            fp.zero_grad()
+        for _ in range(2):                      # two backward passes: gradients accumulate
+            loss, _ = m(x1, x2, v1, v2, noise=noise)
+            loss.backward()
+        grads.append(torch.cat([p.grad.flatten() for p in m.parameters()]).clone())
+    assert_close(grads[1], grads[0], 2e-3, "direct .grad accumulation vs autograd accumulation")
+
+
+
 # ------------------------------------------------------------------------------------- multi-GPU (NCCL)
 @pytest.mark.parametrize("prec", ["bf16", "fp32"])
 def test_data_parallel_matches_single_gpu(dmf, prec):

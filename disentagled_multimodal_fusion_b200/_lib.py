@@ -96,6 +96,7 @@ _SIGS = {
     "dmf_dmvae_poe_mean": ([C.POINTER(c_p), c_i, c_i, c_i, c_f, c_p, c_p], c_i),
     "dmf_dmvae_mse_fwd_bwd": ([c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_ll, c_p], c_i),
     "dmf_edl_fused": ([c_p, c_p, C.POINTER(EdlParams), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p], c_i),
+    "dmf_eval_reduce": ([c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p], c_i),
     "dmf_evidence_fwd": ([c_p, c_p, c_ll, c_p], c_i),
     "dmf_evidence_bwd": ([c_p, c_p, c_p, c_p, c_ll, c_p], c_i),
     "dmf_adam_step": ([c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_f, c_p, c_p], c_i),

@@ -384,6 +384,77 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fused evaluation reducer (analysis.py:5-399): one pass over a batch of evidences accumulates,
+// per slot s (views 0..V-1, then the fused evidence as slot V), everything evaluate_subjective_model[_with_shared]
+// gathers with ~40 torch kernels and ~12 .item() syncs per batch:
+//   stats[s][0..7] = correct, evidence_sum, epi_sum, ale_sum, inc_N, inc_evidence_sum, inc_epi_sum, inc_ale_sum
+//   class_sum[s][c] += sum_b e[b,s,c]        true_sum[s][c] += sum_{b: y_b = c} e[b,s,c]       class_counts[c] += #{y_b = c}
+// One thread per (sample, slot); shared-memory accumulators per CTA, one round of global atomics per CTA.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eval_reduce_kernel(const float* __restrict__ evid, const float* __restrict__ fused, const long long* __restrict__ labels,
+                   int B, int V, int C, float* __restrict__ stats, float* __restrict__ class_sum,
+                   float* __restrict__ true_sum, float* __restrict__ class_counts) {
+  extern __shared__ float sm[];
+  const int S1 = V + 1;
+  float* s_stats = sm;                       // [S1][8]
+  float* s_cls = s_stats + S1 * 8;           // [S1][C]
+  float* s_true = s_cls + S1 * C;            // [S1][C]
+  float* s_cnt = s_true + S1 * C;            // [C]
+  const int nacc = S1 * 8 + 2 * S1 * C + C;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const long long total = (long long)B * S1;
+  const float fC = (float)C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / S1), s = (int)(idx - (long long)b * S1);
+    const float* e = s < V ? evid + ((long long)b * V + s) * C : fused + (long long)b * C;
+    long long yl = labels[b];
+    const int y = (int)min(max(yl, 0LL), (long long)(C - 1));
+    float esum = 0.f, S = 0.f, best = e[0];
+    int arg = 0;
+    for (int c = 0; c < C; ++c) {
+      const float v = e[c];
+      esum += v;
+      S += v + 1.0f;
+      if (v > best) { best = v; arg = c; }
+      atomicAdd(&s_cls[s * C + c], v);
+    }
+    const float psiS = gamma3<false>(S + 1.0f).psi;
+    float ale = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float al = e[c] + 1.0f;
+      ale += (al / S) * (gamma3<false>(al + 1.0f).psi - psiS);
+    }
+    ale = -ale;
+    const float epi = fC / S;
+    const bool ok = arg == y;
+    float* st = s_stats + s * 8;
+    atomicAdd(st + 1, esum);
+    atomicAdd(st + 2, epi);
+    atomicAdd(st + 3, ale);
+    if (ok) {
+      atomicAdd(st + 0, 1.0f);
+    } else {
+      atomicAdd(st + 4, 1.0f);
+      atomicAdd(st + 5, esum);
+      atomicAdd(st + 6, epi);
+      atomicAdd(st + 7, ale);
+    }
+    atomicAdd(&s_true[s * C + y], e[y]);
+    if (s == V) atomicAdd(&s_cnt[y], 1.0f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < S1 * 8; i += blockDim.x) if (s_stats[i] != 0.f) atomicAdd(stats + i, s_stats[i]);
+  for (int i = threadIdx.x; i < S1 * C; i += blockDim.x) {
+    if (s_cls[i] != 0.f) atomicAdd(class_sum + i, s_cls[i]);
+    if (s_true[i] != 0.f) atomicAdd(true_sum + i, s_true[i]);
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) if (s_cnt[i] != 0.f) atomicAdd(class_counts + i, s_cnt[i]);
+}
+
 __global__ void evidence_fwd_kernel(const float* __restrict__ h, float* __restrict__ e, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     e[i] = evidence_act(h[i]);
@@ -460,6 +531,22 @@ extern "C" int dmf_edl_fused(const float* evid, const long long* labels, const d
     case 7: return launch_edl<7>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
     default: return launch_edl<8>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
   }
+}
+
+
+extern "C" int dmf_eval_reduce(const float* evid, const float* fused, const long long* labels, int B, int V, int C,
+                               float* stats, float* class_sum, float* true_sum, float* class_counts, dmf_stream_t s) {
+  DMF_REQUIRE(evid && fused && labels && stats && class_sum && true_sum && class_counts, "dmf_eval_reduce: null argument");
+  DMF_REQUIRE(B >= 0 && V >= 1 && C >= 2, "dmf_eval_reduce: bad shape B=%d V=%d C=%d", B, V, C);
+  if (B == 0) return 0;
+  const size_t smem = ((size_t)(V + 1) * 8 + 2 * (size_t)(V + 1) * C + C) * sizeof(float);
+  DMF_REQUIRE(smem <= 48 * 1024, "dmf_eval_reduce: (V+1)*C = %d too large", (V + 1) * C);
+  const long long total = (long long)B * (V + 1);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+  eval_reduce_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)s>>>(evid, fused, labels, B, V, C, stats, class_sum, true_sum,
+                                                                    class_counts);
+  return launched("dmf_eval_reduce");
 }
 
 extern "C" int dmf_evidence_fwd(const float* h, float* e, long long n, dmf_stream_t s) {

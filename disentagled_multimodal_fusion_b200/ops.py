@@ -964,6 +964,25 @@ def edl_summaries(evid: Tensor, labels: Tensor, agg: str):
     return fused, u, ale, pred
 
 
+def eval_reduce(evid: Tensor, fused: Tensor, labels: Tensor, acc: Optional[dict] = None) -> dict:
+    """One-pass accumulation of the evaluation statistics of analysis.py:5-399 for a batch.  ``acc`` (returned by a
+    previous call) keeps the device accumulators across batches: no per-batch ``.item()``."""
+    L.require_device()
+    evid, fused = _f32c(evid), _f32c(fused)
+    B, V, Cc = evid.shape
+    dev = evid.device
+    if acc is None:
+        acc = dict(stats=torch.zeros(V + 1, 8, dtype=torch.float32, device=dev),
+                   class_sum=torch.zeros(V + 1, Cc, dtype=torch.float32, device=dev),
+                   true_sum=torch.zeros(V + 1, Cc, dtype=torch.float32, device=dev),
+                   class_counts=torch.zeros(Cc, dtype=torch.float32, device=dev), N=0)
+    labels = labels.to(torch.int64).contiguous()
+    check(lib.dmf_eval_reduce(ptr(evid), ptr(fused), ptr(labels), B, V, Cc, ptr(acc["stats"]), ptr(acc["class_sum"]),
+                              ptr(acc["true_sum"]), ptr(acc["class_counts"]), stream()))
+    acc["N"] += B
+    return acc
+
+
 def fuse_evidence(evid: Tensor, agg: str) -> Tensor:
     """utils.py:66-116 aggregation only (no gradient: the reference loss ignores it)."""
     B = evid.shape[0]

@@ -222,6 +222,13 @@ typedef struct {
 int dmf_edl_fused(const float* evid, const long long* labels, const dmf_edl_params* p, const float* gscale,
                   float* fused, float* grad, float* u, float* ale, int* pred, float* loss_parts, dmf_stream_t s);
 
+/* Fused evaluation reducer (analysis.py:5-399).  Slots s = 0..V-1 are the views of evid [B,V,C],
+ * slot V is the fused evidence [B,C].  Everything is ACCUMULATED (caller zeroes once per evaluation):
+ *   stats [V+1][8] = correct, evidence_sum, epi_sum (C/S), ale_sum, inc_N, inc_evidence_sum, inc_epi_sum, inc_ale_sum
+ *   class_sum [V+1][C] = sum_b e;  true_sum [V+1][C] = sum_{b: y_b = c} e[b, c];  class_counts [C]            */
+int dmf_eval_reduce(const float* evid, const float* fused, const long long* labels, int B, int V, int C,
+                    float* stats, float* class_sum, float* true_sum, float* class_counts, dmf_stream_t s);
+
 /* evidence activation alone (utils.py:46-63) and its backward (zero outside the clamp)          */
 int dmf_evidence_fwd(const float* h, float* e, long long n, dmf_stream_t s);
 int dmf_evidence_bwd(const float* h, const float* e, const float* de, float* dh, long long n, dmf_stream_t s);

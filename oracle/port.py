@@ -396,3 +396,31 @@ def xavier_mlp_params(layers: Sequence[int], out: int, gen: torch.Generator, dty
         bb = 1.0 / math.sqrt(fan_in)
         bs.append(((torch.rand(fan_out, generator=gen, dtype=dtype) * 2 - 1) * bb).requires_grad_())
     return ws, bs
+
+
+# --------------------------------------------------------------------------------------
+# evaluation reducer                                                     analysis.py:5-192
+# --------------------------------------------------------------------------------------
+def eval_reduce(evidences: Tensor, fused_ev: Tensor, target: Tensor) -> Dict[str, Tensor]:
+    """Accumulators of ``evaluate_subjective_model`` for ONE batch (analysis.py:27-152), slot V = fused:
+    stats [V+1, 8] = correct, evidence_sum, epi_sum, ale_sum, inc_N, inc_evidence_sum, inc_epi_sum, inc_ale_sum;
+    class_sum / true_sum [V+1, K]; class_counts [K]."""
+    B, V, K = evidences.shape
+    slots = [evidences[:, v, :] for v in range(V)] + [fused_ev]
+    stats = torch.zeros(V + 1, 8, dtype=torch.float64)
+    class_sum = torch.zeros(V + 1, K, dtype=torch.float64)
+    true_sum = torch.zeros(V + 1, K, dtype=torch.float64)
+    for s, ev in enumerate(slots):
+        alphas = ev + 1.0
+        S = alphas.sum(dim=-1, keepdim=True)
+        probs = alphas / S
+        epi = (K / S).squeeze(-1)
+        ale = -torch.sum(probs * (torch.digamma(alphas + 1.0) - torch.digamma(S + 1.0)), dim=-1)
+        escal = ev.sum(dim=-1)
+        ok = ev.argmax(dim=-1) == target
+        inc = ~ok
+        stats[s] = torch.tensor([ok.sum(), escal.sum(), epi.sum(), ale.sum(), inc.sum(), escal[inc].sum(), epi[inc].sum(),
+                                 ale[inc].sum()], dtype=torch.float64)
+        class_sum[s] = ev.sum(dim=0).double()
+        true_sum[s] = torch.bincount(target, weights=ev[torch.arange(B), target], minlength=K).double()
+    return dict(stats=stats, class_sum=class_sum, true_sum=true_sum, class_counts=torch.bincount(target, minlength=K).double())

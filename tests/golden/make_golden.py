@@ -311,6 +311,43 @@ def gen_vmf():
     save("vmf", e=e, z=z, w=w, v=v, grad_e=ge)
 
 
+# ----------------------------------------------------------------------------------------
+# 9. evaluation reducers                                                 analysis.py:5-399
+# ----------------------------------------------------------------------------------------
+def gen_eval():
+    """The reference's evaluate_subjective_model[_with_shared] on a stub model whose shared_step replays fixed
+    evidences over three ragged batches; the returned dicts are stored flattened (JSON)."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("ref_analysis", os.path.join(os.environ.get("DMF_REFERENCE_ROOT", "/root/reference"), "analysis.py"))
+    ana = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ana)
+    g = torch.Generator().manual_seed(41)
+    V, K = 4, 7
+    sizes = [50, 33, 17]
+    evs = [port.evidence_activation(torch.randn(b, V, K, generator=g) * 1.5) for b in sizes]
+    ys = [torch.randint(0, K, (b,), generator=g) for b in sizes]
+    fused = [e.sum(dim=1) for e in evs]
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self.num_classes = K
+            self.i = 0
+
+        def shared_step(self, batch):
+            i = self.i
+            self.i += 1
+            return torch.zeros(()), fused[i], ys[i], evs[i]
+    loader = [[torch.zeros(b, 1), ys[i]] for i, b in enumerate(sizes)]
+    r1 = ana.evaluate_subjective_model(Stub(), loader, device=torch.device("cpu"))
+    r2 = ana.evaluate_subjective_model_with_shared(Stub(), loader, device=torch.device("cpu"))
+    save("eval_reduce", evid=torch.cat(evs), y=torch.cat(ys), fused=torch.cat(fused), sizes=np.asarray(sizes),
+         plain_json=np.frombuffer(json.dumps(r1).encode(), dtype=np.uint8),
+         shared_json=np.frombuffer(json.dumps(r2).encode(), dtype=np.uint8))
+
+
 if __name__ == "__main__":
     gen_activation()
     gen_edl()
@@ -320,3 +357,4 @@ if __name__ == "__main__":
     gen_probes()
     gen_handwritten()
     gen_vmf()
+    gen_eval()

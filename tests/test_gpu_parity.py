@@ -202,6 +202,50 @@ def test_device_augmentation_distribution(dmf):
     assert torch.equal(y3, y), "same seed must reproduce the draw"
 
 
+def test_eval_reducer_kernel_and_analysis_mirror(dmf):
+    """dmf_eval_reduce + the analysis.py mirror vs the dicts returned by the UNMODIFIED reference functions on the
+    same evidences (three ragged batches; fixture eval_reduce.npz), and vs the oracle accumulators."""
+    import json
+    from oracle import port
+    from tests.test_oracle_golden import assert_result_dicts_close
+    from disentagled_multimodal_fusion_b200 import analysis
+    g = load_golden("eval_reduce")
+    evid, y, fused = T(g["evid"], DEV), T(g["y"], DEV), T(g["fused"], DEV)
+    sizes = [int(b) for b in g["sizes"]]
+    K = evid.shape[2]
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1, device=DEV))
+            self.num_classes = K
+            self.o = 0
+
+        def shared_step(self, batch):
+            b = batch[-1].shape[0]
+            o = self.o
+            self.o += b
+            return torch.zeros((), device=DEV), fused[o:o + b], y[o:o + b], evid[o:o + b]
+    o, loader = 0, []
+    for b in sizes:
+        loader.append([torch.zeros(b, 1), y[o:o + b].cpu()])
+        o += b
+    r1 = analysis.evaluate_subjective_model(Stub(), loader)
+    r2 = analysis.evaluate_subjective_model_with_shared(Stub(), loader)
+    assert_result_dicts_close(r1, json.loads(bytes(g["plain_json"]).decode()))
+    assert_result_dicts_close(r2, json.loads(bytes(g["shared_json"]).decode()))
+    # raw accumulators vs the oracle on a larger single batch
+    gen = torch.Generator().manual_seed(8)
+    B, V, C = 5000, 3, 10
+    ev = port.evidence_activation(torch.randn(B, V, C, generator=gen) * 2)
+    yy = torch.randint(0, C, (B,), generator=gen)
+    fu = ev.mean(dim=1)
+    acc = dmf.ops.eval_reduce(ev.to(DEV), fu.to(DEV), yy.to(DEV))
+    ref = port.eval_reduce(ev, fu, yy)
+    for k in ("stats", "class_sum", "true_sum", "class_counts"):
+        assert_close(acc[k], ref[k], 2e-5, k)
+
+
 def test_vmf(dmf):
     g = load_golden("vmf")
     e = T(g["e"], DEV, grad=True)

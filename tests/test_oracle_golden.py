@@ -169,3 +169,62 @@ def test_latefusion(name):
     assert_close(ea, g["evidences_a"], 5e-6, "evidences_a")
     loss.backward()
     assert_close(heads[0][0][0].grad, g["grad.heads.0.layers.0.weight"], 1e-5, "head wgrad")
+
+
+def _reduce_dict(acc, N, with_shared):
+    """Build the reference's result dict from the oracle accumulators (reduce_block of analysis.py:157-169)."""
+    def block(st):
+        c, ev, epi, ale, n_inc, iev, iepi, iale = [float(x) for x in st]
+        return {"accuracy": c / N, "evidence_mean": ev / N, "epistemic_mean": epi / N, "aleatoric_mean": ale / N,
+                "incorrect_only": {"evidence_mean": iev / n_inc if n_inc > 0 else 0.0,
+                                   "epistemic_mean": iepi / n_inc if n_inc > 0 else 0.0,
+                                   "aleatoric_mean": iale / n_inc if n_inc > 0 else 0.0}}
+    V = acc["stats"].shape[0] - 1
+    unc = acc["class_sum"] / N
+    tru = acc["true_sum"] / torch.clamp(acc["class_counts"], min=1e-12)
+    lo = 1 if with_shared else 0
+    out = {"per_view": [block(acc["stats"][v]) for v in range(lo, V)], "fused": block(acc["stats"][V]),
+           "per_class_evidence": {"unconditional": {"per_view": [unc[v].tolist() for v in range(lo, V)], "fused": unc[V].tolist()},
+                                  "true_class": {"per_view": [tru[v].tolist() for v in range(lo, V)], "fused": tru[V].tolist()}}}
+    if with_shared:
+        out["shared"] = block(acc["stats"][0])
+        out["per_class_evidence"]["unconditional"]["shared"] = unc[0].tolist()
+        out["per_class_evidence"]["true_class"]["shared"] = tru[0].tolist()
+    return out
+
+
+def _flat(d, prefix=""):
+    out = {}
+    if isinstance(d, dict):
+        for k, v in d.items():
+            out.update(_flat(v, prefix + str(k) + "."))
+    elif isinstance(d, (list, tuple)):
+        for i, v in enumerate(d):
+            out.update(_flat(v, prefix + str(i) + "."))
+    else:
+        out[prefix] = float(d)
+    return out
+
+
+def assert_result_dicts_close(ours, ref, rtol=1e-5):
+    fo, fr = _flat(ours), _flat(ref)
+    assert fo.keys() == fr.keys(), set(fo) ^ set(fr)
+    for k in fr:
+        assert abs(fo[k] - fr[k]) <= rtol * max(1.0, abs(fr[k])), (k, fo[k], fr[k])
+
+
+def test_eval_reducer_against_reference_dicts():
+    """oracle.port.eval_reduce accumulated over the ragged batches == the dicts the UNMODIFIED reference functions
+    (analysis.py:5-399) returned for the same evidences (fixture eval_reduce.npz)."""
+    import json
+    g = load_golden("eval_reduce")
+    evid, y, fused = T(g["evid"]), T(g["y"]), T(g["fused"])
+    acc, o = None, 0
+    for b in g["sizes"]:
+        b = int(b)
+        part = port.eval_reduce(evid[o:o + b], fused[o:o + b], y[o:o + b])
+        acc = part if acc is None else {k: acc[k] + part[k] for k in acc}
+        o += b
+    N = evid.shape[0]
+    assert_result_dicts_close(_reduce_dict(acc, N, False), json.loads(bytes(g["plain_json"]).decode()))
+    assert_result_dicts_close(_reduce_dict(acc, N, True), json.loads(bytes(g["shared_json"]).decode()))

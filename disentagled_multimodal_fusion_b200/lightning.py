@@ -116,7 +116,7 @@ except Exception:  # noqa: BLE001
                     opt.zero_grad(set_to_none=True)
                     loss.backward()
                     opt.step()
-                if val_dataloaders is not None:
+                if val_dataloaders is not None and hasattr(model, "validation_step"):   # Lightning skips it too
                     self._eval_loop(model, val_dataloaders, "validation")
                 model.on_train_epoch_end()
                 self.callback_metrics.update(model._logged)

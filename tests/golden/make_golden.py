@@ -348,6 +348,38 @@ def gen_eval():
          shared_json=np.frombuffer(json.dumps(r2).encode(), dtype=np.uint8))
 
 
+# ----------------------------------------------------------------------------------------
+# 10. datasets: synthetic generator + MultiViewDataset post-processing   datasets/dataset.py:164-268,331-458
+# ----------------------------------------------------------------------------------------
+def gen_datasets():
+    import hashlib
+    ds_mod = ns.dataset
+    rows = {}
+    for tag, kw in (("common_med", dict(n_samples=10000, n_classes=3, d_signal=16, d_spurious=16, rho=0.5, shared_class_frac=0.5, seed=0)),
+                    ("small_linear", dict(n_samples=257, n_classes=4, d_signal=8, d_spurious=0, rho=0.9, shared_class_frac=0.25,
+                                          hetero_noise=False, nonlinear_shared=False, nonlinear_specific=True, conflict_frac=1.0, seed=3))):
+        d = ds_mod.SimpleTwoModalPlus(**kw)
+        for nm, t in (("X1", d.X1), ("X2", d.X2), ("y", d.y)):
+            rows[f"{tag}.{nm}.sha"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(t.numpy()).tobytes()).hexdigest().encode(), dtype=np.uint8)
+        rows[f"{tag}.X1.head"] = d.X1[:4]
+    # MultiViewDataset on seeded raw arrays (no .mat needed): normalisation, conflict + noise injection
+    rng = np.random.RandomState(5)
+    N, dims, Cn = 120, [7, 3, 5], 4
+    raw = np.empty(len(dims), dtype=object)
+    for v, dv in enumerate(dims):
+        raw[v] = rng.randn(N, dv) * (v + 1) + v
+    yy = rng.randint(1, Cn + 1, size=(N, 1))                     # 1-based labels like the .mat files
+    mv = ds_mod.MultiViewDataset("toy", raw.copy(), yy.copy())
+    np.random.seed(123)
+    idx = np.arange(N)
+    np.random.shuffle(idx)
+    test_idx = idx[96:]
+    mv.postprocessing(test_idx, addNoise=True, sigma=0.5, ratio_noise=0.5, addConflict=True, ratio_conflict=1.0)
+    rows.update({"mv.raw0": raw[0], "mv.raw1": raw[1], "mv.raw2": raw[2], "mv.y_raw": yy, "mv.test_idx": test_idx,
+                 "mv.X0": mv.X[0], "mv.X1": mv.X[1], "mv.X2": mv.X[2], "mv.Y": mv.Y, "mv.dims": mv.dims})
+    save("datasets", **rows)
+
+
 if __name__ == "__main__":
     gen_activation()
     gen_edl()
@@ -358,3 +390,4 @@ if __name__ == "__main__":
     gen_handwritten()
     gen_vmf()
     gen_eval()
+    gen_datasets()

@@ -173,3 +173,100 @@ def test_data_parallel_decomposition_gloo_world2(tmp_path):
                          capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("OK") == 2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# data side: datasets.py / run.py against fixtures minted from the unmodified reference
+# ---------------------------------------------------------------------------------------------------------
+def _sha(t):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(t.numpy()).tobytes()).hexdigest()
+
+
+def test_synthetic_dataset_matches_reference():
+    """SimpleTwoModalPlus replays the reference's draw order: equal seeds -> bit-identical X1, X2, y
+    (datasets/dataset.py:331-458; sha256 of the tensors of the unmodified reference in the fixture)."""
+    from disentagled_multimodal_fusion_b200.datasets import SimpleTwoModalPlus
+    g = load_golden("datasets")
+    cases = (("common_med", dict(n_samples=10000, n_classes=3, d_signal=16, d_spurious=16, rho=0.5, shared_class_frac=0.5, seed=0)),
+             ("small_linear", dict(n_samples=257, n_classes=4, d_signal=8, d_spurious=0, rho=0.9, shared_class_frac=0.25,
+                                   hetero_noise=False, nonlinear_shared=False, nonlinear_specific=True, conflict_frac=1.0, seed=3)))
+    for tag, kw in cases:
+        d = SimpleTwoModalPlus(**kw)
+        assert np.array_equal(d.X1[:4].numpy(), g[f"{tag}.X1.head"]), tag
+        for nm, t in (("X1", d.X1), ("X2", d.X2), ("y", d.y)):
+            assert _sha(t) == bytes(g[f"{tag}.{nm}.sha"]).decode(), f"{tag}.{nm}"
+        x1, x2, y = d[5]
+        assert x1.shape == (kw["d_signal"] + kw["d_spurious"],) and y.dtype == torch.int64
+    with pytest.raises(AssertionError):
+        SimpleTwoModalPlus(rho=1.5)
+
+
+def test_multiview_postprocessing_matches_reference():
+    """MultiViewDataset: min-max scaling, 1-based label shift, dims, and the conflict / noise corruption of the
+    test rows on the numpy global RNG (datasets/dataset.py:164-268) -- bit-identical to the reference."""
+    from disentagled_multimodal_fusion_b200.datasets import MultiViewDataset
+    g = load_golden("datasets")
+    raw = np.empty(3, dtype=object)
+    for v in range(3):
+        raw[v] = g[f"mv.raw{v}"].copy()
+    mv = MultiViewDataset("toy", raw, g["mv.y_raw"].copy())
+    assert mv.num_views == 3 and mv.num_classes == 4 and np.array_equal(mv.dims, g["mv.dims"])
+    np.random.seed(123)
+    idx = np.arange(120)
+    np.random.shuffle(idx)
+    assert np.array_equal(idx[96:], g["mv.test_idx"])
+    mv.postprocessing(idx[96:], addNoise=True, sigma=0.5, ratio_noise=0.5, addConflict=True, ratio_conflict=1.0)
+    for v in range(3):
+        assert np.array_equal(mv.X[v], g[f"mv.X{v}"]), f"view {v}"
+    assert np.array_equal(mv.Y, g["mv.Y"])
+    item = mv[3]
+    assert len(item) == 4 and item[0].dtype == np.float32 and item[0].shape == (7,)
+
+
+def test_device_loader_contract_cpu():
+    """DeviceLoader (here on the CPU device): batches follow the DataLoader contract [x_0..x_{V-1}, y], a shuffled
+    epoch is a permutation of the subset, data-parallel ranks tile each global batch, ragged tail kept / dropped."""
+    from disentagled_multimodal_fusion_b200.datasets import DeviceLoader
+    n = 53
+    views = [np.arange(n * 3, dtype=np.float32).reshape(n, 3), np.arange(n * 2, dtype=np.float32).reshape(n, 2) + 0.5]
+    y = np.arange(n) % 5
+    sub = np.arange(3, 50)
+    ld = DeviceLoader(views, y, 10, device="cpu", indices=sub, shuffle=True, seed=1)
+    assert len(ld) == 5
+    seen = []
+    for b in ld:
+        assert len(b) == 3 and b[0].dtype == torch.float32 and b[2].dtype == torch.int64
+        rows = (b[0][:, 0] / 3).long()
+        assert torch.equal(b[1][:, 0], rows * 2 + 0.5) and torch.equal(b[2], rows % 5)
+        seen.append(rows)
+    assert sorted(torch.cat(seen).tolist()) == sub.tolist()
+    assert [len(s) for s in seen] == [10, 10, 10, 10, 7]
+    assert len(DeviceLoader(views, y, 10, device="cpu", indices=sub, drop_last=True)) == 4
+    full = [b[2] for b in DeviceLoader(views, y, 10, device="cpu", drop_last=True)]
+    parts = [[b[2] for b in DeviceLoader(views, y, 10, device="cpu", drop_last=True, rank=r, world_size=2)] for r in range(2)]
+    for k, fb in enumerate(full):
+        assert torch.equal(torch.cat([parts[0][k], parts[1][k]]), fb)
+    with pytest.raises(ValueError):
+        DeviceLoader(views, y, 9, device="cpu", world_size=2)
+
+
+def test_run_helpers():
+    """run.C dot-path getter with defaults, _get_dataset error behaviour, build_factories wiring (run.py:29-50,135-175)."""
+    from disentagled_multimodal_fusion_b200 import run
+    assert run.C("dataloader.batch_size") == 100 and run.C("probes.model_hidden_dim") == [128]
+    assert run.C("no.such.key", 7) == 7 and run.C("dmvae.a") == 1e-5
+    with pytest.raises(ValueError):
+        run._get_dataset("NoSuchSet")
+    np.random.seed(0)
+    tr, te = run._split_indices(10, 0.8)
+    np.random.seed(0)
+    ref = np.arange(10)
+    np.random.shuffle(ref)
+    assert np.array_equal(tr, ref[:8]) and np.array_equal(te, ref[8:])
+    mp = dict(classes=10, lr=3e-3, annealing_start=50, model_hidden_dim=[128], dropout_p=0.1, classifiers=None, output_dims=[6, 4])
+    dk = dict(dropout=0, a=1e-5, hidden_dim=32, embed_dim=8, lr=1e-4, num_epochs=3)
+    DF, PF, DPF, LF = run.build_factories(mp, 8, dk)
+    m = DF()
+    assert m.N == 2 and sum(p.numel() for p in m.parameters()) > 0
+    assert PF.keywords["input_dim"] == 8 and DPF.keywords["annealing_start"] == 50 and LF.args[2] == 10

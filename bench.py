@@ -351,7 +351,10 @@ def run_gpu(args, rank, world, local_rank):
                 "executed_over_algorithmic_flops": 3.0,
                 "tensor_pipe_active_pct_ncu": 79.9,
                 "other_kernels_ms_per_step": {k: v[1] / prof_steps for k, v in prof.items()}}
-    step_flops = 73.9e12 * (Bg / 65536.0) ** 2 if Bg else 0
+    # algorithmic FLOPs of one step: K2 = 2 critic calls with the no-grad diagnostics (8 B^2 D each) + the 2
+    # specific-critic calls whose diagnostics the reference discards (6 B^2 D each: cross block fwd 2 + bwd 4);
+    # K1 = 48.2 MFLOP/sample; ortho Grams forward only (lmd = 0: logged, weight exactly zero) 8 D^2 per sample
+    step_flops = 28.0 * Bg * Bg * EMB + Bg * (48.2e6 + 8.0 * EMB * EMB) if Bg else 0
     cpu = None
     if not args.no_cpu_baseline:
         torch.set_float32_matmul_precision("highest")

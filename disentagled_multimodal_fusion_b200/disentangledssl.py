@@ -170,8 +170,9 @@ class DisentangledSSL(LightningModule):
         loss_y = 0.5 * (loss_y + loss_y_v)
         loss_shared = joint_loss
 
-        specific_loss_x1, _, _ = self.critic.pair(*pairs[2], pre=pres[2], **kw)
-        specific_loss_x2, _, _ = self.critic.pair(*pairs[3], pre=pres[3], **kw)
+        # the reference discards loss_x / loss_y of the two specific-critic calls: skip their intra-view blocks
+        specific_loss_x1, _, _ = self.critic.pair(*pairs[2], pre=pres[2], diagnostics=False, **kw)
+        specific_loss_x2, _, _ = self.critic.pair(*pairs[3], pre=pres[3], diagnostics=False, **kw)
         loss_specific = specific_loss_x1 + specific_loss_x2
 
         lmd = self.lmd_scheduler(self.iterations) if self.lmd_end_value > 0 else self.lmd_start_value

@@ -34,9 +34,12 @@ class SupConLoss(nn.Module):
             features = features.view(features.shape[0], features.shape[1], -1)
         return self.pair(features[:, 0], features[:, 1])
 
-    def pair(self, z0, z1, unit_norm=False, pre=None, reduce=True):
-        loss, lx, ly = ops.infonce(z0, z1, self.temperature, self.precision, unit_norm=unit_norm, pre=pre, reduce=reduce)
+    def pair(self, z0, z1, unit_norm=False, pre=None, reduce=True, diagnostics=True):
+        loss, lx, ly = ops.infonce(z0, z1, self.temperature, self.precision, unit_norm=unit_norm, pre=pre, reduce=reduce,
+                                   diagnostics=diagnostics)
         r = self.temperature / self.base_temperature
+        if not diagnostics:
+            return r * loss, None, None
         return r * loss, r * lx, r * ly
 
 

@@ -570,7 +570,7 @@ class GatheredPair:
 
 class _InfoNCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z0, z1, temperature, precision, bound, pre, reduce):
+    def forward(ctx, z0, z1, temperature, precision, bound, pre, reduce, diagnostics=True):
         L.require_device()
         z0, z1 = _f32c(z0), _f32c(z1)
         Bl, D = z0.shape
@@ -601,14 +601,20 @@ class _InfoNCE(torch.autograd.Function):
                                                   off, ptr(rs[k]), ptr(cs[k]), off, ptr(dg[k]), stream()))
             with _Prof("rowlse_x4"):
                 rowcol(a0, g1, 0, 0)     # cross block: rows -> view-0 anchors, columns -> view-1 anchors
-                rowcol(a0, g0, 1, 1)     # intra-view blocks (no-grad diagnostics + the reference's row max)
-                rowcol(a1, g1, 2, 1)
+                if diagnostics:
+                    rowcol(a0, g0, 1, 1)     # intra-view blocks: only the no-grad diagnostics loss_x / loss_y need them
+                    rowcol(a1, g1, 2, 1)     # (the reference's row max is the self-similarity 1/T = the fixed shift)
             if world > 1:
-                dist.all_reduce(cs)
+                dist.all_reduce(cs if diagnostics else cs[0])
             mfix = torch.full((Bl,), shift, dtype=torch.float32, device=dev)
             l_c1 = cs[0, off:off + Bl].contiguous()
-            l_i0 = rs[1] + cs[1, off:off + Bl]
-            l_i1 = rs[2] + cs[2, off:off + Bl]
+            if diagnostics:
+                l_i0 = rs[1] + cs[1, off:off + Bl]
+                l_i1 = rs[2] + cs[2, off:off + Bl]
+            else:                            # callers that discard loss_x / loss_y (out3[1:] is then meaningless)
+                l_i0, l_i1 = rs[0], l_c1
+                dg[1].copy_(dg[0])
+                dg[2].copy_(dg[0])
             check(lib.dmf_infonce_finalize(ptr(mfix), ptr(rs[0]), ptr(mfix), ptr(l_i0), ptr(dg[0]), ptr(dg[1]), Bl,
                                            1.0 / (2 * Bg), 1.0 / Bg, 0, ptr(lse[0]), ptr(out3), stream()))
             check(lib.dmf_infonce_finalize(ptr(mfix), ptr(l_c1), ptr(mfix), ptr(l_i1), ptr(dg[0]), ptr(dg[2]), Bl,
@@ -663,20 +669,26 @@ class _InfoNCE(torch.autograd.Function):
             check(lib.dmf_infonce_bwd(ptr(a1), a1.stride(0), Bl, ptr(lse[1]), ptr(g0), g0.stride(0), ptr(g0T),
                                       g0T.stride(0) if g0T is not None else 0, Bg, ptr(lse_all[0]), D, scale, coef, ptr(gs),
                                       off, ptr(dz1), D, 0, dt, stream()))
-        return dz0, dz1, None, None, None, None, None
+        return dz0, dz1, None, None, None, None, None, None
 
 
 def infonce(z0: Tensor, z1: Tensor, temperature: float = 0.07, precision: str = "fp32",
-            unit_norm: bool = False, pre: Optional["GatheredPair"] = None, reduce: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+            unit_norm: bool = False, pre: Optional["GatheredPair"] = None, reduce: bool = True,
+            diagnostics: bool = True) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor]]:
     """(loss, loss_x, loss_y) of SupConLoss()(stack([z0,z1],1)) without the [2B,2B] logits.
     Under torch.distributed the negatives are global (embeddings all-gathered with NCCL).
     ``unit_norm=True`` asserts that the rows of z0 / z1 are L2-normalised (|s| <= 1/T): the bf16 path then runs
     the fixed-shift row+column kernel (dmf_infonce_rowcol_sums) instead of four online-max passes.
     ``pre`` = a GatheredPair built earlier from the same (z0, z1) (asynchronous all-gather already in flight).
     ``reduce=False`` (data parallel only) returns this rank's PARTIAL sums of the three scalars -- the caller
-    all-reduces them later, once for all its critic calls (the gradients do not depend on the loss value)."""
+    all-reduces them later, once for all its critic calls (the gradients do not depend on the loss value).
+    ``diagnostics=False``: the caller discards loss_x / loss_y (the reference's specific-critic calls,
+    models/disentangledssl.py:143-144); the unit-norm bf16 path then skips the two intra-view blocks (half of the
+    forward work) and returns None for them."""
     bound = (1.0 / float(temperature)) if unit_norm else None
-    out = _InfoNCE.apply(z0, z1, float(temperature), precision, bound, pre, reduce)
+    out = _InfoNCE.apply(z0, z1, float(temperature), precision, bound, pre, reduce, diagnostics)
+    if not diagnostics:
+        return out[0], None, None
     return out[0], out[1].detach(), out[2].detach()
 
 

@@ -14,10 +14,12 @@
 // 128 KB instead of 192 KB of operands from L2.
 //
 // Protocol per pair (leader = even CTA rank of the pair):
-//   warp 0  TMA: resident anchor block, 4-stage ring of half k-blocks for OWN S tiles, the V tile of EVERY tile
+//   warp 0  TMA: resident anchor block, then ONE 8-slot ring (8 KB slots) filled in MMA issue order with the half
+//           k-blocks of the OWN S tiles and the V chunks of EVERY tile (V of tile t+1 is in flight while PV(t) runs)
 //   warp 1  MMA (leader): S(own k+1), then per tile PV from TMEM (own) or from the received smem tile (foreign)
-//   warps 2-9 softmax on own tiles: TMEM in-place W + remote copy; arrive p_full (own leader) and, with
-//           release.cluster after fence.proxy.async, wr_full (leader of the other pair)
+//   warps 2-9 softmax on own tiles: TMEM in-place W + remote copy (st.shared::cluster); arrive p_full (own leader) and,
+//           with release.cluster, wr_full (leader of the other pair); the generic->async proxy fence is executed once
+//           by the consuming MMA thread after its acquire, not by the 512 writers
 //   wr_empty (in the PRODUCER CTAs) is arrived by the consumer's tcgen05.commit multicast once its PV has read
 //   the received tile.
 #include <stdlib.h>
@@ -30,11 +32,11 @@ namespace dmf {
 constexpr int B5_THREADS = 320;
 constexpr int B5_TILE = 128 * 64 * 2;   // 16 KB: [128 x 64] bf16
 constexpr int B5_HALF = 64 * 64 * 2;    // 8 KB: this CTA's half of a column k-block
-constexpr int B5_STAGES = 4;
+constexpr int B5_SLOTS = 8;             // unified operand ring: 8 slots of 8 KB (S half k-blocks AND V half chunks)
 constexpr int B5_OW = 256;
 constexpr int B5_KB = 8;                // D = 512 only
 constexpr float kLog2e5 = 1.4426950408889634f;
-constexpr size_t B5_SMEM = 1024 + (size_t)B5_KB * B5_TILE + (size_t)B5_STAGES * B5_HALF + 2 * B5_TILE /*V*/ +
+constexpr size_t B5_SMEM = 1024 + (size_t)B5_KB * B5_TILE + (size_t)B5_SLOTS * B5_HALF /*ring*/ +
                            2 * B5_TILE /*W recv*/ + 1024 /*bs*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ float ex2f5(float x) {
@@ -49,6 +51,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2_5(float lo, float hi) {
 }
 __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// Tried and rejected (9.9 ms vs 9.1 ms): st.async, whose every 16-byte store also completes tx bytes on an mbarrier of
+// the receiving CTA -- no writer-side fences, but 2048 barrier updates per tile and CTA.
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t mbar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%2, %3, %4, %5}, [%1];" ::"r"(addr),
+               "r"(mbar), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
@@ -83,6 +92,20 @@ __device__ __forceinline__ void umma_commit_mask(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 
+#ifdef DMF_TC5_TRACE
+__device__ unsigned long long dmf_tc5_trace[8][2048];
+__device__ __forceinline__ void trace(int stream, int idx) {
+  if (blockIdx.x < 4 && blockIdx.z == 0 && idx < 2048 && (threadIdx.x & 31) == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dmf_tc5_trace[stream][idx] = t;
+  }
+}
+#define TRACE(st, idx) trace(st, idx)
+#else
+#define TRACE(st, idx)
+#endif
+
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(B5_THREADS, 1)
 infonce_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmBT, int Ma, int Nb, float scale,
@@ -92,22 +115,22 @@ infonce_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smemA = smem;                                   // 8 tiles (resident anchors)
-  uint8_t* smemB = smemA + B5_KB * B5_TILE;                // ring of half k-blocks (S operand, own tiles)
-  uint8_t* smemV = smemB + B5_STAGES * B5_HALF;            // 2 tiles: this CTA's 128 d-rows of the BmT slice x 128 j
-  uint8_t* smemW = smemV + 2 * B5_TILE;                    // 2 tiles: W tile received from the other pair
+  uint8_t* smemR = smemA + B5_KB * B5_TILE;                // operand ring, consumed in MMA issue order: a slot holds this
+                                                           // CTA's half of an S k-block ([64 j x 64 k]) or half of a V
+                                                           // chunk ([64 d-rows x 64 j]; a chunk = 2 consecutive slots)
+  uint8_t* smemW = smemR + B5_SLOTS * B5_HALF;             // 2 tiles: W tile received from the other pair
   float* bsm = reinterpret_cast<float*>(smemW + 2 * B5_TILE);   // [2][128] per-tile column factors b_j
   uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + 256);
   uint64_t* a_full = bars;
   uint64_t* full_bar = bars + 1;
-  uint64_t* empty_bar = full_bar + B5_STAGES;
-  uint64_t* s_full = empty_bar + B5_STAGES;    // [2]
+  uint64_t* empty_bar = full_bar + B5_SLOTS;
+  uint64_t* s_full = empty_bar + B5_SLOTS;     // [2]
   uint64_t* p_full = s_full + 2;               // [2] own W(t) stored in TMEM (16 warp arrivals of the pair)
-  uint64_t* v_full = p_full + 2;
-  uint64_t* pv_done = v_full + 1;
-  uint64_t* acc_full = pv_done + 1;
-  uint64_t* wr_full = acc_full + 1;            // leader: 16 softmax warps of the OTHER pair stored a W tile here
+  uint64_t* acc_full = p_full + 2;
+  uint64_t* wr_full = acc_full + 1;            // per CTA: the partner CTA (rank ^ 2) stored its W tile here (32 KB of st.async tx)
   uint64_t* wr_empty = wr_full + 1;            // per CTA: the other pair's PV has consumed the tile we sent
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wr_empty + 1);
+  uint64_t* wr_peer = wr_empty + 1;            // leader: the non-leader CTA of this pair has received its tile (relay)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wr_peer + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank4 = tc2::cluster_ctarank();      // 0..3
@@ -123,19 +146,19 @@ infonce_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int ntiles = max(0, min(total_tiles, tz0 + tiles_per_split) - tz0);
   const bool split = gridDim.z > 1;
   const int n_own = ntiles > (int)pair ? (ntiles - (int)pair + 1) / 2 : 0;   // tiles t = pair, pair+2, ...
+  const int n_foreign = ntiles - n_own;
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
     tc::tma_prefetch_desc(&tmBT);
     tc::mbar_init(a_full, 1);
-    for (int s = 0; s < B5_STAGES; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < B5_SLOTS; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
     for (int b = 0; b < 2; ++b) { tc::mbar_init(s_full + b, 1); tc::mbar_init(p_full + b, 16); }
-    tc::mbar_init(v_full, 1);
-    tc::mbar_init(pv_done, 1);
     tc::mbar_init(acc_full, 1);
     tc::mbar_init(wr_full, 16);
     tc::mbar_init(wr_empty, 1);
+    tc::mbar_init(wr_peer, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc2::tmem_alloc2<512>(tmem_slot);
@@ -152,32 +175,33 @@ infonce_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int kb = 0; kb < B5_KB; ++kb) tc2::tma_load_2d_pair(smemA + kb * B5_TILE, &tmA, kb * 64, m0, a_full);
     }
     __syncwarp();
-    int stage = 0;
+    int slot = 0;
     uint32_t phase = 0;
-    auto load_b = [&](int k) {      // S operand of own tile k (global tile t = pair + 2k)
+    auto load_slot = [&](const CUtensorMap* tm, int c0, int c1) {
+      tc::mbar_wait(empty_bar + slot, phase ^ 1);
+      if (tc::elect_one()) {
+        if (leader) tc::mbar_expect_tx(full_bar + slot, 2 * B5_HALF);
+        tc2::tma_load_2d_pair(smemR + slot * B5_HALF, tm, c0, c1, full_bar + slot);
+      }
+      __syncwarp();
+      if (++slot == B5_SLOTS) { slot = 0; phase ^= 1; }
+    };
+    auto load_s = [&](int k) {      // S operand of own tile k (global tile t = pair + 2k): 8 slots
       const int jrow = (tz0 + (int)pair + 2 * k) * 128 + (int)prank * 64;
-      for (int kb = 0; kb < B5_KB; ++kb) {
-        tc::mbar_wait(empty_bar + stage, phase ^ 1);
-        if (tc::elect_one()) {
-          if (leader) tc::mbar_expect_tx(full_bar + stage, 2 * B5_HALF);
-          tc2::tma_load_2d_pair(smemB + stage * B5_HALF, &tmB, kb * 64, jrow, full_bar + stage);
-        }
-        __syncwarp();
-        if (++stage == B5_STAGES) { stage = 0; phase ^= 1; }
+      for (int kb = 0; kb < B5_KB; ++kb) load_slot(&tmB, kb * 64, jrow);
+    };
+    auto load_v = [&](int t) {      // V operand of tile t: 2 chunks of 64 j, each 2 slots (d-rows 0-63 / 64-127 of this CTA)
+      for (int c = 0; c < 2; ++c) {
+        load_slot(&tmBT, (tz0 + t) * 128 + c * 64, d0 + (int)prank * 128);
+        load_slot(&tmBT, (tz0 + t) * 128 + c * 64, d0 + (int)prank * 128 + 64);
       }
     };
     int k_next = 0;
-    if (n_own > 0) { load_b(0); k_next = 1; }
+    if (n_own > 0) { load_s(0); k_next = 1; }
     for (int t = 0; t < ntiles; ++t) {
       const bool own = ((uint32_t)t & 1u) == pair;
-      if (own && k_next < n_own) load_b(k_next++);
-      tc::mbar_wait(pv_done, ((uint32_t)t & 1) ^ 1);   // smemV free: PV(t-1) retired
-      if (tc::elect_one()) {
-        if (leader) tc::mbar_expect_tx(v_full, 4 * B5_TILE);
-        tc2::tma_load_2d_pair(smemV, &tmBT, (tz0 + t) * 128, d0 + (int)prank * 128, v_full);
-        tc2::tma_load_2d_pair(smemV + B5_TILE, &tmBT, (tz0 + t) * 128 + 64, d0 + (int)prank * 128, v_full);
-      }
-      __syncwarp();
+      if (own && k_next < n_own) load_s(k_next++);
+      load_v(t);
     }
   } else if (warp == 1) {
     if (leader) {
@@ -185,29 +209,55 @@ infonce_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       constexpr uint32_t idesc_s = tc::make_idesc_bf16(256, 128, 0, 0);
       constexpr uint32_t idesc_o = tc::make_idesc_bf16(256, B5_OW, 0, 0);
       const uint64_t adesc0 = tc::make_smem_desc(tc::smem_u32(smemA), 16, 1024);
-      const uint64_t bdesc0 = tc::make_smem_desc(tc::smem_u32(smemB), 16, 1024);
-      const uint64_t vdesc0 = tc::make_smem_desc(tc::smem_u32(smemV), 16, 1024);
+      const uint64_t rdesc0 = tc::make_smem_desc(tc::smem_u32(smemR), 16, 1024);
       const uint64_t wdesc0 = tc::make_smem_desc(tc::smem_u32(smemW), 16, 1024);
       tc::mbar_wait(a_full, 0);
-      int stage = 0;
+      int slot = 0;
       uint32_t phase = 0;
       auto issue_s = [&](int k) {
         const uint32_t d_tmem = tmem_base + (uint32_t)((k & 1) * 128);
         for (int kb = 0; kb < B5_KB; ++kb) {
-          tc::mbar_wait(full_bar + stage, phase);
+          tc::mbar_wait(full_bar + slot, phase);
           tc::tc_fence_after_sync();
           const uint64_t ad = adesc0 + (uint64_t)((kb * B5_TILE) >> 4);
-          const uint64_t bd = bdesc0 + (uint64_t)((stage * B5_HALF) >> 4);
+          const uint64_t bd = rdesc0 + (uint64_t)((slot * B5_HALF) >> 4);
           if (tc::elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) tc2::umma_ss2(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc_s, (kb | kk) != 0 ? 1u : 0u);
-            umma_commit_mask(empty_bar + stage, pmask);
+            umma_commit_mask(empty_bar + slot, pmask);
           }
           __syncwarp();
-          if (++stage == B5_STAGES) { stage = 0; phase ^= 1; }
+          if (++slot == B5_SLOTS) { slot = 0; phase ^= 1; }
         }
         if (tc::elect_one()) umma_commit_mask(s_full + (k & 1), pmask);
         __syncwarp();
+        TRACE(pair * 4 + 0, k);
+      };
+      // PV of one tile: two 64-column chunks, each = two consecutive ring slots (an even slot index, so never wrapping)
+      auto issue_pv = [&](int t, bool from_tmem, uint32_t w_tmem) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          tc::mbar_wait(full_bar + slot, phase);
+          tc::mbar_wait(full_bar + slot + 1, phase);
+          tc::tc_fence_after_sync();
+          const uint64_t vd = rdesc0 + (uint64_t)((slot * B5_HALF) >> 4);
+          if (tc::elect_one()) {
+            if (from_tmem) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                tc2::umma_ts2(tmem_O, w_tmem + (uint32_t)(c * 64 + kk * 8), vd + 2 * kk, idesc_o, (t | c | kk) != 0 ? 1u : 0u);
+            } else {
+              const uint64_t wd = wdesc0 + (uint64_t)((c * B5_TILE) >> 4);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) tc2::umma_ss2(tmem_O, wd + 2 * kk, vd + 2 * kk, idesc_o, (t | c | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit_mask(empty_bar + slot, pmask);
+            umma_commit_mask(empty_bar + slot + 1, pmask);
+          }
+          __syncwarp();
+          slot += 2;
+          if (slot == B5_SLOTS) { slot = 0; phase ^= 1; }
+        }
       };
       int k_next = 0, own_k = 0, f = 0;
       if (n_own > 0) { issue_s(0); k_next = 1; }
@@ -216,39 +266,25 @@ infonce_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (own) {
           if (k_next < n_own) issue_s(k_next++);
           tc::mbar_wait(p_full + (own_k & 1), ((uint32_t)own_k >> 1) & 1);
-          tc::mbar_wait(v_full, (uint32_t)t & 1);
-          tc::tc_fence_after_sync();
-          const uint32_t w_tmem = tmem_base + (uint32_t)((own_k & 1) * 128);
-          if (tc::elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const uint32_t a_t = w_tmem + (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8);
-              const uint64_t vd = vdesc0 + (uint64_t)((((kk >> 2) * B5_TILE) + (kk & 3) * 32) >> 4);
-              tc2::umma_ts2(tmem_O, a_t, vd, idesc_o, (t | kk) != 0 ? 1u : 0u);
-            }
-            umma_commit_mask(pv_done, pmask);
-          }
-          __syncwarp();
+          TRACE(pair * 4 + 1, own_k);
+          issue_pv(t, true, tmem_base + (uint32_t)((own_k & 1) * 128));
           ++own_k;
         } else {
+          // received tile f: own half (st.async tx on the local barrier) and the non-leader's half (relayed)
           mbar_wait_cluster(wr_full, (uint32_t)f & 1);
-          tc::mbar_wait(v_full, (uint32_t)t & 1);
-          tc::tc_fence_after_sync();
-          if (tc::elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const uint64_t off = (uint64_t)((((kk >> 2) * B5_TILE) + (kk & 3) * 32) >> 4);
-              tc2::umma_ss2(tmem_O, wdesc0 + off, vdesc0 + off, idesc_o, (t | kk) != 0 ? 1u : 0u);
-            }
-            umma_commit_mask(pv_done, pmask);
-            umma_commit_mask(wr_empty, qmask);     // the producers of this tile may overwrite our smemW
-          }
+          TRACE(pair * 4 + 2, f);
+          tc::fence_proxy_async_smem();          // generic-proxy (st.async) writes -> tensor-core (async proxy) reads
+          issue_pv(t, false, 0u);
+          if (tc::elect_one()) umma_commit_mask(wr_empty, qmask);     // the producers of this tile may overwrite our smemW
           __syncwarp();
           ++f;
         }
       }
       if (tc::elect_one()) umma_commit_mask(acc_full, pmask);
       __syncwarp();
+    } else {
+      // ---- non-leader: relay "my half of the received W tile is complete" to the leader's MMA warp
+      (void)n_foreign;
     }
   } else {
     // ---- softmax warps: own tiles only
@@ -278,6 +314,7 @@ infonce_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       asm volatile("bar.sync 1, 256;" ::: "memory");
       tc::mbar_wait(s_full + (k & 1), ((uint32_t)k >> 1) & 1);
       tc::tc_fence_after_sync();
+      if (warp == 2 && leader) TRACE(pair * 4 + 3, 2 * k);
       // the other pair must have consumed the tile we sent last time before its buffer is overwritten
       tc::mbar_wait(wr_empty, ((uint32_t)k & 1) ^ 1);
       const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((k & 1) * 128 + ch * 64);
@@ -311,12 +348,12 @@ infonce_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       tc::tmem_st_wait();
       tc::tc_fence_before_sync();
-      fence_proxy_async_all();               // generic-proxy stores -> visible to the consumer's tensor-core reads
       __syncwarp();
       if (lane == 0) {
         tc2::mbar_arrive_cluster(p_full_leader + (uint32_t)((k & 1) * 8));
-        mbar_arrive_cluster_release(wr_full_remote);
+        mbar_arrive_cluster_release(wr_full_remote);     // orders this warp's remote stores before the arrival
       }
+      if (warp == 2 && leader) TRACE(pair * 4 + 3, 2 * k + 1);
     }
     // epilogue: this warp stores its lane quarter x column half of the dA slice
     tc::mbar_wait(acc_full, 0);
@@ -377,7 +414,7 @@ int dmf_infonce_bwd_bf16_tc5(const void* A, long long lda, int Ma, const float* 
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, Bm, Nb, D, ldb, 64);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmBT, BmT, D, Nb, ldbt, 128);
+  rc = make_tmap_bf16_2d(&tmBT, BmT, D, Nb, ldbt, 64);
   if (rc) return rc;
   static int usable = -1;       // -1 unknown, 0 no, else max active 4-CTA clusters
   if (usable < 0) {
@@ -400,9 +437,13 @@ int dmf_infonce_bwd_bf16_tc5(const void* A, long long lda, int Ma, const float* 
         e = cudaOccupancyMaxActiveClusters(&ncl, infonce_bwd_tc5_kernel, &cfg);
       }
       if (e != cudaSuccess) { cudaGetLastError(); ncl = 0; }
-      // Measured on B200 (B = 65 536, D = 512): 9.56 ms vs 9.18 ms for the pair kernel -- only 33 four-CTA clusters are
-      // co-resident (132 of 148 SMs), the ring is 4 stages deep (smem is full) and the V-tile load is exposed
-      // between the two back-to-back PV MMAs.  Kept as an opt-in experiment: DMF_BWD_TC5=1.
+      // Measured on B200 (B = 65 536, D = 512): 9.09 ms vs 8.64 ms for the pair kernel alone, 115.5 vs 115.0 ms per
+      // training step (the pair kernel sits at the power cap, 1.55 GHz; this one runs at 1.96 GHz with the tensor pipe
+      // only 50 % active).  A %globaltimer trace of one cluster (-DDMF_TC5_TRACE, tools/trace_tc5.py) shows a latency-
+      // bound ping-pong between the two pairs: softmax + remote copy of a 128x128 W tile takes 2.6 us (TMEM read
+      // 64 B/clk, DSMEM store round trip inside the release), and with smem (227 KB) and TMEM (512 columns) both full
+      // there is no room for a third S buffer, a second receive buffer or a ring deeper than 8 x 8 KB to hide it.
+      // st.async (tx-counting remote stores, no writer fences) was slower (9.9 ms).  Opt-in: DMF_BWD_TC5=1.
       {
         const char* ev = getenv("DMF_BWD_TC5");
         if (!ev || !atoi(ev)) ncl = 0;
@@ -438,3 +479,9 @@ int dmf_infonce_bwd_bf16_tc5(const void* A, long long lda, int Ma, const float* 
                                                            (const uint16_t*)Bm, ldb, dA, ldda);
   return launched("dmf_infonce_bwd(bf16 quad)");
 }
+
+#ifdef DMF_TC5_TRACE
+extern "C" int dmf_tc5_trace_read(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, dmf::dmf_tc5_trace, sizeof(unsigned long long) * 8 * 2048);
+}
+#endif

@@ -18,8 +18,10 @@
 // in with 128-bit coalesced loads, the row threads overwrite each evidence value by its gradient IN PLACE,
 // and the tile (plus the fused-evidence tile) goes back out with 128-bit coalesced stores.  CTAs are
 // persistent (tiles dealt round-robin) and 4 fit per SM.  Algorithmic bytes per sample: 8VC + 4C + 16.
+#include <type_traits>
 #include "common.cuh"
 #include "special_math.cuh"
+#include "tc_common.cuh"
 
 namespace dmf {
 
@@ -34,13 +36,33 @@ __device__ __forceinline__ float sgn_mul(float d, float x) {
   return d == 0.f ? 0.f : t;
 }
 
+// 1D bulk copies (TMA engine, no registers, no per-thread address arithmetic): global -> shared completes on an
+// mbarrier, shared -> global is tracked by the issuing thread's bulk group.  Both need 16-byte aligned addresses
+// and sizes; the callers fall back to cooperative loops otherwise.
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   tc::smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)),
+               "r"(tc::smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ bool bulk_ok(const void* g, long long bytes) {
+  return ((reinterpret_cast<uintptr_t>(g) | (uintptr_t)bytes) & 15) == 0 && bytes > 0;
+}
+
 // MODE specialises the hot loops at compile time (the per-iteration uniform branches on runtime flags cost
 // ~10 BRA + dead selects per element, ncu source page of v3):
 //   0 = generic (any flag combination, eval outputs, DBF)      1 = train: loss + KL + conflict term, sum-type fusion
 //   2 = train: loss + KL, no conflict term, sum-type fusion
 enum { EDL_GENERIC = 0, EDL_TRAIN_DC = 1, EDL_TRAIN = 2 };
 
-template <int VT, int MODE>
+template <int VT, int MODE, bool CE>      // CE: C is even (64-bit shared-memory accesses on class pairs)
 __global__ void __launch_bounds__(kEdlThreads, 4)
 edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ labels, dmf_edl_params prm,
                  int spw, int ntiles, float lgammaC, const float* __restrict__ gscale_ptr,
@@ -48,6 +70,7 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
                  float* __restrict__ ale_out, int* __restrict__ pred_out, float* __restrict__ loss_parts) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[32];
+  __shared__ __align__(8) uint64_t ldbar;          // completion of the tile's bulk load
   constexpr int V = VT;
   const int C = prm.C, B = prm.B;
   const int VC = V * C;
@@ -72,24 +95,42 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
   const float w_dc = prm.dc_weight * prm.inv_B_global * inv_vm1;
   const float gs = (grad_out && gscale_ptr) ? __ldg(gscale_ptr) : 1.0f;
   float acc_edl = 0.f, acc_kl = 0.f, acc_dc = 0.f;
+  if (tid == 0) {
+    tc::mbar_init(&ldbar, 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  uint32_t ldphase = 0;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long b0 = (long long)tile * SPB;
     const int nS = (int)min((long long)SPB, (long long)B - b0);
     const int E = nS * VC;
-    // ---- copy in (coalesced 128-bit)
+    // ---- copy in: one bulk copy (TMA) per tile; cooperative 128-bit loads when the tile is not 16-byte aligned
     {
       const float* src = evid + b0 * VC;
-      if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-        const int n4 = E >> 2;
-        for (int i = tid; i < n4; i += kEdlThreads)
-          reinterpret_cast<float4*>(te)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-        for (int i = (n4 << 2) + tid; i < E; i += kEdlThreads) te[i] = __ldg(src + i);
+      if (bulk_ok(src, (long long)E * 4)) {
+        if (tid == 0) {
+          bulk_wait_read();                        // the bulk stores of the previous tile have read the buffers
+          tc::mbar_expect_tx(&ldbar, (uint32_t)E * 4u);
+          bulk_load(te, src, (uint32_t)E * 4u, &ldbar);
+        }
+        tc::mbar_wait(&ldbar, ldphase);
+        ldphase ^= 1u;
       } else {
-        for (int i = tid; i < E; i += kEdlThreads) te[i] = __ldg(src + i);
+        if (tid == 0) bulk_wait_read();
+        __syncthreads();
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+          const int n4 = E >> 2;
+          for (int i = tid; i < n4; i += kEdlThreads)
+            reinterpret_cast<float4*>(te)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+          for (int i = (n4 << 2) + tid; i < E; i += kEdlThreads) te[i] = __ldg(src + i);
+        } else {
+          for (int i = tid; i < E; i += kEdlThreads) te[i] = __ldg(src + i);
+        }
+        __syncthreads();
       }
     }
-    __syncthreads();
 
     const int bs = warp * spw + sl;                // sample slot within the tile
     const bool active = slot_ok && bs < nS;
@@ -104,11 +145,111 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
 
     // ---- row statistics
     float S = 0.f;
-    for (int c = 0; c < C; ++c) S += row[c] + 1.0f;
+    float gy = 0.f, gA = 0.f, psiT = 0.f, hy = 0.f;
+    if (MODE != EDL_GENERIC) {
+      // training path.  Row sum S: when the fused evidence is wanted (and C is even) ONE loop does both -- the V
+      // lanes of a sample split the class pairs, each lane sums its pairs over the views in reference order (fused
+      // evidence) and keeps a partial row sum per view; V shuffles per lane then complete the row sums.
+      if (CE && fused_out != nullptr) {
+        f2 part[V];
+#pragma unroll
+        for (int vv = 0; vv < V; ++vv) part[vv] = splat2(0.f);
+        const float* sb = te + (size_t)(active ? bs : 0) * VC;
+        float* fo = tf + (size_t)(active ? bs : 0) * C;
+        auto fuse_loop = [&](auto tag) {
+          constexpr int AGG = decltype(tag)::value;
+          for (int c = 2 * v; c < C; c += 2 * V) {
+            const f2 t0 = *reinterpret_cast<const f2*>(sb + c);
+            part[0] = add2(part[0], t0);
+            f2 sall = t0, d1 = splat2(0.f);
+#pragma unroll
+            for (int vv = 1; vv < V; ++vv) {
+              const f2 tv = *reinterpret_cast<const f2*>(sb + vv * C + c);
+              part[vv] = add2(part[vv], tv);
+              if (AGG == DMF_AGG_CML || AGG == DMF_AGG_AVG) sall = add2(sall, tv);
+              if (AGG == DMF_AGG_JOINT || AGG == DMF_AGG_DISENTANGLED) d1 = vv == 1 ? tv : add2(d1, tv);
+            }
+            f2 f;
+            if (AGG == DMF_AGG_CML) {
+              f = sall;
+            } else if (AGG == DMF_AGG_AVG) {
+              float a0, a1;
+              unpk2(sall, a0, a1);
+              f = pk2(a0 / (float)V, a1 / (float)V);
+            } else if (AGG == DMF_AGG_JOINT) {
+              f = fma2(splat2(0.5f), t0, mul2(splat2(0.5f), d1));
+            } else {
+              f = d1;
+            }
+            if (active) *reinterpret_cast<f2*>(fo + c) = f;
+          }
+        };
+        switch (prm.agg) {
+          case DMF_AGG_CML: fuse_loop(std::integral_constant<int, DMF_AGG_CML>{}); break;
+          case DMF_AGG_AVG: fuse_loop(std::integral_constant<int, DMF_AGG_AVG>{}); break;
+          case DMF_AGG_JOINT: fuse_loop(std::integral_constant<int, DMF_AGG_JOINT>{}); break;
+          default: fuse_loop(std::integral_constant<int, DMF_AGG_DISENTANGLED>{}); break;
+        }
+        // lane v needs the sum over the sample's lanes of part[v]: in round r it receives from lane (v + r) % V the
+        // partial that lane holds for view v, i.e. the source lane gives part[(own view - r) mod V]
+        float ps[V];
+#pragma unroll
+        for (int vv = 0; vv < V; ++vv) {
+          float lo, hi;
+          unpk2(part[vv], lo, hi);
+          ps[vv] = lo + hi;
+        }
+        float mine = ps[0];
+#pragma unroll
+        for (int vv = 1; vv < V; ++vv) mine = (v == vv) ? ps[vv] : mine;      // r = 0: own partial
+#pragma unroll
+        for (int r = 1; r < V; ++r) {
+          int recv = v - r;
+          if (recv < 0) recv += V;
+          float give = ps[0];
+#pragma unroll
+          for (int vv = 1; vv < V; ++vv) give = (recv == vv) ? ps[vv] : give;
+          int src = v + r;
+          if (src >= V) src -= V;
+          mine += __shfl_sync(0xffffffffu, give, base + src);
+        }
+        S = mine + fC;
+      } else {
+        f2 s2 = splat2(0.f);
+        for (int c = 0; c + 1 < C; c += 2) {
+          const f2 e2 = CE ? *reinterpret_cast<const f2*>(row + c) : pk2(row[c], row[c + 1]);
+          s2 = add2(s2, e2);
+        }
+        float s_lo, s_hi;
+        unpk2(s2, s_lo, s_hi);
+        S = (s_lo + s_hi) + ((C & 1) ? row[C - 1] : 0.f) + fC;
+      }
+      const float ay = row[y] + 1.0f;
+      const float St = S - ay + 1.0f;
+      const Gamma3x2 ga = gamma3x2(pk2(S, St));
+      const Gamma3x2 gb = gamma3x2(pk2(ay, ay));
+      float psiS, psi1S, psi1T, lgT, psiY, psi1Y, lgY, dummy;
+      unpk2(ga.psi, psiS, psiT);
+      unpk2(ga.psi1, psi1S, psi1T);
+      unpk2(ga.lgam, dummy, lgT);
+      unpk2(gb.psi, psiY, dummy);
+      unpk2(gb.psi1, psi1Y, dummy);
+      unpk2(gb.lgam, lgY, dummy);
+      const float am1y = ay - 1.0f;
+      hy = am1y * psi1Y;
+      gy = psi1S - psi1Y;
+      gA = psi1S - coef * (St - fC) * psi1T;
+      if (active) {
+        acc_edl += psiS - psiY;
+        // KL = lgamma(S~) - lgamma(C) - psi(S~) (S~ - C) + sum_{c != y} k(alpha_c),  k(x) = (x-1) psi(x) - lgamma(x)
+        acc_kl += (lgT - lgammaC) - psiT * (St - fC) - (am1y * psiY - lgY);
+      }
+    } else {
+      for (int c = 0; c < C; ++c) S += row[c] + 1.0f;
+    }
     const float iT = 1.0f / (S + 1e-8f);
     const float om = 1.0f - fC * iT;
-    float gy = 0.f, gA = 0.f, psiT = 0.f;
-    if (need_loss) {
+    if (MODE == EDL_GENERIC && need_loss) {
       const float ay = row[y] + 1.0f;
       const Gamma3 gS = gamma3_fast<false>(S);
       const Gamma3 gyv = gamma3_fast<false>(ay);
@@ -140,7 +281,7 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
       // ================= training fast path (compile-time flags) =================
       // fused evidence of the sum-type rules first (the evidence tile is overwritten by the gradient below):
       // the V lanes of a sample split the classes, each value summed over the views in reference order
-      if (fused_out != nullptr && active) {
+      if (!CE && fused_out != nullptr && active) {
         const float* sb = te + (size_t)bs * VC;
         for (int c = v; c < C; c += V) {
           float t0 = sb[c], sall = t0, d1 = 0.f;
@@ -157,52 +298,104 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
         }
       }
       __syncwarp();
-      // ONE pass over the classes: gamma triple, KL terms, EDL gradient and (MODE 1) the conflict sums; the part
-      // of the conflict gradient that needs the completed sums (rowK) is subtracted in a light second pass
+      // ONE pass over the classes, two at a time in packed fp32x2: (-k, h) of the pair, KL sum, EDL gradient and
+      // (MODE 1) the conflict sums.  Conflict term: with t_j = sign(p - p_j) (1 - u_j),
+      //   gp_c = sum_j t_j,   sum_j (1-u_j) sum_c |p - p_j| = sum_c sum_j d_j t_j,   sum_j (1-u_j) q_j = sum_c alpha_c gp_c
+      // so no per-pair accumulators are needed.  The part of the gradient that needs the completed sums (kk) and
+      // the label class are patched in a light second pass.
       constexpr bool kDC = MODE == EDL_TRAIN_DC && V > 1;
-      float pdv[V > 1 ? V - 1 : 1], qv[V > 1 ? V - 1 : 1];
-#pragma unroll
-      for (int jj = 0; jj < V - 1; ++jj) { pdv[jj] = 0.f; qv[jj] = 0.f; }
       const float wg = w_edl * gs, wd = w_dc * gs * om * iT;
-#pragma unroll 2
-      for (int c = 0; c < C; ++c) {
-        const float al = row[c] + 1.0f;
-        const float am1 = al - 1.0f;
-        const Gamma3 ga = gamma3_fast<true>(al);
-        const bool isy = c == y;
-        const float klt = am1 * (ga.psi - psiT) - ga.lgam;
-        acc_kl += (active && !isy) ? klt : 0.f;
-        float g = (isy ? gy : fmaf(coef * am1, ga.psi1, gA)) * wg;
+      const f2 one2 = splat2(1.0f), cw2 = splat2(coef * wg), ga2 = splat2(gA * wg), wd2 = splat2(wd), iT2 = splat2(iT);
+      f2 niTj2[V > 1 ? V - 1 : 1];
+#pragma unroll
+      for (int jj = 0; jj < V - 1; ++jj) niTj2[jj] = splat2(-iTj[jj]);
+      f2 acck = splat2(0.f), gu2 = splat2(0.f), dot2 = splat2(0.f);
+      auto pair_step = [&](f2 e2, bool both) -> f2 {
+        const f2 x2 = add2(e2, one2);
+        const KH2 r = gamma_kh2(x2);
+        if (both) {
+          acck = add2(acck, r.kn);
+        } else {
+          float k0, k1;
+          unpk2(r.kn, k0, k1);
+          acck = add2(acck, pk2(k0, 0.f));
+        }
+        f2 g2 = fma2(r.h, cw2, ga2);
         if (kDC) {
-          const float p = al * iT;
-          float gp = 0.f;
+          float al0, al1;
+          unpk2(x2, al0, al1);
+          const f2 p2 = mul2(x2, iT2);
+          float gp0 = 0.f, gp1 = 0.f;
 #pragma unroll
           for (int jj = 0; jj < V - 1; ++jj) {
-            const float alj = __shfl_sync(0xffffffffu, al, srcl[jj]);
-            const float d = p - alj * iTj[jj];
-            pdv[jj] += fabsf(d);
-            qv[jj] += sgn_mul(d, al);
-            gp += sgn_mul(d, omj[jj]);
+            const float alj0 = __shfl_sync(0xffffffffu, al0, srcl[jj]);
+            const float alj1 = __shfl_sync(0xffffffffu, al1, srcl[jj]);
+            const f2 d2 = fma2(pk2(alj0, alj1), niTj2[jj], p2);
+            float d0, d1;
+            unpk2(d2, d0, d1);
+            const int omb = __float_as_int(omj[jj]) & 0x7fffffff;
+            const float t0 = __int_as_float(omb | (__float_as_int(d0) & (int)0x80000000));
+            const float t1 = __int_as_float(omb | (__float_as_int(d1) & (int)0x80000000));
+            gu2 = fma2(d2, pk2(t0, both ? t1 : 0.f), gu2);
+            if (d0 != 0.f) gp0 += t0;
+            if (d1 != 0.f) gp1 += t1;
           }
-          g = fmaf(wd, gp, g);
+          if (!both) gp1 = 0.f;
+          const f2 gp2 = pk2(gp0, gp1);
+          dot2 = fma2(x2, gp2, dot2);
+          g2 = fma2(wd2, gp2, g2);
         }
-        if (active) row[c] = g;
+        return g2;
+      };
+#pragma unroll 1
+      for (int c = 0; c + 1 < C; c += 2) {
+        const f2 e2 = CE ? *reinterpret_cast<const f2*>(row + c) : pk2(row[c], row[c + 1]);
+        const f2 g2 = pair_step(e2, true);
+        if (active) {
+          if (CE) {
+            *reinterpret_cast<f2*>(row + c) = g2;
+          } else {
+            float g0, g1;
+            unpk2(g2, g0, g1);
+            row[c] = g0;
+            row[c + 1] = g1;
+          }
+        }
       }
+      if (!CE) {      // odd C: the last class rides alone (the upper lane runs on a dummy alpha = 1 and is discarded)
+        const f2 g2 = pair_step(pk2(row[C - 1], 0.f), false);
+        float g0, g1;
+        unpk2(g2, g0, g1);
+        if (active) row[C - 1] = g0;
+      }
+      {
+        float k0, k1;
+        unpk2(acck, k0, k1);
+        if (active) acc_kl -= k0 + k1;         // acck holds -k
+      }
+      float kk = 0.f;
       if (kDC) {
-        float gu = 0.f, dcs = 0.f, dot = 0.f;
-#pragma unroll
-        for (int jj = 0; jj < V - 1; ++jj) {
-          const float pdh = 0.5f * pdv[jj];
-          gu += pdh * omj[jj];
-          dcs += pdh * (om * omj[jj]);
-          dot = fmaf(omj[jj], qv[jj], dot);
-        }
-        dot *= om;
-        if (active) acc_dc += dcs * inv_vm1;
-        const float kk = w_dc * gs * (dot - 2.0f * gu * fC) * iT * iT;
-        if (active)
+        float a0, a1, b0, b1;
+        unpk2(gu2, a0, a1);
+        unpk2(dot2, b0, b1);
+        const float gus = a0 + a1;             // sum_j (1-u_j) sum_c |p - p_j|
+        const float dot = om * (b0 + b1);
+        if (active) acc_dc += 0.5f * gus * om * inv_vm1;
+        kk = w_dc * gs * (dot - gus * fC) * iT * iT;
+      }
+      if (active) {
+        // label class: its EDL gradient is gy, not gA + coef h  (the conflict part is the same for every class)
+        row[y] += (gy - gA - coef * hy) * wg;
+        if (kDC) {
+          if (CE) {
+            const f2 nkk = splat2(-kk);
 #pragma unroll 4
-          for (int c = 0; c < C; ++c) row[c] -= kk;
+            for (int c = 0; c < C; c += 2) *reinterpret_cast<f2*>(row + c) = add2(*reinterpret_cast<const f2*>(row + c), nkk);
+          } else {
+#pragma unroll 4
+            for (int c = 0; c < C; ++c) row[c] -= kk;
+          }
+        }
       }
     } else {
     // ---- loop A: pairwise conflict sums (models/losses.py:161-187): pd_kj = 0.5 sum_c |p_k - p_j|,
@@ -343,32 +536,42 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
       if (active && v == 0) ale_out[b0 + bs] = -tot;
     }
     }   // generic path
-    __syncthreads();
 
-    // ---- copy out (coalesced 128-bit): gradient tile, fused-evidence tile
-    if (grad_out) {
-      float* dst = grad_out + b0 * VC;
-      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-        const int n4 = E >> 2;
-        for (int i = tid; i < n4; i += kEdlThreads) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(te)[i];
-        for (int i = (n4 << 2) + tid; i < E; i += kEdlThreads) dst[i] = te[i];
-      } else {
-        for (int i = tid; i < E; i += kEdlThreads) dst[i] = te[i];
+    // ---- copy out: gradient tile and fused-evidence tile as bulk stores (cooperative stores when misaligned)
+    {
+      float* gdst = grad_out ? grad_out + b0 * VC : nullptr;
+      float* fdst = fused_out ? fused_out + b0 * C : nullptr;
+      const int nf = nS * C;
+      const bool gb = gdst && bulk_ok(gdst, (long long)E * 4), fb = fdst && bulk_ok(fdst, (long long)nf * 4);
+      if (gb || fb) tc::fence_proxy_async_smem();     // this thread's generic-proxy writes -> visible to the bulk engine
+      __syncthreads();
+      if (tid == 0 && (gb || fb)) {
+        if (gb) bulk_store(gdst, te, (uint32_t)E * 4u);
+        if (fb) bulk_store(fdst, tf, (uint32_t)nf * 4u);
+        bulk_commit();
       }
-    }
-    if (fused_out) {
-      float* dst = fused_out + b0 * C;
-      const int n = nS * C;
-      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-        const int n4 = n >> 2;
-        for (int i = tid; i < n4; i += kEdlThreads) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(tf)[i];
-        for (int i = (n4 << 2) + tid; i < n; i += kEdlThreads) dst[i] = tf[i];
-      } else {
-        for (int i = tid; i < n; i += kEdlThreads) dst[i] = tf[i];
+      if (gdst && !gb) {
+        if ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0) {
+          const int n4 = E >> 2;
+          for (int i = tid; i < n4; i += kEdlThreads) reinterpret_cast<float4*>(gdst)[i] = reinterpret_cast<const float4*>(te)[i];
+          for (int i = (n4 << 2) + tid; i < E; i += kEdlThreads) gdst[i] = te[i];
+        } else {
+          for (int i = tid; i < E; i += kEdlThreads) gdst[i] = te[i];
+        }
       }
+      if (fdst && !fb) {
+        if ((reinterpret_cast<uintptr_t>(fdst) & 15) == 0) {
+          const int n4 = nf >> 2;
+          for (int i = tid; i < n4; i += kEdlThreads) reinterpret_cast<float4*>(fdst)[i] = reinterpret_cast<const float4*>(tf)[i];
+          for (int i = (n4 << 2) + tid; i < nf; i += kEdlThreads) fdst[i] = tf[i];
+        } else {
+          for (int i = tid; i < nf; i += kEdlThreads) fdst[i] = tf[i];
+        }
+      }
+      if ((gdst && !gb) || (fdst && !fb)) __syncthreads();     // cooperative readers are done before the next tile lands
     }
-    __syncthreads();     // tiles are reused by the next tile of this CTA
   }
+  if (tid == 0) bulk_wait_read();
 
   if (loss_parts) {
     const float s_edl = block_sum(acc_edl, red);
@@ -469,7 +672,7 @@ __global__ void evidence_bwd_kernel(const float* __restrict__ h, const float* __
 
 using namespace dmf;
 
-template <int VT, int MODE>
+template <int VT, int MODE, bool CE>
 static int launch_edl_mode(const float* evid, const long long* labels, const dmf_edl_params* p, const float* gscale, float* fused,
                       float* grad, float* u, float* ale, int* pred, float* loss_parts, cudaStream_t st) {
   const int VC = VT * p->C;
@@ -481,7 +684,7 @@ static int launch_edl_mode(const float* evid, const long long* labels, const dmf
   const size_t smem = ((((size_t)SPB * VC + 3) & ~(size_t)3) + (size_t)SPB * p->C + 4) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(edl_fused_kernel<VT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(edl_fused_kernel<VT, MODE, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return fail((int)e, "dmf_edl_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -494,7 +697,7 @@ static int launch_edl_mode(const float* evid, const long long* labels, const dmf
   if (per_sm < 1) per_sm = 1;
   const long long capb = (long long)kNumSMs * per_sm;
   const unsigned blocks = (unsigned)(tiles < capb ? tiles : capb);
-  edl_fused_kernel<VT, MODE><<<blocks, kEdlThreads, smem, st>>>(evid, labels, *p, spw, (int)tiles, lgammaf((float)p->C), gscale,
+  edl_fused_kernel<VT, MODE, CE><<<blocks, kEdlThreads, smem, st>>>(evid, labels, *p, spw, (int)tiles, lgammaf((float)p->C), gscale,
                                                           fused, grad, u, ale, pred, loss_parts);
   return launched("dmf_edl_fused");
 }
@@ -505,11 +708,14 @@ static int launch_edl(const float* evid, const long long* labels, const dmf_edl_
   // the training call (gradient and/or loss, annealed KL on, no eval outputs, sum-type fusion) gets loops
   // specialised at compile time; everything else runs the generic instantiation
   const bool train = (grad || loss_parts) && p->coef != 0.f && !u && !ale && !pred && p->agg != DMF_AGG_DBF;
+  const bool ce = (p->C & 1) == 0;
   if (train && p->dc_weight != 0.f && VT > 1)
-    return launch_edl_mode<VT, EDL_TRAIN_DC>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
-  if (train && p->dc_weight == 0.f)
-    return launch_edl_mode<VT, EDL_TRAIN>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
-  return launch_edl_mode<VT, EDL_GENERIC>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
+    return ce ? launch_edl_mode<VT, EDL_TRAIN_DC, true>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st)
+              : launch_edl_mode<VT, EDL_TRAIN_DC, false>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
+  if (train && (p->dc_weight == 0.f || VT == 1))
+    return ce ? launch_edl_mode<VT, EDL_TRAIN, true>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st)
+              : launch_edl_mode<VT, EDL_TRAIN, false>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
+  return launch_edl_mode<VT, EDL_GENERIC, false>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
 }
 
 extern "C" int dmf_edl_fused(const float* evid, const long long* labels, const dmf_edl_params* p, const float* gscale,

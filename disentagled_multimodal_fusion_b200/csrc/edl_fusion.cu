@@ -25,10 +25,20 @@
 
 namespace dmf {
 
-constexpr int kEdlThreads = 256;
+// CTA shape, swept on B200 at B = 2^22, V = 4, C = 42 (tools/edl_sweep.sh; GB/s without / with the conflict term):
+//   256 x 4: 3785 / 3059    256 x 3: 3880 / 2934    128 x 8: 3942 / 3135    128 x 6: 4150 / 3132
+// Small CTAs desynchronise the load -> compute -> store phases of the tiles sharing an SM.
+#ifndef EDL_THREADS
+#define EDL_THREADS 128
+#endif
+#ifndef EDL_MINB
+#define EDL_MINB 6
+#endif
+constexpr int kEdlThreads = EDL_THREADS;
+constexpr int kEdlMinBlocks = EDL_MINB;          // resident CTAs per SM the register budget is sized for
 constexpr int kEdlWarps = kEdlThreads / 32;
 constexpr int kEdlMaxV = 8;
-constexpr int kEdlTileFloats = 10752;   // evidence tile per CTA (42 KB): 64 samples at V*C = 168
+constexpr int kEdlTileFloats = 1344 * kEdlWarps;   // evidence tile per CTA (42 KB at 8 warps: 64 samples at V*C = 168)
 
 // sign(d) * x for x >= 0 (alpha and 1-u are non-negative): copysign + a zero guard (3 instructions, no int->float)
 __device__ __forceinline__ float sgn_mul(float d, float x) {
@@ -63,7 +73,7 @@ __device__ __forceinline__ bool bulk_ok(const void* g, long long bytes) {
 enum { EDL_GENERIC = 0, EDL_TRAIN_DC = 1, EDL_TRAIN = 2 };
 
 template <int VT, int MODE, bool CE>      // CE: C is even (64-bit shared-memory accesses on class pairs)
-__global__ void __launch_bounds__(kEdlThreads, 4)
+__global__ void __launch_bounds__(kEdlThreads, kEdlMinBlocks)
 edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ labels, dmf_edl_params prm,
                  int spw, int ntiles, float lgammaC, const float* __restrict__ gscale_ptr,
                  float* __restrict__ fused_out, float* __restrict__ grad_out, float* __restrict__ u_out,
@@ -267,14 +277,24 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
     // statistics of the other views of this sample (lane base + (v + jj) % V)
     float omj[V > 1 ? V - 1 : 1], iTj[V > 1 ? V - 1 : 1], Sj[V > 1 ? V - 1 : 1];
     int srcl[V > 1 ? V - 1 : 1];
+    // power-of-two V in the training modes: partner jj = lane ^ (jj + 1) -- butterfly shuffles with immediate
+    // offsets, no index registers (with 64 registers per thread ptxas rematerialised the rotation indices inside
+    // the class loop: 16 of 112 instructions per class pair)
+    constexpr bool kXor = MODE != EDL_GENERIC && (V & (V - 1)) == 0;
 #pragma unroll
     for (int jj = 0; jj < V - 1; ++jj) {
       int vj = v + jj + 1;
       if (vj >= V) vj -= V;
       srcl[jj] = base + vj;
-      omj[jj] = __shfl_sync(0xffffffffu, om, srcl[jj]);
-      iTj[jj] = __shfl_sync(0xffffffffu, iT, srcl[jj]);
-      Sj[jj] = __shfl_sync(0xffffffffu, S, srcl[jj]);
+      if (kXor) {
+        omj[jj] = __shfl_xor_sync(0xffffffffu, om, jj + 1);
+        iTj[jj] = __shfl_xor_sync(0xffffffffu, iT, jj + 1);
+        Sj[jj] = 0.f;
+      } else {
+        omj[jj] = __shfl_sync(0xffffffffu, om, srcl[jj]);
+        iTj[jj] = __shfl_sync(0xffffffffu, iT, srcl[jj]);
+        Sj[jj] = __shfl_sync(0xffffffffu, S, srcl[jj]);
+      }
     }
 
     if (MODE != EDL_GENERIC) {
@@ -328,8 +348,8 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
           float gp0 = 0.f, gp1 = 0.f;
 #pragma unroll
           for (int jj = 0; jj < V - 1; ++jj) {
-            const float alj0 = __shfl_sync(0xffffffffu, al0, srcl[jj]);
-            const float alj1 = __shfl_sync(0xffffffffu, al1, srcl[jj]);
+            const float alj0 = kXor ? __shfl_xor_sync(0xffffffffu, al0, jj + 1) : __shfl_sync(0xffffffffu, al0, srcl[jj]);
+            const float alj1 = kXor ? __shfl_xor_sync(0xffffffffu, al1, jj + 1) : __shfl_sync(0xffffffffu, al1, srcl[jj]);
             const f2 d2 = fma2(pk2(alj0, alj1), niTj2[jj], p2);
             float d0, d1;
             unpk2(d2, d0, d1);
@@ -347,18 +367,36 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
         }
         return g2;
       };
-#pragma unroll 1
-      for (int c = 0; c + 1 < C; c += 2) {
-        const f2 e2 = CE ? *reinterpret_cast<const f2*>(row + c) : pk2(row[c], row[c + 1]);
-        const f2 g2 = pair_step(e2, true);
-        if (active) {
-          if (CE) {
-            *reinterpret_cast<f2*>(row + c) = g2;
-          } else {
-            float g0, g1;
-            unpk2(g2, g0, g1);
-            row[c] = g0;
-            row[c + 1] = g1;
+      if (kDC) {      // two pairs in flight amortise the loop overhead; without the conflict term ptxas does worse unrolled
+  #pragma unroll 2
+        for (int c = 0; c + 1 < C; c += 2) {
+          const f2 e2 = CE ? *reinterpret_cast<const f2*>(row + c) : pk2(row[c], row[c + 1]);
+          const f2 g2 = pair_step(e2, true);
+          if (active) {
+            if (CE) {
+              *reinterpret_cast<f2*>(row + c) = g2;
+            } else {
+              float g0, g1;
+              unpk2(g2, g0, g1);
+              row[c] = g0;
+              row[c + 1] = g1;
+            }
+          }
+        }
+      } else {
+  #pragma unroll 1
+        for (int c = 0; c + 1 < C; c += 2) {
+          const f2 e2 = CE ? *reinterpret_cast<const f2*>(row + c) : pk2(row[c], row[c + 1]);
+          const f2 g2 = pair_step(e2, true);
+          if (active) {
+            if (CE) {
+              *reinterpret_cast<f2*>(row + c) = g2;
+            } else {
+              float g0, g1;
+              unpk2(g2, g0, g1);
+              row[c] = g0;
+              row[c + 1] = g1;
+            }
           }
         }
       }
@@ -693,7 +731,7 @@ static int launch_edl_mode(const float* evid, const long long* labels, const dmf
   DMF_REQUIRE(tiles < (1LL << 31), "dmf_edl_fused: batch too large");
   // persistent CTAs: whole multiples of the SM count, as many as stay resident (4 by registers, smem permitting)
   int per_sm = (int)((220 * 1024) / (smem + 1024));
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > kEdlMinBlocks) per_sm = kEdlMinBlocks;
   if (per_sm < 1) per_sm = 1;
   const long long capb = (long long)kNumSMs * per_sm;
   const unsigned blocks = (unsigned)(tiles < capb ? tiles : capb);

@@ -411,6 +411,20 @@ def test_cast_dual_and_colsum_bf16(dmf):
         assert_close(cs2, ref.float().sum(0), 1e-5, "bf16 column sums")
 
 
+def test_transpose_bf16_bit_exact(dmf):
+    """dmf_transpose_bf16: the wide 64x64 kernel (full tiles) and the generic one (ragged shapes, padded leading
+    dimension, strided source) are pure data movement -> bit-exact against torch."""
+    ops = dmf.ops
+    gen = torch.Generator().manual_seed(22)
+    for R, Cc in ((4096, 512), (64, 64), (1024, 192), (1000, 520), (333, 47), (130, 64)):
+        x = torch.randn(R, Cc, generator=gen).to(DEV).bfloat16()
+        t = ops.transpose_bf16(x)
+        assert t.shape[0] == Cc and torch.equal(t[:, :R], x.T), (R, Cc)
+    big = torch.randn(256, 320, generator=gen).to(DEV).bfloat16()
+    view = big[:, 64:192]                                     # strided source (leading dimension 320)
+    assert torch.equal(ops.transpose_bf16(view)[:, :256], view.T)
+
+
 def test_dssl_bf16_pair_kernel_path(dmf):
     """DSSL step large enough (2B = 1024 rows, widths >= 128) that every MLP GEMM runs on the CTA-pair kernel
     with the fused transposed-copy epilogues and split-K wgrad; vs the fp32 path."""

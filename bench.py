@@ -172,11 +172,26 @@ def run_gpu(args, rank, world, local_rank):
     host = {}
     for k, d in (("x1", DIMS[0]), ("x2", DIMS[1])):
         host[k] = torch.randn(Bl, d, generator=gen).pin_memory()
-    host["v1"] = (host["x1"] + 0.01 * torch.randn(Bl, DIMS[0], generator=gen)).pin_memory()
-    host["v2"] = (host["x2"] + 0.01 * torch.randn(Bl, DIMS[1], generator=gen)).pin_memory()
     host["y"] = torch.randint(0, NCLS, (Bl,), generator=gen).pin_memory()
-    devin = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    # The batch a user hands to training_step is (x1, x2[, y]); the augmented views v1, v2 are made ON THE DEVICE by
+    # dmf_augment (DisentangledSSL.shared_step, noise_mode="device": SURVEY 8f-1 -- the reference's augment_data is an
+    # O(B) host loop).  Like the vMF noise, the two augmentation launches run before every step, outside the graph
+    # (host-side seed counter), into fixed buffers.
+    aug_seed = [0]
+
+    def with_views(bufset):
+        bufset["v1"] = torch.empty_like(bufset["x1"])
+        bufset["v2"] = torch.empty_like(bufset["x2"])
+        return bufset
+
+    def augment_views(bufset):
+        aug_seed[0] += 1
+        ops.augment(bufset["x1"], 0xA06 + aug_seed[0], 0, out=bufset["v1"])
+        ops.augment(bufset["x2"], 0xA06 + aug_seed[0], 1, out=bufset["v2"])
+    devin = with_views({k: v.to(dev) for k, v in host.items()})
+    augment_views(devin)
 
     noise_bufs = model.draw_noise(Bl, dev)          # fixed buffers, refilled in place every step (outside the graph)
 
@@ -222,6 +237,7 @@ def run_gpu(args, rank, world, local_rank):
     W = max(args.warmup, 3)
     for _ in range(W):
         model.draw_noise(Bl, dev, out=noise_bufs)
+        augment_views(devin)
         step(devin)
     l0 = _lib.launch_count()
     ops.PROFILE.clear()
@@ -229,6 +245,7 @@ def run_gpu(args, rank, world, local_rank):
     prof_steps = 2
     for _ in range(prof_steps):
         model.draw_noise(Bl, dev, out=noise_bufs)
+        augment_views(devin)
         step(devin)
     torch.cuda.synchronize()
     ops.PROFILE_ON = False
@@ -252,6 +269,7 @@ def run_gpu(args, rank, world, local_rank):
 
     def run_value():
         model.draw_noise(Bl, dev, out=noise_bufs)
+        augment_views(devin)
         if gstep is not None:
             gstep()
         else:
@@ -268,7 +286,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- end-to-end: pinned host -> device copies every step + loss read back
     copy_stream = torch.cuda.Stream()
-    bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    bufs = [with_views({k: torch.empty_like(v, device=dev) for k, v in host.items()}) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     gsteps = [None, None]
     if gstep is not None:
@@ -276,6 +294,7 @@ def run_gpu(args, rank, world, local_rank):
             for i in range(2):
                 for k, v in host.items():
                     bufs[i][k].copy_(v)
+                augment_views(bufs[i])
                 gsteps[i] = GraphedStep(lambda i=i: step(bufs[i], capturable=True), warmup=1, pool=gstep.pool(),
                                         stream=torch.cuda.current_stream())
         except Exception:  # noqa: BLE001
@@ -302,6 +321,7 @@ def run_gpu(args, rank, world, local_rank):
         copy_stream.wait_stream(torch.cuda.current_stream())   # next copy must not overwrite a buffer in use
         prefetch(i ^ 1)
         model.draw_noise(Bl, dev, out=noise_bufs)
+        augment_views(bufs[i])
         out = gsteps[i]() if gsteps[i] is not None else step(bufs[i])
         d2h[i].copy_(out.reshape(1), non_blocking=True)         # device->host read of the step's loss
         d2h_ev[i].record()
@@ -368,7 +388,7 @@ def run_gpu(args, rank, world, local_rank):
         "config": {"workload": "C5 DisentangledSSL 2x1024-d, hidden 512, embed 512, T=0.07 + 3-head evidential probe (C=10)",
                    "global_batch": Bg, "per_gpu_batch": Bl, "parallelism": f"dp{world}",
                    "l2": "inputs (1 GiB/step/GPU at dp1) and embeddings are larger than the 126 MB L2",
-                   "noise": "vMF noise drawn on device every step (dmf_vmf_draw)", "launch": launch_mode},
+                   "noise": "vMF noise and the augmented views v1, v2 drawn on device every step (dmf_vmf_draw, dmf_augment)", "launch": launch_mode},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},

@@ -166,13 +166,13 @@ def vmf_draw(rows: int, D: int, kappa: float, seed: int, offset: int, device, ou
 
 
 def augment(x: Tensor, seed: int, offset: int = 0, noise_scale: float = 0.01, drop_scale: int = 10,
-            return_choice: bool = False):
+            return_choice: bool = False, out: Optional[Tensor] = None):
     """Device-side ``augment_data`` (utils.py:118-151): per row noise / random column drop / identity with
     probability 1/3 each.  Distribution-equal to the reference's host loop, not stream-equal."""
     L.require_device()
     x = _f32c(x)
     B, D = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if out is None else out        # ``out``: fixed buffer refilled in place (CUDA-graph replays)
     ch = torch.empty(B, dtype=torch.int32, device=x.device) if return_choice else None
     check(lib.dmf_augment(ptr(x), x.stride(0), ptr(y), y.stride(0), B, D, float(noise_scale), int(drop_scale), int(seed),
                           int(offset), ptr(ch), stream()))

@@ -70,7 +70,127 @@ __device__ __forceinline__ bool bulk_ok(const void* g, long long bytes) {
 // ~10 BRA + dead selects per element, ncu source page of v3):
 //   0 = generic (any flag combination, eval outputs, DBF)      1 = train: loss + KL + conflict term, sum-type fusion
 //   2 = train: loss + KL, no conflict term, sum-type fusion
-enum { EDL_GENERIC = 0, EDL_TRAIN_DC = 1, EDL_TRAIN = 2 };
+//   3 = eval: forward only (fused evidence, u, aleatoric, argmax), sum-type fusion
+enum { EDL_GENERIC = 0, EDL_TRAIN_DC = 1, EDL_TRAIN = 2, EDL_EVAL = 3 };
+
+// Forward-only pass of one tile (models/evidential_probe.py:139-143,177-181, analysis.py:27-34): fused evidence of the
+// sum-type rules, u = C / S, aleatoric = -sum_c (a_c/S)(psi(a_c + 1) - psi(S + 1)), per-view and fused argmax.
+// Thread = one (sample, view) row as in the training path; the V lanes of a sample split the class pairs for the
+// fused evidence and for the digamma terms (packed fp32x2), every lane scans its own row for the per-view argmax and
+// the fused row for S / the fused argmax in class order (same summation order as the generic path: the epistemic
+// ranking stays bit-exact).
+template <int V, bool CE>
+__device__ __forceinline__ void edl_eval_tile(const float* te, float* tf, const dmf_edl_params& prm, int C, int bs, int v, int base,
+                                              bool active, long long b0, float* __restrict__ u_out,
+                                              float* __restrict__ ale_out, int* __restrict__ pred_out) {
+  const int VC = V * C;
+  const float fC = (float)C;
+  const float* sb = te + (size_t)(active ? bs : 0) * VC;
+  const float* row = sb + (active ? v : 0) * C;
+  float* fo = tf + (size_t)(active ? bs : 0) * C;
+  // (1) fused evidence, views summed in reference order
+  if (CE) {
+    auto fuse_loop = [&](auto tag) {
+      constexpr int AGG = decltype(tag)::value;
+      for (int c = 2 * v; c < C; c += 2 * V) {
+        const f2 t0 = *reinterpret_cast<const f2*>(sb + c);
+        f2 sall = t0, d1 = splat2(0.f);
+#pragma unroll
+        for (int vv = 1; vv < V; ++vv) {
+          const f2 tv = *reinterpret_cast<const f2*>(sb + vv * C + c);
+          if (AGG == DMF_AGG_CML || AGG == DMF_AGG_AVG) sall = add2(sall, tv);
+          if (AGG == DMF_AGG_JOINT || AGG == DMF_AGG_DISENTANGLED) d1 = vv == 1 ? tv : add2(d1, tv);
+        }
+        f2 f;
+        if (AGG == DMF_AGG_CML) {
+          f = sall;
+        } else if (AGG == DMF_AGG_AVG) {
+          float a0, a1;
+          unpk2(sall, a0, a1);
+          f = pk2(a0 / (float)V, a1 / (float)V);
+        } else if (AGG == DMF_AGG_JOINT) {
+          f = fma2(splat2(0.5f), t0, mul2(splat2(0.5f), d1));
+        } else {
+          f = d1;
+        }
+        if (active) *reinterpret_cast<f2*>(fo + c) = f;
+      }
+    };
+    switch (prm.agg) {
+      case DMF_AGG_CML: fuse_loop(std::integral_constant<int, DMF_AGG_CML>{}); break;
+      case DMF_AGG_AVG: fuse_loop(std::integral_constant<int, DMF_AGG_AVG>{}); break;
+      case DMF_AGG_JOINT: fuse_loop(std::integral_constant<int, DMF_AGG_JOINT>{}); break;
+      default: fuse_loop(std::integral_constant<int, DMF_AGG_DISENTANGLED>{}); break;
+    }
+  } else if (active) {
+    for (int c = v; c < C; c += V) {
+      float t0 = sb[c], sall = t0, d1 = 0.f;
+#pragma unroll
+      for (int vv = 1; vv < V; ++vv) { const float tv = sb[vv * C + c]; sall += tv; d1 += tv; }
+      float f;
+      switch (prm.agg) {
+        case DMF_AGG_CML: f = sall; break;
+        case DMF_AGG_AVG: f = sall / (float)V; break;
+        case DMF_AGG_JOINT: f = 0.5f * t0 + 0.5f * d1; break;
+        default: f = d1; break;
+      }
+      fo[c] = f;
+    }
+  }
+  __syncwarp();
+  // (2) per-view argmax (first maximum wins), (3) S and argmax of the fused row in class order
+  float bestv = row[0], best = fo[0], Sf = fo[0] + 1.0f;
+  int argv = 0, arg = 0;
+  if (pred_out) {
+    for (int c = 1; c < C; ++c) {
+      const float e = row[c];
+      if (e > bestv) { bestv = e; argv = c; }
+    }
+  }
+  for (int c = 1; c < C; ++c) {
+    const float f = fo[c];
+    Sf += f + 1.0f;
+    if (f > best) { best = f; arg = c; }
+  }
+  if (active) {
+    if (u_out && v == 0) u_out[b0 + bs] = fC / Sf;
+    if (pred_out) {
+      int* po = pred_out + (b0 + bs) * (V + 1);
+      po[v] = argv;
+      if (v == 0) po[V] = arg;
+    }
+  }
+  // (4) aleatoric: the sample's lanes split the class pairs; psi in packed fp32x2
+  if (ale_out) {
+    const float iSf = 1.0f / Sf;
+    float psiSf, dummy;
+    unpk2(gamma_psi2(pk2(Sf + 1.0f, Sf + 1.0f)), psiSf, dummy);
+    float a = 0.f;
+    if (CE) {
+      f2 a2 = splat2(0.f);
+      const f2 npsi = splat2(-psiSf), is2 = splat2(iSf);
+      for (int c = 2 * v; c < C; c += 2 * V) {
+        const f2 al = add2(*reinterpret_cast<const f2*>(fo + c), splat2(1.0f));
+        const f2 ps = gamma_psi2(add2(al, splat2(1.0f)));
+        a2 = fma2(mul2(al, is2), add2(ps, npsi), a2);
+      }
+      float a0, a1;
+      unpk2(a2, a0, a1);
+      a = a0 + a1;
+    } else {
+      for (int c = v; c < C; c += V) {
+        const float al = fo[c] + 1.0f;
+        float ps;
+        unpk2(gamma_psi2(pk2(al + 1.0f, al + 1.0f)), ps, dummy);
+        a += (al * iSf) * (ps - psiSf);
+      }
+    }
+    float tot = 0.f;
+#pragma unroll
+    for (int vv = 0; vv < V; ++vv) tot += __shfl_sync(0xffffffffu, a, base + vv);
+    if (active && v == 0) ale_out[b0 + bs] = -tot;
+  }
+}
 
 template <int VT, int MODE, bool CE>      // CE: C is even (64-bit shared-memory accesses on class pairs)
 __global__ void __launch_bounds__(kEdlThreads, kEdlMinBlocks)
@@ -147,6 +267,9 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
     // inactive lanes run the same instruction stream on a dummy row (row 0 of the tile) so that the
     // full-mask shuffles stay convergent; they never store
     float* row = te + (size_t)(active ? bs * V + v : 0) * C;
+    if (MODE == EDL_EVAL) {
+      edl_eval_tile<V, CE>(te, tf, prm, C, bs, v, base, active, b0, u_out, ale_out, pred_out);
+    } else {
     int y = 0;
     if (active) {
       const long long yl = labels[b0 + bs];
@@ -574,6 +697,7 @@ edl_fused_kernel(const float* __restrict__ evid, const long long* __restrict__ l
       if (active && v == 0) ale_out[b0 + bs] = -tot;
     }
     }   // generic path
+    }   // not EDL_EVAL
 
     // ---- copy out: gradient tile and fused-evidence tile as bulk stores (cooperative stores when misaligned)
     {
@@ -747,6 +871,10 @@ static int launch_edl(const float* evid, const long long* labels, const dmf_edl_
   // specialised at compile time; everything else runs the generic instantiation
   const bool train = (grad || loss_parts) && p->coef != 0.f && !u && !ale && !pred && p->agg != DMF_AGG_DBF;
   const bool ce = (p->C & 1) == 0;
+  const bool eval = !grad && !loss_parts && fused && p->agg != DMF_AGG_DBF;
+  if (eval)
+    return ce ? launch_edl_mode<VT, EDL_EVAL, true>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st)
+              : launch_edl_mode<VT, EDL_EVAL, false>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);
   if (train && p->dc_weight != 0.f && VT > 1)
     return ce ? launch_edl_mode<VT, EDL_TRAIN_DC, true>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st)
               : launch_edl_mode<VT, EDL_TRAIN_DC, false>(evid, labels, p, gscale, fused, grad, u, ale, pred, loss_parts, st);

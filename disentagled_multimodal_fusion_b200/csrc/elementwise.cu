@@ -237,7 +237,7 @@ __device__ __forceinline__ unsigned aug_key(unsigned long long seed, unsigned lo
   return (unsigned)((z ^ (z >> 31)) >> 32);
 }
 
-__global__ void __launch_bounds__(256, 2) augment_kernel(const float* __restrict__ X, long long ldx, float* __restrict__ Y, long long ldy, int rows,
+__global__ void __launch_bounds__(256) augment_kernel(const float* __restrict__ X, long long ldx, float* __restrict__ Y, long long ldy, int rows,
                                int D, float noise_scale, int n_drop, unsigned long long seed, unsigned long long offset,
                                int* __restrict__ choice_out) {
   const int lane = threadIdx.x & 31;
@@ -255,8 +255,27 @@ __global__ void __launch_bounds__(256, 2) augment_kernel(const float* __restrict
   if (choice_out && lane == 0) choice_out[row] = t;
   const float* x = X + (long long)row * ldx;
   float* y = Y + (long long)row * ldy;
+  // D <= 1024: the lane's <= 32 elements are loaded up front (32 independent loads in flight: one row per warp
+  // with a load -> store dependency per iteration left the kernel latency-bound at 16 warps per SM)
+  float xv[32];
+  const bool cached = D <= 1024;
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int k = lane + 32 * i;
+      xv[i] = k < D ? x[k] : 0.f;
+    }
+  }
   if (t == 0) {
-    for (int k = lane; k < D; k += 32) y[k] = x[k] + noise_scale * curand_normal(&st);
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int k = lane + 32 * i;
+        if (k < D) y[k] = xv[i] + noise_scale * curand_normal(&st);
+      }
+    } else {
+      for (int k = lane; k < D; k += 32) y[k] = x[k] + noise_scale * curand_normal(&st);
+    }
   } else if (t == 1 && n_drop > 0 && D <= 1024) {
     // D <= 1024: the <= 32 keys of this lane are hashed ONCE into registers; every bisection step is then 32
     // compares instead of 32 hashes (two 64-bit multiplies each): the drop rows cost 1/20 of the generic path below
@@ -293,7 +312,7 @@ __global__ void __launch_bounds__(256, 2) augment_kernel(const float* __restrict
         const unsigned tm = __ballot_sync(0xffffffffu, tie);
         const int rank_in = __popc(tm & ((1u << lane) - 1u));
         const bool drop = k < D && (key[i] < lo || (tie && rank_in < ties_left));
-        if (k < D) y[k] = drop ? 0.f : x[k];
+        if (k < D) y[k] = drop ? 0.f : xv[i];
         ties_left -= __popc(tm);
         if (ties_left < 0) ties_left = 0;
       }
@@ -326,6 +345,12 @@ __global__ void __launch_bounds__(256, 2) augment_kernel(const float* __restrict
       if (k < D) y[k] = drop ? 0.f : x[k];
       ties_left -= __popc(tm);
       if (ties_left < 0) ties_left = 0;
+    }
+  } else if (cached) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int k = lane + 32 * i;
+      if (k < D) y[k] = xv[i];
     }
   } else {
     for (int k = lane; k < D; k += 32) y[k] = x[k];

@@ -162,7 +162,7 @@ def run_gpu(args, rank, world, local_rank):
     model = pkg.DisentangledSSL(output_dim=DIMS, hidden_dim=HID, embed_dim=EMB, a=1.0, vmfkappa=1, precision=prec,
                                 noise_mode="device").to(dev)
     probe = pkg.EvidentialProbeModule(model, num_classes=NCLS, input_dim=EMB, hidden_dim=(128,), lr=3e-3, dropout=0.0,
-                                      annealing_start=50, aggregation="cml", fused=1).to(dev)
+                                      annealing_start=50, aggregation="cml", fused=1, precision=prec).to(dev)
     probe.backbone = model                    # the probe reads the live (frozen-for-it) backbone of this step
     probe.criterion.annealing_step = 5
     bb = FlatParams(model.parameters())

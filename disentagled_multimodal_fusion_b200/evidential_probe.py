@@ -109,7 +109,7 @@ class EvidentialProbeModule(_ProbeBase):
     """models/evidential_probe.py:11-212 (1 shared + N specific heads)."""
 
     def __init__(self, backbone, num_classes, input_dim, hidden_dim=(32), lr=1e-4, dropout=0.3, annealing_start=20,
-                 optimizer=torch.optim.Adam, freeze_backbone=True, aggregation='cml', fused=1):
+                 optimizer=torch.optim.Adam, freeze_backbone=True, aggregation='cml', fused=1, precision="fp32"):
         super().__init__()
         self.backbone = copy.deepcopy(backbone)
         if not hasattr(self.backbone, 'N'):
@@ -131,6 +131,9 @@ class EvidentialProbeModule(_ProbeBase):
         self.x_specs = nn.ModuleList([
             EvidentialNN(dropout=dropout, output_dims=num_classes, layers=(input_dim, *hidden_dim))
             for _ in range(self.N)])
+        # "bf16": hidden layers of the heads on the tensor cores, evidence layer in fp32 (ops.grouped_mlp)
+        for head in [self.x_shared, *self.x_specs]:
+            head.precision = precision
         self._init_metrics(num_classes)
         self.criterion = AvgTrustedLoss(num_views=self.num_views, annealing_start=annealing_start)
         if freeze_backbone:

@@ -411,8 +411,8 @@ class _GroupedMLP(torch.autograd.Function):
                     else:
                         actTs[g].append(None)
                 descs.append(d)
-            gemm_tc(descs, L.EPI_BIAS if last else L.EPI_BIAS_RELU)
-        return outs, dict(acts=acts, actTs=actTs, Wb=Wb)
+            gemm_tc(descs, L.EPI_BIAS if (last and final != "relu") else L.EPI_BIAS_RELU)
+        return outs, dict(acts=acts, actTs=actTs, Wb=Wb, outs=outs if final == "relu" else None)
 
     @staticmethod
     def _bwd_bf16(ctx, grads):
@@ -431,6 +431,8 @@ class _GroupedMLP(torch.autograd.Function):
             if dy is None:
                 dy = torch.zeros(M, N, dtype=torch.float32, device=dev)
             dy = _f32c(dy)
+            if final == "relu":                      # the call ends in a ReLU: its mask is the saved output
+                dy = dy * (ctx.saved["outs"][g] > 0)
             Np, Mp = (N + 7) // 8 * 8, (M + 7) // 8 * 8
             b = torch.empty(M, Np, dtype=torch.bfloat16, device=dev)
             bT = torch.empty(N, Mp, dtype=torch.bfloat16, device=dev)
@@ -530,6 +532,23 @@ def grouped_mlp(xs: Sequence[Tensor], weights: Sequence[Sequence[Tensor]], biase
     of the final output from the last GEMM's epilogue, ``extras_prefilled`` = the tail columns of x already
     hold bf16(extra)."""
     G, NL = len(xs), len(weights[0])
+    if precision == "bf16" and final == "evidence":
+        # evidential heads in the bf16 path: the wide hidden layers (K = embedding width) run on the tensor cores
+        # (bf16 operands, fp32 accumulate, ReLU in the epilogue); the narrow evidence layer (hidden -> C) and its
+        # activation stay in fp32 -- exp() amplifies logit errors, and that layer is < 2 % of the head's FLOPs
+        if NL < 2 or extras is not None:
+            precision = "fp32"
+        else:
+            if dropout_masks is not None and NL > 2:
+                raise NotImplementedError("bf16 evidential heads: dropout on inner hidden layers")
+            hid = grouped_mlp(xs, [list(w[:-1]) for w in weights], [list(b[:-1]) for b in biases], final="relu",
+                              precision="bf16")
+            if dropout_masks is not None:
+                hid = [h if (m is None or m[-1] is None) else h * m[-1] for h, m in zip(hid, dropout_masks)]
+            return grouped_mlp(hid, [[w[-1]] for w in weights], [[b[-1]] for b in biases], final="evidence",
+                               precision="fp32")
+    if final == "relu" and precision != "bf16":
+        raise L.DmfError("grouped_mlp: final='relu' is an internal mode of the bf16 path")
     flat = list(xs) + (list(extras) if extras is not None else [None] * G)
     for g in range(G):
         flat += list(weights[g])

@@ -756,3 +756,113 @@ def test_device_resident_pipeline_c2(dmf):
     res = analysis.evaluate_subjective_model_with_shared(probe, te)
     accs = [v["accuracy"] for k, v in res.items() if isinstance(v, dict) and "accuracy" in v]
     assert accs and max(accs) > 0.5, res
+
+
+# ------------------------------------------------------------------------------------- BASELINE.json full sizes
+def test_infonce_full_size_against_chunked_fp32(dmf):
+    """C5 size (B = 65 536, D = 512, T = 0.07): the bf16 tensor-core path (fixed-shift forward, recompute backward)
+    against a chunked fp32 torch evaluation of the same formulas (models/losses.py:64-99; the [B, B] logits never
+    exist at once: 16 row chunks of 1 GB).  Loss to 2e-3, the two no-grad diagnostics to 1e-2, gradient rows of 256
+    sampled anchors per view to the bf16 tolerance 2e-2 (BASELINE.json north_star)."""
+    import torch.nn.functional as Fn
+    B, D, Tm = 65536, 512, 0.07
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    z0 = Fn.normalize(torch.randn(B, D, device=DEV, generator=gen), dim=-1)
+    z1 = Fn.normalize(0.6 * z0 + 0.8 * Fn.normalize(torch.randn(B, D, device=DEV, generator=gen), dim=-1), dim=-1)
+    z0.requires_grad_()
+    z1.requires_grad_()
+    loss, lx, ly = dmf.ops.infonce(z0, z1, Tm, "bf16", unit_norm=True)
+    loss.backward()
+    a, b = z0.detach(), z1.detach()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+
+    def row_lse(p, q):
+        out = torch.empty(B, device=DEV)
+        for c in range(0, B, 4096):
+            out[c:c + 4096] = torch.logsumexp((p[c:c + 4096] @ q.T) / Tm, dim=1)
+        return out
+    lse0, lse1 = row_lse(a, b), row_lse(b, a)               # view-0 / view-1 anchors against the other view
+    pos = (a * b).sum(1) / Tm
+    ref_loss = ((lse0 - pos).sum() + (lse1 - pos).sum()) / (2 * B)
+    ref_lx = (row_lse(a, a) - (a * a).sum(1) / Tm).mean()
+    ref_ly = (row_lse(b, b) - (b * b).sum(1) / Tm).mean()
+    assert_close(loss, ref_loss, 2e-3, "loss at B=65536")
+    # loss_x / loss_y are cancellation residues (lse - s_ii ~ 0.05 with s_ii = 1/T = 14.3): bf16 tolerance
+    assert_close(lx, ref_lx, 1e-2, "loss_x at B=65536")
+    assert_close(ly, ref_ly, 1e-2, "loss_y at B=65536")
+    rows = torch.randperm(B, device=DEV, generator=gen)[:256]
+    for p, q, lp, lq, g, tag in ((a, b, lse0, lse1, z0.grad, "dz0"), (b, a, lse1, lse0, z1.grad, "dz1")):
+        S = (p[rows] @ q.T) / Tm                              # [256, B]
+        W = torch.exp(S - lp[rows, None]) + torch.exp(S - lq[None, :])
+        ref = (W @ q - 2.0 * q[rows]) / (2 * B * Tm)
+        assert_close(g[rows], ref, 2e-2, f"{tag} rows at B=65536")
+    # size-independent property: the loss is invariant under a common rotation of both views (Householder reflection)
+    u = Fn.normalize(torch.randn(D, device=DEV, generator=gen), dim=0)
+    refl = lambda z: z - 2.0 * (z @ u)[:, None] * u[None, :]          # noqa: E731
+    loss_r, _, _ = dmf.ops.infonce(refl(a), refl(b), Tm, "bf16", unit_norm=True)
+    assert_close(loss_r, loss, 2e-3, "rotation invariance")
+
+
+def test_edl_full_size_sampled_against_oracle(dmf):
+    """Bandwidth-benchmark size of the fused EDL kernel (B = 2^20, V = 4, C = 42; 0.7 GB of evidence): gradient,
+    fused evidence, u, aleatoric and argmax of 2048 sampled samples against the CPU oracle on exactly those samples
+    (the kernel's gradient carries 1/B of the full batch, the oracle's 1/n of the subset)."""
+    from oracle import port
+    gen = torch.Generator().manual_seed(9)
+    B, V, C, n = 1 << 20, 4, 42, 2048
+    evid = torch.exp((torch.randn(B, V, C, generator=gen) * 2).clamp(-10, 10))
+    y = torch.randint(0, C, (B,), generator=gen)
+    idx = torch.randperm(B, generator=gen)[:n]
+    ed = evid.to(DEV).requires_grad_()
+    yd = y.to(DEV)
+    for fused_flag in (1, 0):
+        loss, fe, parts = dmf.ops.edl_fused_loss(ed, yd, "cml", 7, 20, fused=fused_flag)
+        (gd,) = torch.autograd.grad(loss, ed)
+        es = evid[idx].clone().requires_grad_()
+        ref = port.avg_trusted_loss(es, y[idx], None, fused_flag, 7, 20)
+        (gs,) = torch.autograd.grad(ref, es)
+        assert_close(gd[idx.to(DEV)] * (B / n), gs, FP32, f"gradient of sampled rows, fused={fused_flag}")
+        assert_close(fe[idx.to(DEV)], port.fuse(evid[idx], "cml"), 2e-6, "fused evidence of sampled rows")
+        # full-batch mean against the mean of a 2048-sample subset: statistical agreement only
+        lv, rv = float(loss.detach()), float(ref.detach())
+        assert np.isfinite(lv) and abs(lv - rv) < 0.2 * abs(rv), (lv, rv)
+    for agg in ("cml", "avg"):
+        fused, u, ale, pred = dmf.ops.edl_summaries(evid.to(DEV), yd, agg)
+        fs = port.fuse(evid[idx], agg)
+        ru, rale, rarg = port.uncertainty_summaries(fs)
+        j = idx.to(DEV)
+        assert_close(fused[j], fs, 2e-6, f"fused {agg}")
+        assert_close(u[j], ru, 2e-6, f"u {agg}")
+        assert_close(ale[j], rale, FP32, f"aleatoric {agg}")
+        assert torch.equal(pred[j, -1].long().cpu(), rarg), f"fused argmax {agg}"
+        assert torch.equal(pred[j, :-1].long().cpu(), evid[idx].argmax(dim=2)), "per-view argmax"
+
+
+def test_probe_heads_bf16_tensor_core_path(dmf):
+    """precision='bf16' evidential heads (hidden layers on the tensor cores, evidence layer in fp32) against the fp32
+    heads with the same weights: evidences / loss within the bf16 tolerance, weight gradients close."""
+    import copy
+    torch.manual_seed(4)
+    B, D, C = 1024, 256, 10
+    bb = dmf.DisentangledSSL(output_dim=[96, 80], hidden_dim=64, embed_dim=D, precision="fp32").to(DEV)
+    p32 = dmf.EvidentialProbeModule(bb, num_classes=C, input_dim=D, hidden_dim=(128,), dropout=0.0, annealing_start=10,
+                                    aggregation="cml", fused=1).to(DEV)
+    p16 = copy.deepcopy(p32)
+    for head in [p16.x_shared, *p16.x_specs]:
+        head.precision = "bf16"
+    gen = torch.Generator().manual_seed(5)
+    batch = [torch.randn(B, 96, generator=gen).to(DEV), torch.randn(B, 80, generator=gen).to(DEV),
+             torch.randint(0, C, (B,), generator=gen).to(DEV)]
+    outs = []
+    for m in (p32, p16):
+        m.criterion.annealing_step = 3
+        loss, ev_a, _, ev = m.shared_step(batch)
+        loss.backward()
+        outs.append((loss.detach(), ev.detach(), ev_a.detach(), m.x_shared.weights()[0].grad, m.x_specs[1].weights()[1].grad))
+    (l32, e32, a32, g0_32, g1_32), (l16, e16, a16, g0_16, g1_16) = outs
+    assert_close(l16, l32, 2e-2, "loss")
+    assert_close(e16, e32, 3e-2, "evidences")
+    assert_close(a16, a32, 3e-2, "fused evidence")
+    assert_close(g0_16, g0_32, 6e-2, "dW hidden layer (shared head)")
+    assert_close(g1_16, g1_32, 6e-2, "dW evidence layer (specific head)")

@@ -301,8 +301,6 @@ infonce_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t p_full_leader = tc2::mapa(tc::smem_u32(p_full), leader_rank);
     const uint32_t wr_full_remote = tc2::mapa(tc::smem_u32(wr_full), leader_rank ^ 2u);
     const uint32_t w_remote = tc2::mapa(tc::smem_u32(smemW), partner) + (uint32_t)(ch * B5_TILE + rloc * 128);
-    const bool send = ntiles > 1 || false;   // with a single tile the other pair still consumes it
-    (void)send;
     for (int k = 0; k < n_own; ++k) {
       const int t = (int)pair + 2 * k;
       const int j0 = (tz0 + t) * 128;

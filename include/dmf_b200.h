@@ -218,7 +218,12 @@ typedef struct {
 } dmf_edl_params;
 /* outputs (each may be NULL): fused [B,C]; grad [B,V,C] = d loss/d evid * (*gscale, or 1 if NULL);
  * u [B] = C/S; ale [B]; pred [B,V+1] int32 (per-view argmax then fused argmax);
- * loss_parts[4] += {edl(A) term, coef*KL term, dc term, total loss}                              */
+ * loss_parts[4] += {edl(A) term, coef*KL term, dc term, total loss}
+ * The argument combination selects a compile-time specialised kernel: grad and/or loss_parts with coef != 0 and a
+ * sum-type rule = training pass (packed fp32x2 math; dc_weight == 0 drops the conflict term); fused without grad /
+ * loss_parts and a sum-type rule = forward-only evaluation pass; anything else (DBF, mixed outputs) = generic pass.
+ * Tiles move as 1D bulk copies when evid / grad / fused tiles are 16-byte aligned (always for contiguous buffers with
+ * V*C*samples-per-tile % 4 == 0), cooperative loads otherwise -- results are identical.                            */
 int dmf_edl_fused(const float* evid, const long long* labels, const dmf_edl_params* p, const float* gscale,
                   float* fused, float* grad, float* u, float* ale, int* pred, float* loss_parts, dmf_stream_t s);
 

@@ -97,7 +97,7 @@ def test_supcon_symmetries_and_clip_form(seed, B, D):
     z0 = torch.nn.functional.normalize(torch.randn(B, D, generator=g, dtype=DT), dim=-1)
     # positives kept close to their anchors: the reference adds 1e-12 inside the log after subtracting the row max
     # (the self-similarity 1/T = 14.3), so rows whose cross-view logits are ALL below -27 deviate from the closed forms
-    z1 = torch.nn.functional.normalize(z0 + 0.4 * torch.randn(B, D, generator=g, dtype=DT), dim=-1)
+    z1 = torch.nn.functional.normalize(z0 + 0.15 * torch.randn(B, D, generator=g, dtype=DT), dim=-1)
     loss, lx, ly = port.supcon(z0, z1)
     l2, lx2, ly2 = port.supcon(z1, z0)                       # swapping the views swaps the diagnostics only
     assert torch.allclose(l2, loss) and torch.allclose(lx2, ly) and torch.allclose(ly2, lx)

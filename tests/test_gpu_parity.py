@@ -866,3 +866,34 @@ def test_probe_heads_bf16_tensor_core_path(dmf):
     assert_close(a16, a32, 3e-2, "fused evidence")
     assert_close(g0_16, g0_32, 6e-2, "dW hidden layer (shared head)")
     assert_close(g1_16, g1_32, 6e-2, "dW evidence layer (specific head)")
+
+
+def test_edl_unaligned_buffers_take_the_cooperative_path(dmf):
+    """The EDL kernel moves tiles with 16-byte-aligned bulk copies and falls back to cooperative loads / stores when
+    a tile is not 16-byte aligned (here: the evidence buffer starts 4 bytes past a boundary; ragged tail tiles hit
+    the same path): both paths must give bit-identical results (training, both conflict settings, and evaluation;
+    odd and even C)."""
+    gen = torch.Generator().manual_seed(12)
+    for B, V, C in ((700, 4, 42), (333, 3, 7), (257, 2, 10)):
+        n = B * V * C
+        flat = torch.empty(n + 1, device=DEV)
+        ev_al = torch.exp(torch.randn(B, V, C, generator=gen) * 1.5).to(DEV)
+        flat[1:].copy_(ev_al.reshape(-1))
+        ev_un = flat[1:].view(B, V, C)                       # data pointer 4 bytes past a 16-byte boundary
+        assert ev_un.data_ptr() % 16 == 4 and ev_un.is_contiguous()
+        y = torch.randint(0, C, (B,), generator=gen).to(DEV)
+        for fused_flag in (1, 0):
+            res = []
+            for ev in (ev_al, ev_un):
+                e = ev.clone().requires_grad_() if ev is ev_al else ev.detach().requires_grad_()
+                loss, fe, parts = dmf.ops.edl_fused_loss(e, y, "avg", 4, 10, fused=fused_flag)
+                (g,) = torch.autograd.grad(loss, e)
+                res.append((loss.detach(), fe, g))
+            # per-thread arithmetic is identical; only the block-level loss reduction order may differ in the last bit
+            assert_close(res[1][0], res[0][0], 1e-6, "loss")
+            assert torch.equal(res[1][1], res[0][1]), "fused evidence"
+            assert torch.equal(res[1][2], res[0][2]), "gradient"
+        a = dmf.ops.edl_summaries(ev_al, y, "cml")
+        b = dmf.ops.edl_summaries(ev_un, y, "cml")
+        for t0, t1, nm in zip(a, b, ("fused", "u", "ale", "pred")):
+            assert torch.equal(t0, t1), nm

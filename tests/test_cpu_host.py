@@ -270,3 +270,46 @@ def test_run_helpers():
     m = DF()
     assert m.N == 2 and sum(p.numel() for p in m.parameters()) > 0
     assert PF.keywords["input_dim"] == 8 and DPF.keywords["annealing_start"] == 50 and LF.args[2] == 10
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/data/handwritten.mat"),
+                    reason="reference data files only exist in the build container")
+def test_real_mat_loaders_match_reference():
+    """HandWritten / Scene / CUB / PIE through our loaders (datasets.py) against the reference's own loaders run on
+    the same files (datasets/dataset.py:270-328): views, labels, dims, class counts and the conflict post-processing
+    of run.get_conflict_data -- bit-identical."""
+    from oracle.ref_harness import in_reference_cwd, load_reference
+    from disentagled_multimodal_fusion_b200 import datasets as ours
+    ns = load_reference()
+    old = os.environ.get("DMF_DATA_ROOT")
+    os.environ["DMF_DATA_ROOT"] = "/root/reference/data"
+    try:
+        for name, dims in (("HandWritten", [240, 76, 216, 47, 64, 6]), ("Scene", [20, 59, 40]), ("CUB", [1024, 300]),
+                           ("PIE", [484, 256, 279])):
+            with in_reference_cwd():
+                ref = getattr(ns.dataset, name)()
+            mine = getattr(ours, name)()
+            assert mine.num_views == ref.num_views and mine.num_classes == ref.num_classes and len(mine) == len(ref)
+            assert [int(d) for d in np.squeeze(mine.dims)] == dims == [int(d) for d in np.squeeze(ref.dims)]
+            for v in range(ref.num_views):
+                assert np.array_equal(mine.X[v], ref.X[v]), (name, v)
+            assert np.array_equal(mine.Y, ref.Y)
+            item_m, item_r = mine[7], ref[7]
+            # the reference returns ({view: x}, y); ours returns [x_0 .. x_{V-1}, y] (README.md:54-70 contract)
+            xr = item_r[0] if isinstance(item_r, (tuple, list)) and isinstance(item_r[0], dict) else None
+            if xr is not None:
+                for v in range(ref.num_views):
+                    assert np.array_equal(item_m[v], xr[v])
+            np.random.seed(3)
+            idx = np.random.permutation(len(ref))[: len(ref) // 5]
+            np.random.seed(11)
+            ref.postprocessing(idx, addNoise=False, sigma=0.5, ratio_noise=0.0, addConflict=True, ratio_conflict=1.0)
+            np.random.seed(11)
+            mine.postprocessing(idx, addNoise=False, sigma=0.5, ratio_noise=0.0, addConflict=True, ratio_conflict=1.0)
+            for v in range(ref.num_views):
+                assert np.array_equal(mine.X[v], ref.X[v]), (name, v, "after conflict injection")
+    finally:
+        if old is None:
+            os.environ.pop("DMF_DATA_ROOT", None)
+        else:
+            os.environ["DMF_DATA_ROOT"] = old

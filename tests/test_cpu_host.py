@@ -294,12 +294,10 @@ def test_real_mat_loaders_match_reference():
             for v in range(ref.num_views):
                 assert np.array_equal(mine.X[v], ref.X[v]), (name, v)
             assert np.array_equal(mine.Y, ref.Y)
-            item_m, item_r = mine[7], ref[7]
-            # the reference returns ({view: x}, y); ours returns [x_0 .. x_{V-1}, y] (README.md:54-70 contract)
-            xr = item_r[0] if isinstance(item_r, (tuple, list)) and isinstance(item_r[0], dict) else None
-            if xr is not None:
-                for v in range(ref.num_views):
-                    assert np.array_equal(item_m[v], xr[v])
+            item_m, item_r = mine[7], ref[7]                  # [x_0 .. x_{V-1}, y] (datasets/dataset.py:196-201)
+            assert len(item_m) == len(item_r) == ref.num_views + 1 and item_m[-1] == item_r[-1]
+            for v in range(ref.num_views):
+                assert item_m[v].dtype == np.float32 and np.array_equal(item_m[v], item_r[v])
             np.random.seed(3)
             idx = np.random.permutation(len(ref))[: len(ref) // 5]
             np.random.seed(11)

@@ -311,3 +311,66 @@ def test_real_mat_loaders_match_reference():
             os.environ.pop("DMF_DATA_ROOT", None)
         else:
             os.environ["DMF_DATA_ROOT"] = old
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/data/handwritten.mat"),
+                    reason="reference data files only exist in the build container")
+def test_run_data_helpers_on_real_data(monkeypatch):
+    """run.get_normal_data / get_conflict_data (run.py:59-102): 80/20 split drawn from the numpy RNG, loaders that
+    follow the [x_0..x_{V-1}, y] contract, conflict injection on the test rows only."""
+    from disentagled_multimodal_fusion_b200 import run
+    monkeypatch.setenv("DMF_DATA_ROOT", "/root/reference/data")
+    np.random.seed(0)
+    tl, vl, ncls, nviews, dims = run.get_normal_data("HandWritten")
+    assert (ncls, nviews, dims) == (10, 6, [240, 76, 216, 47, 64, 6])
+    assert len(tl.dataset) == 1600 and len(vl.dataset) == 400
+    batch = next(iter(vl))
+    assert len(batch) == 7 and batch[0].shape == (100, 240) and batch[0].dtype == torch.float32 and batch[-1].shape == (100,)
+    np.random.seed(0)
+    tl2, vl2, *_ = run.get_conflict_data("HandWritten")
+    same_train = all(np.array_equal(a, b) for a, b in zip(tl.dataset[5][:-1], tl2.dataset[5][:-1]))
+    assert same_train, "training rows must not be corrupted"
+    b2 = next(iter(vl2))
+    changed = sum(int(not torch.equal(a, b)) for a, b in zip(batch[:-1], b2[:-1]))
+    assert changed >= 1 and torch.equal(batch[-1], b2[-1]), "conflict injection rewrites views of test rows, never labels"
+
+
+def test_trainer_standin_follows_lightning_order():
+    """lightning.Trainer (used when pytorch_lightning is absent): optimiser step per batch, validation after every
+    epoch only if the module defines validation_step, on_train_epoch_end after validation, epoch-wise LR schedulers,
+    ReduceLROnPlateau fed the logged monitor."""
+    from disentagled_multimodal_fusion_b200 import lightning as L
+    if L.HAVE_LIGHTNING:
+        pytest.skip("real pytorch_lightning present")
+    events = []
+
+    class M(L.LightningModule):
+        def __init__(self, with_val):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(4.0))
+            if with_val:
+                self.validation_step = self._val
+
+        def training_step(self, batch, bi):
+            events.append(("train", bi))
+            return (self.w - batch[0].mean()) ** 2
+
+        def _val(self, batch, bi):
+            events.append(("val", bi))
+            self.log("val_loss", float((self.w.detach() - batch[0].mean()) ** 2))
+
+        def on_train_epoch_end(self):
+            events.append(("epoch_end",))
+
+        def configure_optimizers(self):
+            opt = torch.optim.SGD(self.parameters(), lr=0.1)
+            sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, factor=0.5, patience=0)
+            return {"optimizer": opt, "lr_scheduler": {"scheduler": sch, "monitor": "val_loss"}}
+    data = [[torch.ones(3)], [torch.ones(3)]]
+    m = M(True)
+    L.Trainer(max_epochs=2, accelerator="cpu").fit(m, data, data)
+    assert events == [("train", 0), ("train", 1), ("val", 0), ("val", 1), ("epoch_end",)] * 2
+    assert abs(float(m.w.detach()) - 1.0) < abs(4.0 - 1.0)            # SGD moved the parameter towards the data mean
+    events.clear()
+    L.Trainer(max_epochs=1, accelerator="cpu").fit(M(False), data, data)
+    assert events == [("train", 0), ("train", 1), ("epoch_end",)]

@@ -374,3 +374,20 @@ def test_trainer_standin_follows_lightning_order():
     events.clear()
     L.Trainer(max_epochs=1, accelerator="cpu").fit(M(False), data, data)
     assert events == [("train", 0), ("train", 1), ("epoch_end",)]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/datasets"), reason="reference tree only exists in the build container")
+def test_make_loaders_simple_plus_split_matches_reference():
+    """datasets.make_loaders_simple_plus (datasets/dataset.py:460-471): same dataset, same seeded random_split, same
+    loader settings (shuffled train loader with drop_last, plain validation loader)."""
+    from oracle.ref_harness import load_reference
+    from disentagled_multimodal_fusion_b200 import datasets as ours
+    ns = load_reference()
+    kw = dict(n_samples=500, n_classes=3, d_signal=8, d_spurious=4, rho=0.5, shared_class_frac=0.5, seed=2)
+    ds_r, tl_r, vl_r = ns.dataset.make_loaders_simple_plus(batch_size=64, **kw)
+    ds_m, tl_m, vl_m = ours.make_loaders_simple_plus(batch_size=64, **kw)
+    assert torch.equal(ds_m.X1, ds_r.X1) and torch.equal(ds_m.X2, ds_r.X2) and torch.equal(ds_m.y, ds_r.y)
+    assert list(tl_m.dataset.indices) == list(tl_r.dataset.indices) and list(vl_m.dataset.indices) == list(vl_r.dataset.indices)
+    assert len(tl_m) == len(tl_r) == 400 // 64 and len(vl_m) == len(vl_r) == 2
+    for bm, br in zip(vl_m, vl_r):
+        assert all(torch.equal(a, b) for a, b in zip(bm, br))

@@ -1,7 +1,6 @@
 """Mirror of the hot-path part of the reference's ``models/losses.py``."""
 from __future__ import annotations
 
-import torch
 from torch import nn
 
 from . import ops

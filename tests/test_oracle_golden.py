@@ -1,6 +1,5 @@
 """Pins oracle/port.py against the fixtures minted from the unmodified reference
 (tests/golden/make_golden.py).  CPU only."""
-import numpy as np
 import pytest
 import torch
 

@@ -4,7 +4,6 @@ properties pin its STRUCTURE on random inputs: closed forms, symmetries and limi
 (utils.py:46-116, models/losses.py:17-248, models/classifiers.py:314-437) imply.  float64 so the assertions are sharp."""
 import math
 
-import pytest
 import torch
 from hypothesis import given, settings, strategies as st
 

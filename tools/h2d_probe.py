@@ -1,5 +1,5 @@
 """H2D bandwidth of pinned host buffers with all ranks copying at once (torchrun); prints GB/s per rank."""
-import os, time, torch, torch.distributed as dist
+import os, torch, torch.distributed as dist
 rank = int(os.environ.get("RANK", 0)); lr = int(os.environ.get("LOCAL_RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(lr)
 if world > 1:
@@ -17,10 +17,6 @@ for mb in (32, 64, 128):
         d.copy_(h, non_blocking=True)
     e.record(); torch.cuda.synchronize()
     res.append((mb, mb * 10 / 1024 / (s.elapsed_time(e) / 1e3)))
-try:
-    import numa_info  # noqa
-except Exception:
-    pass
 aff = len(os.sched_getaffinity(0))
 print(f"rank {rank}: " + ", ".join(f"{mb} MB: {g:.1f} GB/s" for mb, g in res) + f"  (cpu affinity {aff} cores)", flush=True)
 if world > 1:

@@ -4,7 +4,6 @@ import argparse
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import disentagled_multimodal_fusion_b200 as pkg
 from disentagled_multimodal_fusion_b200 import ops, _lib as L
 from disentagled_multimodal_fusion_b200._lib import lib, check, ptr, stream
 

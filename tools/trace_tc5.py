@@ -1,9 +1,14 @@
-import sys, os, ctypes
-sys.path.insert(0, "/root/repo")
-import numpy as np, torch
-import disentagled_multimodal_fusion_b200 as pkg
-from disentagled_multimodal_fusion_b200 import ops, _lib as L
-from disentagled_multimodal_fusion_b200._lib import lib, check, ptr, stream
+"""%globaltimer trace of one cluster of the 4-CTA InfoNCE backward (infonce_bwd_tc5.cu built with -DDMF_TC5_TRACE,
+run with DMF_BWD_TC5=1): when each pair issued S(k), saw its own / the foreign W tile, and how long the softmax took."""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from disentagled_multimodal_fusion_b200 import ops  # noqa: E402
+from disentagled_multimodal_fusion_b200._lib import lib, check, ptr, stream  # noqa: E402
 B, D = 65536, 512
 dev = "cuda"
 torch.manual_seed(0)
@@ -22,7 +27,8 @@ out = np.zeros((8, 2048), dtype=np.uint64)
 f = lib.dmf_tc5_trace_read
 f.argtypes = [ctypes.c_void_p]; f.restype = ctypes.c_int
 print("rc", f(out.ctypes.data))
-np.save("/root/repo/gpurun_out/tc5_trace.npy", out)
+os.makedirs("gpurun_out", exist_ok=True)
+np.save("gpurun_out/tc5_trace.npy", out)
 t0 = out[out > 0].min()
 rel = (out.astype(np.int64) - int(t0))
 names = ["p0 S issued", "p0 own W ready (p_full)", "p0 foreign W ready", "p0 softmax s_full/done", "p1 S issued", "p1 own W ready", "p1 foreign W ready", "p1 softmax"]

@@ -301,26 +301,38 @@ infonce_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t p_full_leader = tc2::mapa(tc::smem_u32(p_full), leader_rank);
     const uint32_t wr_full_remote = tc2::mapa(tc::smem_u32(wr_full), leader_rank ^ 2u);
     const uint32_t w_remote = tc2::mapa(tc::smem_u32(smemW), partner) + (uint32_t)(ch * B5_TILE + rloc * 128);
+    // column factors b_j = exp(c0 - lseB_j) of own tile k live in bsm[(k & 1) * 128 ...]; the global loads for tile k + 1
+    // are issued at the top of tile k and consumed at its end (an L2 round trip at the head of every tile sat on the
+    // softmax -> PV critical path of the first version)
+    auto col_index = [&](int k) { return (tz0 + (int)pair + 2 * k) * 128 + st; };
+    if (st < 128 && n_own > 0) {
+      const int j = col_index(0);
+      bsm[st] = (j < Nb) ? ex2f5(c0 - __ldg(lseB + j) * kLog2e5) : 0.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int k = 0; k < n_own; ++k) {
-      const int t = (int)pair + 2 * k;
-      const int j0 = (tz0 + t) * 128;
-      float* bs = bsm + (k & 1) * 128;
-      if (st < 128) {
-        const int j = j0 + st;
-        bs[st] = (j < Nb) ? ex2f5(c0 - __ldg(lseB + j) * kLog2e5) : 0.f;
+      const float* bs = bsm + (k & 1) * 128;
+      float lb_next = 0.f;
+      bool next_ok = false;
+      if (st < 128 && k + 1 < n_own) {
+        const int j = col_index(k + 1);
+        next_ok = j < Nb;
+        if (next_ok) lb_next = __ldg(lseB + j);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
       tc::mbar_wait(s_full + (k & 1), ((uint32_t)k >> 1) & 1);
       tc::tc_fence_after_sync();
       if (warp == 2 && leader) TRACE(pair * 4 + 3, 2 * k);
       // the other pair must have consumed the tile we sent last time before its buffer is overwritten
       tc::mbar_wait(wr_empty, ((uint32_t)k & 1) ^ 1);
       const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((k & 1) * 128 + ch * 64);
+      // both 32-column chunks are requested before the first wait (one TMEM read latency per tile instead of two)
+      uint32_t rr[2][32];
+      tc::tmem_ld_32x32(tS, rr[0]);
+      tc::tmem_ld_32x32(tS + 32u, rr[1]);
+      tc::tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(tS + (uint32_t)(c * 32), r);
-        tc::tmem_ld_wait();
+        const uint32_t (&r)[32] = rr[c];
         const float4* b4 = reinterpret_cast<const float4*>(bs + ch * 64 + c * 32);
         uint32_t pk[16];
 #pragma unroll
@@ -352,6 +364,10 @@ infonce_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         mbar_arrive_cluster_release(wr_full_remote);     // orders this warp's remote stores before the arrival
       }
       if (warp == 2 && leader) TRACE(pair * 4 + 3, 2 * k + 1);
+      // publish the column factors of the next own tile (its other buffer was last read one tile ago, before the
+      // barrier that ended that tile)
+      if (st < 128 && k + 1 < n_own) bsm[((k + 1) & 1) * 128 + st] = next_ok ? ex2f5(c0 - lb_next * kLog2e5) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     // epilogue: this warp stores its lane quarter x column half of the dA slice
     tc::mbar_wait(acc_full, 0);
@@ -441,7 +457,9 @@ int dmf_infonce_bwd_bf16_tc5(const void* A, long long lda, int Ma, const float* 
       // bound ping-pong between the two pairs: softmax + remote copy of a 128x128 W tile takes 2.6 us (TMEM read
       // 64 B/clk, DSMEM store round trip inside the release), and with smem (227 KB) and TMEM (512 columns) both full
       // there is no room for a third S buffer, a second receive buffer or a ring deeper than 8 x 8 KB to hide it.
-      // st.async (tx-counting remote stores, no writer fences) was slower (9.9 ms).  Opt-in: DMF_BWD_TC5=1.
+      // st.async (tx-counting remote stores, no writer fences) was slower (9.9 ms); prefetching the column factors and
+      // requesting both TMEM chunks before the first wait changed nothing (9.14 ms): the chain is bound by the DSMEM
+      // hand-off and the shallow ring, not by the softmax warps' own latencies.  Opt-in: DMF_BWD_TC5=1.
       {
         const char* ev = getenv("DMF_BWD_TC5");
         if (!ev || !atoi(ev)) ncl = 0;

@@ -459,7 +459,9 @@ int dmf_infonce_bwd_bf16_tc5(const void* A, long long lda, int Ma, const float* 
       // there is no room for a third S buffer, a second receive buffer or a ring deeper than 8 x 8 KB to hide it.
       // st.async (tx-counting remote stores, no writer fences) was slower (9.9 ms); prefetching the column factors and
       // requesting both TMEM chunks before the first wait changed nothing (9.14 ms): the chain is bound by the DSMEM
-      // hand-off and the shallow ring, not by the softmax warps' own latencies.  Opt-in: DMF_BWD_TC5=1.
+      // hand-off and the shallow ring, not by the softmax warps' own latencies.  Handing W over per 64-column chunk (all
+      // eight softmax warps on chunk 0 first, PV of chunk 0 under the softmax of chunk 1) was slower too (10.3 ms: twice
+      // the release fences and TMEM store waits per tile).  Opt-in: DMF_BWD_TC5=1.
       {
         const char* ev = getenv("DMF_BWD_TC5");
         if (!ev || !atoi(ev)) ncl = 0;

@@ -433,6 +433,11 @@ int dmf_infonce_bwd_bf16_tc5(const void* A, long long lda, int Ma, const float* 
                              const void* BmT, long long ldbt, int Nb, const float* lseB, int D, float scale, float coef,
                              const float* gscale, long long diag_offset, float* dA, long long ldda, cudaStream_t s);
 
+int dmf_infonce_bwd_bf16_tc6(const void* A, long long lda, int Ma, const float* lseA, const void* Bm, long long ldb,
+                             const void* BmT, long long ldbt, int Nb, const float* lseB, int D, float scale, float coef,
+                             const float* gscale, long long diag_offset, float* dA, long long ldda, int accumulate,
+                             cudaStream_t s);
+
 static int pick_nsplit(int row_blocks, int col_tiles) {
   int best = 1;
   double best_eff = 0.0;
@@ -514,8 +519,14 @@ int dmf_infonce_bwd_bf16_tc(const void* A, long long lda, int Ma, const float* l
               D, 64 * NT_MAX_KB);
   DMF_REQUIRE(BmT, "dmf_infonce_bwd(bf16): needs the transposed column block BmT [D, Nb]");
   {
-    static int use_v1 = -1, use_v2 = -1;
-    if (use_v1 < 0) { use_v1 = getenv("DMF_BWD_V1") ? 1 : 0; use_v2 = getenv("DMF_BWD_V2") ? 1 : 0; }
+    static int use_v1 = -1, use_v2 = -1, use_v3 = -1;
+    if (use_v1 < 0) { use_v1 = getenv("DMF_BWD_V1") ? 1 : 0; use_v2 = getenv("DMF_BWD_V2") ? 1 : 0; use_v3 = getenv("DMF_BWD_V3") ? 1 : 0; }
+    if (!use_v1 && !use_v2 && !use_v3) {
+      // M = 128 pair kernel: S computed once per column tile, full output row resident in TMEM (executed = 2x algorithmic)
+      const int rc6 = dmf_infonce_bwd_bf16_tc6(A, lda, Ma, lseA, Bm, ldb, BmT, ldbt, Nb, lseB, D, scale, coef, gscale,
+                                               diag_offset, dA, ldda, accumulate, s);
+      if (rc6 != -100) return rc6;
+    }
     if (!use_v1 && !use_v2 && !accumulate && D == 512) {
       // 4-CTA clusters: S recomputed once per row block, W exchanged between the two slice pairs over DSMEM
       const int rc5 = dmf_infonce_bwd_bf16_tc5(A, lda, Ma, lseA, Bm, ldb, BmT, ldbt, Nb, lseB, D, scale, coef, gscale,

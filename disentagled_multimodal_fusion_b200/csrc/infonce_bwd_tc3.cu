@@ -336,8 +336,10 @@ int dmf_infonce_bwd_bf16_tc3(const void* A, long long lda, int Ma, const float* 
     if (e != cudaSuccess) return fail((int)e, "dmf_infonce_bwd(bf16 pair): memset: %s", cudaGetErrorString(e));
   }
   dim3 grid(2 * pairs, slices, nsplit);
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("DMF_BWD_DBG"); dbg = e ? atoi(e) : 0; }   // timing experiments only (wrong results)
+  int dbg = 0;
+#ifdef DMF_BWD_DBG_BUILD   // timing experiments only (wrong results): never compiled into the shipped library
+  { const char* e = getenv("DMF_BWD_DBG"); dbg = e ? atoi(e) : 0; }
+#endif
   infonce_bwd_tc3_kernel<<<grid, B3_THREADS, smem, s>>>(tmA, tmB, tmBT, Ma, Nb, D, num_kb, scale, lseA, lseB, coef, gscale,
                                                         diag_offset, (const uint16_t*)Bm, ldb, dA, ldda, accumulate, dbg);
   return launched("dmf_infonce_bwd(bf16 pair)");

@@ -14,7 +14,7 @@
 //   S(t)   = anchors[64 x D] (smem, resident)  x  Bm[j0 + 128 r .. +128, D]^T       8 ring stages [128 j x 64 d]
 //   W(t)   = softmax warps: TMEM -> exp2 -> bf16 -> smem (K-major, 128B swizzle), the A operand of
 //   O     += W(t)[64 x 256]  x  BmT[d, j0 .. j0 + 256)^T   two N = 256 halves h    8 ring stages [128 d x 64 j]
-// One unified 6-stage ring of 16 KB operand tiles, consumed in the order S(0) S(1) PV(0) S(2) PV(1) ...
+// One unified 8-stage ring of 16 KB operand tiles, consumed in the order S(0) S(1) PV(0) S(2) PV(1) ...
 // W goes through shared memory (not TMEM): the TMEM A operand of a 2-SM M = 128 MMA must be duplicated on both
 // lane halves, i.e. every softmax warp would have to hand its half tile to the warp of the opposite lane half.
 #include <stdlib.h>
@@ -27,11 +27,11 @@ namespace dmf {
 constexpr int B6_THREADS = 320;
 constexpr int B6_STAGE = 128 * 64 * 2;    // 16 KB: [128 x 64] bf16 operand tile
 constexpr int B6_KB = 64 * 64 * 2;        // 8 KB: [64 rows x 64] bf16 (anchor / W k-block of this CTA)
-constexpr int B6_STAGES = 6;
+constexpr int B6_STAGES = 8;
 constexpr int B6_NT = 256;                // columns per tile
 constexpr int B6_MAX_KB = 8;              // D <= 512
 constexpr int B6_WBUF = 4 * B6_KB;        // one W tile: [64 x 256] bf16
-constexpr int B6_SMEM_USED = B6_MAX_KB * B6_KB + 2 * B6_WBUF + B6_STAGES * B6_STAGE + 2 * B6_NT * 4 + 256;
+constexpr int B6_SMEM_USED = B6_MAX_KB * B6_KB + B6_WBUF + B6_STAGES * B6_STAGE + 2 * B6_NT * 4 + 256;
 constexpr int B6_SMEM = 232448;           // the whole opt-in window; the kernel checks that its carve-up fits
 constexpr float kLog2e6 = 1.4426950408889634f;
 
@@ -61,8 +61,8 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     __trap();
   }
   uint8_t* smemA = smem;                                     // B6_MAX_KB k-blocks [64 x 64] (resident anchors)
-  uint8_t* smemW = smemA + B6_MAX_KB * B6_KB;                // 2 W tiles of 4 k-blocks [64 rows x 64 j]
-  uint8_t* ring = smemW + 2 * B6_WBUF;                       // B6_STAGES operand tiles [128 x 64]
+  uint8_t* smemW = smemA + B6_MAX_KB * B6_KB;                // ONE W tile: 4 k-blocks [64 rows x 64 j]
+  uint8_t* ring = smemW + B6_WBUF;                       // B6_STAGES operand tiles [128 x 64]
   float* bsm = reinterpret_cast<float*>(ring + B6_STAGES * B6_STAGE);   // [2][256] column factors of the tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + 2 * B6_NT);
   uint64_t* a_full = bars;
@@ -70,8 +70,8 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* empty_bar = full_bar + B6_STAGES;
   uint64_t* s_full = empty_bar + B6_STAGES;    // [2] S(t) complete in TMEM
   uint64_t* w_full = s_full + 2;               // [2] W(t) in shared memory, S buffer drained (16 warp arrivals)
-  uint64_t* pv_done = w_full + 2;              // [2] PV(t) retired: W buffer (t & 1) reusable
-  uint64_t* acc_full = pv_done + 2;
+  uint64_t* pv_done = w_full + 2;              // PV(t) retired: the W tile may be overwritten
+  uint64_t* acc_full = pv_done + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,7 +92,8 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     tc::tma_prefetch_desc(&tmBT);
     tc::mbar_init(a_full, 1);
     for (int s = 0; s < B6_STAGES; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(s_full + b, 1); tc::mbar_init(w_full + b, 16); tc::mbar_init(pv_done + b, 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(s_full + b, 1); tc::mbar_init(w_full + b, 16); }
+    tc::mbar_init(pv_done, 1);
     tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
   }
@@ -178,12 +179,11 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (t + 1 < ntiles) issue_s(t + 1);
         tc::mbar_wait(w_full + (t & 1), ((uint32_t)t >> 1) & 1);
         tc::tc_fence_after_sync();
-        const uint64_t wd0 = wdesc0 + (uint64_t)(((t & 1) * B6_WBUF) >> 4);
         for (int jc = 0; jc < 4; ++jc)
           for (int h = 0; h < nh; ++h) {
             tc::mbar_wait(full_bar + stage, phase);
             tc::tc_fence_after_sync();
-            const uint64_t wd = wd0 + (uint64_t)((jc * B6_KB) >> 4);
+            const uint64_t wd = wdesc0 + (uint64_t)((jc * B6_KB) >> 4);
             const uint64_t vd = rdesc0 + (uint64_t)((stage * B6_STAGE) >> 4);
             if (tc::elect_one()) {
               if (!(DBG & 2)) {
@@ -196,7 +196,7 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             __syncwarp();
             if (++stage == B6_STAGES) { stage = 0; phase ^= 1; }
           }
-        if (tc::elect_one()) tc2::umma_commit2(pv_done + (t & 1));
+        if (tc::elect_one()) tc2::umma_commit2(pv_done);
         __syncwarp();
       }
       if (tc::elect_one()) tc2::umma_commit2(acc_full);
@@ -226,11 +226,11 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         bs[st] = (j < Nb) ? ex2f6(c0 - __ldg(lseB + j) * kLog2e6) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (t >= 2) tc::mbar_wait(pv_done + (t & 1), (((uint32_t)t >> 1) - 1) & 1);   // W buffer (t & 1) free
       tc::mbar_wait(s_full + (t & 1), ((uint32_t)t >> 1) & 1);
       tc::tc_fence_after_sync();
       const uint32_t tS = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((t & 1) * 128 + ch * 64);
-      uint8_t* wdst = wrow + (t & 1) * B6_WBUF;
+      // W(t) is formed in registers while PV(t-1) still reads the (single) W tile; it is stored once PV(t-1) retired
+      uint32_t pk[32];
       if (!(DBG & 1)) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -239,24 +239,26 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tc::tmem_ld_wait();
           const float4* b4 = reinterpret_cast<const float4*>(bs + cb + c * 32);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float4 bb = b4[g * 2 + u];
-              const int i = g * 8 + u * 4;
-              const float e0 = ex2f6(fmaf(__uint_as_float(r[i + 0]), sl2, -la2));
-              const float e1 = ex2f6(fmaf(__uint_as_float(r[i + 1]), sl2, -la2));
-              const float e2 = ex2f6(fmaf(__uint_as_float(r[i + 2]), sl2, -la2));
-              const float e3 = ex2f6(fmaf(__uint_as_float(r[i + 3]), sl2, -la2));
-              pk[u * 2 + 0] = pack_bf16x2_6(fmaf(e0 * ai, bb.x, e0), fmaf(e1 * ai, bb.y, e1));
-              pk[u * 2 + 1] = pack_bf16x2_6(fmaf(e2 * ai, bb.z, e2), fmaf(e3 * ai, bb.w, e3));
-            }
-            *reinterpret_cast<uint4*>(wdst + (((c * 4 + g) ^ sx) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          for (int g = 0; g < 8; ++g) {
+            const float4 bb = b4[g];
+            const int i = g * 4;
+            const float e0 = ex2f6(fmaf(__uint_as_float(r[i + 0]), sl2, -la2));
+            const float e1 = ex2f6(fmaf(__uint_as_float(r[i + 1]), sl2, -la2));
+            const float e2 = ex2f6(fmaf(__uint_as_float(r[i + 2]), sl2, -la2));
+            const float e3 = ex2f6(fmaf(__uint_as_float(r[i + 3]), sl2, -la2));
+            pk[c * 16 + g * 2 + 0] = pack_bf16x2_6(fmaf(e0 * ai, bb.x, e0), fmaf(e1 * ai, bb.y, e1));
+            pk[c * 16 + g * 2 + 1] = pack_bf16x2_6(fmaf(e2 * ai, bb.z, e2), fmaf(e3 * ai, bb.w, e3));
           }
         }
       }
       tc::tc_fence_before_sync();
+      if (t >= 1) tc::mbar_wait(pv_done, ((uint32_t)t - 1) & 1);
+      if (!(DBG & 1)) {
+#pragma unroll
+        for (int cg4 = 0; cg4 < 8; ++cg4)
+          *reinterpret_cast<uint4*>(wrow + ((cg4 ^ sx) << 4)) =
+              make_uint4(pk[cg4 * 4 + 0], pk[cg4 * 4 + 1], pk[cg4 * 4 + 2], pk[cg4 * 4 + 3]);
+      }
       tc::fence_proxy_async_smem();          // generic-proxy W stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) tc2::mbar_arrive_cluster(w_full_leader + (uint32_t)((t & 1) * 8));

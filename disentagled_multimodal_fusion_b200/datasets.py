@@ -242,9 +242,13 @@ class DeviceLoader:
     def __iter__(self):
         n = self.index.shape[0]
         order = self.index[torch.randperm(n, device=self.index.device, generator=self.gen)] if self.shuffle else self.index
-        per = self.batch_size // self.world_size
         for b in range(len(self)):
             rows = order[b * self.batch_size:(b + 1) * self.batch_size]
             if self.world_size > 1:
+                # equal shards on every rank (the all-gathers of the data-parallel step need them): a final partial
+                # batch keeps len(rows) // world_size rows per rank and drops the remainder
+                per = rows.shape[0] // self.world_size
+                if per == 0:
+                    continue
                 rows = rows[self.rank * per:(self.rank + 1) * per]
             yield [v.index_select(0, rows) for v in self.views] + [self.labels.index_select(0, rows)]

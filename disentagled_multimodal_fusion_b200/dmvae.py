@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import dp, ops
 from ._lib import lib, check, ptr, stream, ptr_array, require_device
 from .classifiers import IdentityEncoder, Linear, grouped_forward
 from .lightning import LightningModule
@@ -101,6 +101,12 @@ class DMVAE(LightningModule):
         loss_joint = loss_recon_joint + self.a * (kl_private + N * kl_shared_poe)
         loss_cross = loss_recon_cross + self.a * kl_shared_uni
         loss = loss_joint + loss_cross
+        # data parallel: every term is a mean over this rank's rows; value -> global mean, gradient -> local / world
+        # (dp.FlatParams.allreduce_grads SUMs), logs -> global means
+        if dp.world()[1] > 1:
+            zero = torch.zeros((), device=loss.device)
+            loss, (loss_recon_joint, loss_recon_cross, kl_private, kl_shared_poe, kl_shared_uni) = dp.globalize_mean_losses(
+                loss, [loss_recon_joint, loss_recon_cross if pairs > 0 else zero, kl_private, kl_shared_poe, kl_shared_uni])
         # device scalars: one host sync when the caller reads them, not five float() calls per step
         logs = {'loss': loss.detach(), 'loss_joint_recon': loss_recon_joint.detach(),
                 'loss_cross_recon': loss_recon_cross.detach() if pairs > 0 else 0.0,

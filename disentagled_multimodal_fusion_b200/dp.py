@@ -26,6 +26,33 @@ def shard_rows(global_batch: int, rank: int, world_size: int) -> Tuple[int, int]
     return rank * per, (rank + 1) * per
 
 
+def globalize_mean_losses(loss: torch.Tensor, logs: List[torch.Tensor]):
+    """For a loss that is a MEAN over the local batch rows (equal shards): returns (loss', logs') whose VALUES are the
+    global means (one all-reduce of the stacked scalars) while d loss'/d params = d loss / d params / world -- so that
+    the SUM all-reduce of ``FlatParams.allreduce_grads`` yields the single-process gradient.  No-op without
+    torch.distributed."""
+    rank, ws = world()
+    if ws == 1:
+        return loss, logs
+    vals = torch.stack([loss.detach().float().reshape(())] + [torch.as_tensor(v, dtype=torch.float32, device=loss.device).detach().reshape(()) for v in logs])
+    vals = vals / ws
+    dist.all_reduce(vals)
+    local = loss / ws
+    out = local + (vals[0] - local.detach())
+    return out, [vals[i + 1] for i in range(len(logs))]
+
+
+def globalize_sum_loss(loss: torch.Tensor) -> torch.Tensor:
+    """For a loss already normalised by the GLOBAL batch (this rank holds a partial sum): value = all-reduced sum,
+    gradient = the local one."""
+    rank, ws = world()
+    if ws == 1:
+        return loss
+    tot = loss.detach().clone()
+    dist.all_reduce(tot)
+    return loss + (tot - loss.detach())
+
+
 class FlatParams:
     """Views of all trainable parameters (and their grads) inside two flat fp32 buffers, so that the
     gradient all-reduce and the fused Adam step are ONE collective / ONE kernel per step."""

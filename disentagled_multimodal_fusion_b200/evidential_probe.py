@@ -9,7 +9,7 @@ import copy
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import dp, ops
 from .classifiers import EvidentialNN, grouped_forward
 from .lightning import Accuracy, LightningModule
 from .losses import AvgTrustedLoss
@@ -45,7 +45,13 @@ class _ProbeBase(LightningModule):
 
     def _fused_step(self, evidences_list, labels, fused=1):
         evidences = torch.stack(evidences_list, dim=1)                  # (B, V, C)
-        loss, evidences_a = self.criterion.fused_forward(evidences, labels, self.agg_name, fused=fused)
+        # data parallel: the kernel normalises by the GLOBAL batch (this rank's loss is then a partial sum and the
+        # SUM all-reduce of the gradients gives the single-process gradient); the returned VALUE is the global loss
+        _, ws = dp.world()
+        gb = evidences.shape[0] * ws if ws > 1 else None
+        loss, evidences_a = self.criterion.fused_forward(evidences, labels, self.agg_name, fused=fused, global_batch=gb)
+        if ws > 1:
+            loss = dp.globalize_sum_loss(loss)
         return loss, evidences_a, labels, evidences
 
     # ----------------- Training / eval steps (models/evidential_probe.py:106-203)

@@ -202,6 +202,10 @@ class _GroupedMLP(torch.autograd.Function):
         ctx.in_needs_grad = [bool(x.requires_grad) and extras[g] is None for g, x in enumerate(xs)]
         ctx.extra_cols = [0 if e is None else e.shape[1] for e in extras]
         ctx.extra_needs_grad = [e is not None and bool(e.requires_grad) for e in extras]
+        if precision == "bf16" and masks is not None and any(m is not None and any(x is not None for x in m) for m in masks):
+            # the tensor-core epilogues carry no dropout mask: refuse loudly instead of training without dropout
+            raise NotImplementedError("bf16 grouped MLP with dropout masks: use precision='fp32' or dropout=0 "
+                                      "(the reference configs run the DMVAE / DSSL encoders with dropout 0)")
         with _Prof("mlp_fwd"):
             if precision == "bf16":
                 outs, saved = _GroupedMLP._fwd_bf16(xs, extras, Ws, bs, G, NL, final, opts or {})
@@ -606,7 +610,9 @@ class _InfoNCE(torch.autograd.Function):
         off = rank * Bl
         out3 = torch.zeros(3, dtype=torch.float32, device=dev)
         lse = torch.empty(2, Bl, dtype=torch.float32, device=dev)
-        fused = bound is not None and dt == 1 and D % 64 == 0 and D <= 512 and off % 256 == 0
+        # the choice must be the SAME on every rank (the two paths issue different collective sequences): it may
+        # depend on the shard size, never on this rank's row offset (off = rank * Bl is a multiple of 256 iff Bl is)
+        fused = bound is not None and dt == 1 and D % 64 == 0 and D <= 512 and (world == 1 or Bl % 256 == 0)
         if fused:
             # unit-norm embeddings: fixed shift, row AND column sums from one pass over S01, symmetric
             # intra-view blocks on a half window (two B x B blocks of work instead of four)

@@ -249,6 +249,12 @@ def test_device_loader_contract_cpu():
         assert torch.equal(torch.cat([parts[0][k], parts[1][k]]), fb)
     with pytest.raises(ValueError):
         DeviceLoader(views, y, 9, device="cpu", world_size=2)
+    # drop_last=False under data parallelism: the ragged final batch (47 = 4 x 10 + 7 rows) is cut into EQUAL shards
+    # (3 + 3, one row dropped) -- unequal shards would hang the equal-size all-gathers of the step
+    tails = [[b[2] for b in DeviceLoader(views, y, 10, device="cpu", indices=sub, rank=r, world_size=2)] for r in range(2)]
+    assert [len(t) for t in tails[0]] == [len(t) for t in tails[1]] == [5, 5, 5, 5, 3]
+    one = [b[2] for b in DeviceLoader(views, y, 10, device="cpu", indices=np.arange(41), rank=1, world_size=2)]
+    assert [len(t) for t in one] == [5, 5, 5, 5]          # a 1-row tail cannot be sharded over 2 ranks: skipped
 
 
 def test_run_helpers():

@@ -708,18 +708,22 @@ def test_direct_grad_accumulation_matches_autograd(dmf):
 
 
 # ------------------------------------------------------------------------------------- multi-GPU (NCCL)
-@pytest.mark.parametrize("prec", ["bf16", "fp32"])
-def test_data_parallel_matches_single_gpu(dmf, prec):
-    """2-rank NCCL run of one DSSL step (global negatives via all-gather, column sums / Gram / gradients
-    all-reduced) vs the same step on the full batch in one process.  Skipped on a 1-GPU box."""
+@pytest.mark.parametrize("prec,case", [("bf16", "dssl"), ("fp32", "dssl"), ("bf16", "dssl_small"), ("fp32", "probe"),
+                                       ("fp32", "dmvae")])
+def test_data_parallel_matches_single_gpu(dmf, prec, case):
+    """2-rank NCCL run of one step vs the same step on the full batch in one process: DSSL (global negatives via
+    all-gather, column sums / Gram / gradients all-reduced; ``dssl_small`` = 128 rows per rank, where the fused
+    row+column kernel is not eligible and every rank must pick the generic path), the evidential probe (EDL loss
+    normalised by the global batch) and DMVAE (local means -> global mean).  Skipped on a 1-GPU box."""
     import os, subprocess, sys
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    port = "29541" if prec == "bf16" else "29542"
+    port = str(29541 + sum(map(ord, prec + case)) % 400)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", port, os.path.join(root, "tests", "dp_worker.py"), prec],
-                         capture_output=True, text=True, timeout=300, cwd=root)
+                          "--master-addr", "127.0.0.1", "--master-port", port, os.path.join(root, "tests", "dp_worker.py"),
+                          prec, case], capture_output=True, text=True, timeout=300, cwd=root)
+    print(out.stdout[-1500:])
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("OK") == 2, out.stdout[-2000:]
 

@@ -121,12 +121,22 @@ def time_cpu(B, steps, warmup):
     return B / dt, dt
 
 
+def host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1: give the CPU arm every core this process may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     torch.set_float32_matmul_precision("highest")
     B = args.cpu_batch
-    cores = torch.get_num_threads()
+    cores = host_threads()
     val, dt = time_cpu(B, max(1, args.steps), max(1, min(args.warmup, 2)))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -140,6 +150,92 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def _timeit(fn, iters, warm):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def kernel_rooflines(dev, Bl, pk):
+    """Live rooflines of K1 (grouped MLP GEMM, tensor bound) and K3 (evidence fusion + EDL, HBM bound), each kernel
+    timed alone with CUDA events on the current stream; inputs rotate through buffers larger than the L2."""
+    from disentagled_multimodal_fusion_b200 import ops, _lib as L
+    from disentagled_multimodal_fusion_b200._lib import lib, check, ptr, stream
+    M = 2 * Bl
+    per_shape, flops_tot, ms_tot = {}, 0.0, 0.0
+    for K in (1024, 512, 1536):
+        A = [torch.randn(M, K, device=dev).bfloat16() for _ in range(2)]
+        W = [torch.randn(HID, K, device=dev).bfloat16() for _ in range(2)]
+        o = [torch.empty(M, HID, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        bias = torch.zeros(HID, device=dev)
+        descs = [dict(A=A[g], lda=K, B=W[g], ldb=K, out_bf16=o[g], ldo_bf16=HID, bias=bias, M=M, N=HID, K=K) for g in range(2)]
+        ms = _timeit(lambda: ops.gemm_tc(descs, L.EPI_BIAS_RELU), 10, 3)
+        fl = 2.0 * 2 * M * HID * K
+        per_shape[f"K={K}"] = round(fl / ms / 1e9, 1)
+        flops_tot += fl
+        ms_tot += ms
+        del A, W, o
+    k1 = {"kernel": "gemm_bf16_tc2_kernel", "bound": "tensor", "achieved": flops_tot / ms_tot / 1e9, "peak": pk["tf_burst"],
+          "unit": "TFLOP/s", "frac": flops_tot / ms_tot / 1e9 / pk["tf_burst"], "traffic": None,
+          "peak_source": pk["src"] + " burst bf16 (kernel timed alone)",
+          "shape": f"2 groups, M={M}, N={HID}, K in (1024, 512, 1536), bias+ReLU epilogue, bf16 out; FLOP-weighted over the three layers",
+          "tflops_by_layer": per_shape}
+    Be, V, C = 1 << 22, 4, 42
+    evid = torch.rand(Be, V, C, device=dev) * 3
+    y = torch.randint(0, C, (Be,), device=dev)
+    fused = torch.empty(Be, C, device=dev)
+    grad = torch.empty_like(evid)
+    parts = torch.zeros(4, device=dev)
+    p = L.EdlParams(Be, V, C, 0, 0.5, 0.6, 1.0 / Be)
+    ms = _timeit(lambda: check(lib.dmf_edl_fused(ptr(evid), ptr(y), p, 0, ptr(fused), ptr(grad), 0, 0, 0, ptr(parts), stream())), 5, 2)
+    byt = Be * (8.0 * V * C + 4 * C + 16)
+    cap = {}
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            cap = json.load(open(tpath)).get("edl_fused_kernel", {})
+        except Exception:  # noqa: BLE001
+            cap = {}
+    k3 = {"kernel": "edl_fused_kernel (training mode: gradient + loss + conflict term)", "bound": "hbm",
+          "achieved": byt / ms / 1e6, "peak": pk["hbm"], "unit": "GB/s", "frac": byt / ms / 1e6 / pk["hbm"],
+          "traffic": cap.get("dram_bytes"), "avg_ms": ms, "peak_source": pk["src"] + " HBM copy bandwidth",
+          "shape": f"B={Be}, V={V}, C={C}; algorithmic bytes/sample = 8VC + 4C + 16 = {8 * V * C + 4 * C + 16}"}
+    del evid, grad, fused
+    torch.cuda.empty_cache()
+    return k1, k3
+
+
+def gpu_eager_context(dev, B):
+    """The oracle port of the reference step executed by torch-eager ATen kernels on the GPU (context only: this is
+    what the unmodified reference would run on this device; it is neither the product nor the stated baseline)."""
+    from oracle import port
+    g = torch.Generator().manual_seed(0)
+    names = {"x1s": (DIMS[0], EMB), "x2s": (DIMS[1], EMB), "x1": (DIMS[0] + EMB, EMB), "x2": (DIMS[1] + EMB, EMB)}
+    p = {k: port.xavier_mlp_params((din, HID, HID), dout, g) for k, (din, dout) in names.items()}
+    p = {k: ([w.detach().to(dev).requires_grad_() for w in ws], [b.detach().to(dev).requires_grad_() for b in bs]) for k, (ws, bs) in p.items()}
+    params = [t for ws, bs in p.values() for t in ws + bs]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    x1, x2 = torch.randn(B, DIMS[0], generator=g).to(dev), torch.randn(B, DIMS[1], generator=g).to(dev)
+    v1, v2 = x1 + 0.01 * torch.randn_like(x1), x2 + 0.01 * torch.randn_like(x2)
+    noise = [tuple(t.to(dev) for t in port.draw_vmf_noise(B, EMB, 1.0)) for _ in range(4)]
+
+    def step():
+        loss, _ = port.dssl_forward(x1, x2, v1, v2, p, noise, a=1.0, lmd=0.0, T=TEMP)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    ms = _timeit(step, 3, 2)
+    return {"value": B / (ms / 1e3), "unit": UNIT, "batch": B, "ms_per_step": ms,
+            "what": "oracle port of the DSSL step (fp32, torch-eager ATen/cuBLAS kernels, vMF noise pre-drawn, no probe) on this GPU"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -168,11 +264,19 @@ def run_gpu(args, rank, world, local_rank):
     bb = FlatParams(model.parameters())
     hd = FlatParams([p for n, p in probe.named_parameters() if not n.startswith("backbone.")])
 
-    gen = torch.Generator().manual_seed(1234 + rank)
-    host = {}
-    for k, d in (("x1", DIMS[0]), ("x2", DIMS[1])):
-        host[k] = torch.randn(Bl, d, generator=gen).pin_memory()
-    host["y"] = torch.randint(0, NCLS, (Bl,), generator=gen).pin_memory()
+    # Rank-independent synthetic data: the GLOBAL batch is cut into 8 fixed chunks, chunk c drawn from seed 1234 + c,
+    # so that N = 1, 2, 4, 8 all train on the same global batch (loss_check below compares them).
+    def host_chunk(c, rows):
+        g = torch.Generator().manual_seed(1234 + c)
+        return {"x1": torch.randn(rows, DIMS[0], generator=g), "x2": torch.randn(rows, DIMS[1], generator=g),
+                "y": torch.randint(0, NCLS, (rows,), generator=g)}
+
+    def host_rows(r, w):
+        if Bg % 8 == 0 and 8 % w == 0:
+            parts = [host_chunk(c, Bg // 8) for c in range(r * 8 // w, (r + 1) * 8 // w)]
+            return {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
+        return host_chunk(100 + r, Bg // w)
+    host = {k: v.pin_memory() for k, v in host_rows(rank, world).items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
     # The batch a user hands to training_step is (x1, x2[, y]); the augmented views v1, v2 are made ON THE DEVICE by
@@ -212,6 +316,39 @@ def run_gpu(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- loss_check: ONE step without optimizer update on the fresh (seed 0) parameters, rank-independent data AND
+    #      rank-independent noise (noise / augmentation drawn for the GLOBAL batch on every rank, local rows sliced):
+    #      global loss, probe loss and the norms of the all-reduced gradients must agree between N = 1, 2, 4, 8
+    def loss_check():
+        full = host_rows(0, 1) if world > 1 else host
+        gx1, gx2 = full["x1"].to(dev), full["x2"].to(dev)
+        gv1 = ops.augment(gx1, 0xC0FFEE, 0)
+        gv2 = ops.augment(gx2, 0xC0FFEE, 1)
+        seed_keep = model.noise_seed
+        model.noise_seed = 0x777
+        gnoise = model.draw_noise(Bg, dev)
+        model.noise_seed = seed_keep
+        inp = {"x1": gx1[lo:hi], "x2": gx2[lo:hi], "v1": gv1[lo:hi].contiguous(), "v2": gv2[lo:hi].contiguous(),
+               "y": full["y"].to(dev)[lo:hi]}
+        nz = [(w[lo:hi].contiguous(), v[lo:hi].contiguous()) for w, v in gnoise]
+        loss, logs = model(inp["x1"], inp["x2"], inp["v1"], inp["v2"], noise=nz)
+        bb.zero_grad()
+        loss.backward()
+        bb.allreduce_grads()
+        ploss = probe.shared_step([inp["x1"], inp["x2"], inp["y"]])[0]
+        hd.zero_grad()
+        ploss.backward()
+        hd.allreduce_grads()
+        out = {"loss": float(loss.detach()), "shared": float(logs["shared"]), "specific": float(logs["specific"]),
+               "probe_loss": float(ploss.detach()), "grad_norm": float(bb.grad.norm()), "probe_grad_norm": float(hd.grad.norm()),
+               "what": "one step on the fresh parameters; data, augmentation and vMF noise identical for every N"}
+        bb.zero_grad()
+        hd.zero_grad()
+        del gx1, gx2, gv1, gv2, gnoise
+        torch.cuda.empty_cache()
+        return out
+    lcheck = loss_check() if args.loss_check else None
 
     step_marks = []
 
@@ -256,15 +393,36 @@ def run_gpu(args, rank, world, local_rank):
     #      redrawn in place before every replay by four launches outside the graph (host-side RNG counter)
     launch_mode = "eager"
     gstep = None
+    phase_events = None
     if args.graph != "off":
         try:
-            gstep = GraphedStep(lambda: step(devin, capturable=True), warmup=2, stream=torch.cuda.current_stream())
+            # the phase regions of ops._Prof become event-record NODES of the graph (external events): every replay
+            # re-times them, so the per-phase breakdown below is measured inside the timed region itself
+            ops.PROFILE.clear()
+            ops.PROFILE_ON, ops.PROFILE_EXTERNAL = True, True
+            step_s = torch.cuda.Event(enable_timing=True, external=True)
+            step_e = torch.cuda.Event(enable_timing=True, external=True)
+
+            def graphed():
+                if ops.PROFILE_ON:              # external events can only be recorded under capture
+                    step_s.record()
+                out = step(devin, capturable=True)
+                if ops.PROFILE_ON:
+                    step_e.record()
+                return out
+            ops.PROFILE_ON = False
+            gstep = GraphedStep(graphed, warmup=2, stream=torch.cuda.current_stream(),
+                                on_capture=lambda on: setattr(ops, "PROFILE_ON", on))
+            ops.PROFILE_ON, ops.PROFILE_EXTERNAL = False, False
+            phase_events = dict(ops.PROFILE)
             launch_mode = "cuda_graph"
         except Exception as ex:  # noqa: BLE001
             if args.graph == "on":
                 raise
             launch_mode = f"eager (graph capture failed: {type(ex).__name__})"
             gstep = None
+            phase_events = None
+            ops.PROFILE_ON, ops.PROFILE_EXTERNAL = False, False
             torch.cuda.synchronize()
 
     def run_value():
@@ -283,6 +441,17 @@ def run_gpu(args, rank, world, local_rank):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     value = Bg * args.steps / (ms / 1e3)
+    # per-phase device time of the LAST timed replay (event nodes inside the graph), max over ranks
+    phases = None
+    if phase_events:
+        names = sorted(phase_events)
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in phase_events[k]) for k in names] + [step_s.elapsed_time(step_e)],
+                         device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        phases = {k: round(float(v), 3) for k, v in zip(names, t[:-1])}
+        phases["graph_total"] = round(float(t[-1]), 3)
+        phases["unattributed"] = round(float(t[-1]) - sum(phases[k] for k in names), 3)
 
     # ---- end-to-end: pinned host -> device copies every step + loss read back
     copy_stream = torch.cuda.Stream()
@@ -348,39 +517,64 @@ def run_gpu(args, rank, world, local_rank):
     if rank != 0:
         return
     pk = peaks()
-    # roofline of the dominant kernel (InfoNCE backward): algorithmic FLOPs per launch = 2*Ma*Nb*D
+    # roofline of the dominant kernel (InfoNCE backward): algorithmic FLOPs per launch = 2*Ma*Nb*D (the
+    # recompute of S is not counted).  DRAM traffic, tensor-pipe activity and executed/algorithmic FLOPs come from the
+    # committed ncu capture of the same kernel at this shape (profiles/r02_traffic.json), never from literals here.
     roof = None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.isfile(tpath) and world == 1 and Bg == 65536:
+    kname = "infonce_bwd_tc6_kernel"
+    cap = {}
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.isfile(tpath):
         try:
-            traffic = json.load(open(tpath))["infonce_bwd_tc3_kernel"]["dram_bytes"]
+            cap = json.load(open(tpath)).get(kname, {})
         except Exception:  # noqa: BLE001
-            traffic = None
+            cap = {}
+    same_shape = world == 1 and Bg == 65536 and prec == "bf16"
     if "infonce_bwd" in prof:
         n, tot_ms = prof["infonce_bwd"]
         avg_ms = tot_ms / n
         flops = 2.0 * Bl * Bg * EMB
         ach = flops / (avg_ms * 1e-3) / 1e12
-        roof = {"kernel": "infonce_bwd_tc3_kernel", "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sust"], "traffic": traffic, "launches": n, "avg_ms": avg_ms,
-                "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
+        roof = {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                "frac": ach / pk["tf_sust"], "traffic": cap.get("dram_bytes") if same_shape else None, "launches": n,
+                "avg_ms": avg_ms, "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
                 "share_of_step": (tot_ms / prof_steps) / (ms / args.steps),
                 "timed_in": f"{prof_steps} eager steps after warm-up (CUDA events on the launching stream)",
-                "traffic_source": "bytes/launch, ncu --set full capture of this kernel at this shape (profiles/r01_traffic.json)" if traffic else None,
-                "executed_over_algorithmic_flops": 3.0,
-                "tensor_pipe_active_pct_ncu": 79.9,
+                "traffic_source": "bytes/launch, ncu --set full capture of this kernel at this shape (profiles/r02_traffic.json)" if same_shape and cap else None,
+                "executed_over_algorithmic_flops": cap.get("executed_over_algorithmic_flops"),
+                "tensor_pipe_active_pct_ncu": cap.get("tensor_pipe_active_pct") if same_shape else None,
                 "other_kernels_ms_per_step": {k: v[1] / prof_steps for k, v in prof.items()}}
+    # rooflines of the other two kernel families, measured live (CUDA events, kernels timed alone -> burst peak):
+    #   K1 grouped MLP GEMM at the C5 layer shapes (2 groups, M = 2 x per-GPU batch), K3 evidence fusion + EDL loss in
+    #   the mode training uses (gradient + conflict term) at the C4 shape B = 2^22, V = 4, C = 42
+    roof_k1 = roof_k3 = None
+    if world == 1 and not args.no_kernel_rooflines:
+        roof_k1, roof_k3 = kernel_rooflines(dev, Bl, pk)
     # algorithmic FLOPs of one step: K2 = 2 critic calls with the no-grad diagnostics (8 B^2 D each) + the 2
     # specific-critic calls whose diagnostics the reference discards (6 B^2 D each: cross block fwd 2 + bwd 4);
     # K1 = 48.2 MFLOP/sample; ortho Grams forward only (lmd = 0: logged, weight exactly zero) 8 D^2 per sample
     step_flops = 28.0 * Bg * Bg * EMB + Bg * (48.2e6 + 8.0 * EMB * EMB) if Bg else 0
     cpu = None
     if not args.no_cpu_baseline:
+        cores = host_threads()
         torch.set_float32_matmul_precision("highest")
         cval, cdt = time_cpu(args.cpu_batch, 2, 1)
-        cpu = {"value": cval, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        cpu = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"2 full steps of the oracle port at batch {args.cpu_batch} (reference cost grows ~B^2; B=65536 needs 64 GiB per logits temp)"}
+        try:        # the reference imports with torch.set_float32_matmul_precision('medium') (models/dmvae.py:9)
+            torch.set_float32_matmul_precision("medium")
+            mval, _ = time_cpu(args.cpu_batch, 1, 1)
+            cpu["value_medium_precision"] = mval
+        except Exception:  # noqa: BLE001
+            pass
+        finally:
+            torch.set_float32_matmul_precision("highest")
+        # context only: the same oracle port run with torch-eager ATen kernels ON THIS GPU at the largest batch
+        # whose [2B,2B] logits it can hold comfortably
+        try:
+            cpu["gpu_eager_context"] = gpu_eager_context(dev, 8192)
+        except Exception as ex:  # noqa: BLE001
+            cpu["gpu_eager_context"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:160]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -395,7 +589,8 @@ def run_gpu(args, rank, world, local_rank):
         "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
         "step_tflops_algorithmic": step_flops / 1e12,
         "step_frac_of_sustained_bf16": step_flops / (ms / args.steps * 1e-3) / 1e12 / (pk["tf_sust"] * world),
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "roofline_k1": roof_k1, "roofline_k3": roof_k3, "cpu_baseline": cpu,
+        "loss_check": lcheck, "phase_ms": phases,
         "step_ms": {"value": step_marks[0], "e2e": step_marks[-1]},
     }
     print(json.dumps(line), flush=True)
@@ -411,6 +606,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-rooflines", action="store_true", help="skip the live K1 / K3 roofline measurements")
+    ap.add_argument("--no-loss-check", dest="loss_check", action="store_false",
+                    help="skip the cross-N loss / gradient-norm check step")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step as one CUDA graph (auto: fall back to eager launches if capture fails)")
     args = ap.parse_args()

@@ -89,9 +89,10 @@ class DisentangledSSL(LightningModule):
                 buf = torch.empty(n, d + D, dtype=torch.bfloat16, device=parts[0].device)
                 bufT = torch.empty(d + D, npad, dtype=torch.bfloat16, device=parts[0].device) if need_t else None
                 o = 0
-                for p in parts:
-                    ops.cast_dual_bf16(p, buf[o:], d + D, bufT[:, o:] if need_t else None, npad)
-                    o += p.shape[0]
+                with ops._Prof("cast_in"):
+                    for p in parts:
+                        ops.cast_dual_bf16(p, buf[o:], d + D, bufT[:, o:] if need_t else None, npad)
+                        o += p.shape[0]
                 bufs.append(buf)
                 bufTs.append(bufT)
                 dims.append(d)
@@ -181,7 +182,7 @@ class DisentangledSSL(LightningModule):
             # reference default (lmd_start_value = lmd_end_value = 0): the term is logged but its weight is
             # exactly zero, so neither its backward pass nor autograd bookkeeping is needed: one grouped Gram
             # launch + one all-reduce for the four calls (rows of P are already normalised for the critic)
-            with torch.no_grad():
+            with torch.no_grad(), ops._Prof("ortho"):
                 E1n, E2n = ops.row_normalize(E1), ops.row_normalize(E2)
                 ov = ops.ortho_values_nograd([(P1n[:B], E1n[:B]), (P2n[:B], E2n[:B]), (P1n[B:], E1n[B:]), (P2n[B:], E2n[B:])],
                                              self.precision)
@@ -197,7 +198,8 @@ class DisentangledSSL(LightningModule):
             # ortho is already global (its Gram was all-reduced); the InfoNCE terms are partial sums
             part = loss - lmd * loss_ortho if lmd != 0 else loss
             vals = torch.stack([part.detach(), loss_shared.detach(), loss_x, loss_y, loss_specific.detach()])
-            dist.all_reduce(vals)
+            with ops._Prof("loss_allreduce"):
+                dist.all_reduce(vals)
             loss = loss + (vals[0] - part.detach())        # global value, local gradient
             loss_shared, joint_loss, loss_x, loss_y, loss_specific = vals[1], vals[1], vals[2], vals[3], vals[4]
         # device scalars (the reference does seven .item() syncs here)

@@ -78,7 +78,9 @@ class FlatParams:
         self._lr_on_device = None
 
     def zero_grad(self):
-        self.grad.zero_()
+        from . import ops
+        with ops._Prof("zero_grad"):
+            self.grad.zero_()
         o = 0
         for p in self.params:           # autograd may have replaced .grad; re-point it at the flat buffer
             k = p.numel()
@@ -87,22 +89,25 @@ class FlatParams:
 
     def allreduce_grads(self):
         """SUM over ranks (losses are normalised by the global batch, so no division here)."""
+        from . import ops
         rank, ws = world()
         if ws > 1:
-            dist.all_reduce(self.grad)
+            with ops._Prof("grad_allreduce"):
+                dist.all_reduce(self.grad)
 
     def adam_step(self, lr: float, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, capturable=False):
         """Fused flat-buffer Adam / AdamW.  ``capturable=True`` keeps the step count and the learning rate in device
         memory (``self.state``) so the call can sit inside a captured CUDA graph; set a new learning rate with
         ``set_lr`` between replays."""
         from . import ops
-        if capturable:
-            if self._lr_on_device is None:
-                self.set_lr(lr)
-            ops.adam_step_flat_dev(self.flat, self.grad, self.m, self.v, self.state, betas, eps, weight_decay, decoupled)
-            return
-        self.step_count += 1
-        ops.adam_step_flat(self.flat, self.grad, self.m, self.v, lr, self.step_count, betas, eps, weight_decay, decoupled)
+        with ops._Prof("adam"):
+            if capturable:
+                if self._lr_on_device is None:
+                    self.set_lr(lr)
+                ops.adam_step_flat_dev(self.flat, self.grad, self.m, self.v, self.state, betas, eps, weight_decay, decoupled)
+                return
+            self.step_count += 1
+            ops.adam_step_flat(self.flat, self.grad, self.m, self.v, lr, self.step_count, betas, eps, weight_decay, decoupled)
 
     def set_lr(self, lr: float):
         """Write the learning rate (and the host-side step count) into the device state; not capturable."""
@@ -117,7 +122,7 @@ class GraphedStep:
     from fixed device buffers and must not synchronise; anything that changes per step through HOST scalars (RNG
     seeds, step counts, learning rates) has to live in device memory or run outside the graph."""
 
-    def __init__(self, fn, warmup: int = 2, pool=None, stream=None):
+    def __init__(self, fn, warmup: int = 2, pool=None, stream=None, on_capture=None):
         # Run the warm-up and the capture on ONE non-default stream.  Everything that touched the parameters
         # before (eager steps, optimizer state) should have run on a non-default stream too: autograd replays
         # each AccumulateGrad on the stream its node was created on, and a node created on the legacy default
@@ -130,8 +135,14 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, pool=pool, stream=side):
-            self.out = fn()
+        if on_capture is not None:        # e.g. switch the event-record phase markers on for the captured pass only
+            on_capture(True)
+        try:
+            with torch.cuda.graph(self.graph, pool=pool, stream=side):
+                self.out = fn()
+        finally:
+            if on_capture is not None:
+                on_capture(False)
 
     def pool(self):
         return self.graph.pool()

@@ -30,6 +30,7 @@ def _dist_on() -> bool:
 
 # ---- optional per-kernel timing with CUDA events on the launching stream (used by bench.py)
 PROFILE_ON = False
+PROFILE_EXTERNAL = False     # events recorded as nodes of a CUDA graph under capture (timed on every replay)
 PROFILE: dict = {}
 
 
@@ -39,8 +40,8 @@ class _Prof:
 
     def __enter__(self):
         if PROFILE_ON:
-            self.s = torch.cuda.Event(enable_timing=True)
-            self.e = torch.cuda.Event(enable_timing=True)
+            self.s = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
+            self.e = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
             self.s.record()
         return self
 
@@ -572,22 +573,24 @@ class GatheredPair:
 
     def __init__(self, z0: Tensor, z1: Tensor, precision: str):
         L.require_device()
-        z0, z1 = _f32c(z0.detach()), _f32c(z1.detach())
-        self.a0, self.a1 = (cast_bf16(z0), cast_bf16(z1)) if precision == "bf16" else (z0, z1)
-        self.works = []
-        if _dist_on():
-            world = dist.get_world_size()
-            Bl, D = z0.shape
-            self.g0 = torch.empty(Bl * world, D, dtype=self.a0.dtype, device=z0.device)
-            self.g1 = torch.empty(Bl * world, D, dtype=self.a1.dtype, device=z0.device)
-            self.works.append(dist.all_gather_into_tensor(self.g0, self.a0, async_op=True))
-            self.works.append(dist.all_gather_into_tensor(self.g1, self.a1, async_op=True))
-        else:
-            self.g0, self.g1 = self.a0, self.a1
+        with _Prof("gather_launch"):
+            z0, z1 = _f32c(z0.detach()), _f32c(z1.detach())
+            self.a0, self.a1 = (cast_bf16(z0), cast_bf16(z1)) if precision == "bf16" else (z0, z1)
+            self.works = []
+            if _dist_on():
+                world = dist.get_world_size()
+                Bl, D = z0.shape
+                self.g0 = torch.empty(Bl * world, D, dtype=self.a0.dtype, device=z0.device)
+                self.g1 = torch.empty(Bl * world, D, dtype=self.a1.dtype, device=z0.device)
+                self.works.append(dist.all_gather_into_tensor(self.g0, self.a0, async_op=True))
+                self.works.append(dist.all_gather_into_tensor(self.g1, self.a1, async_op=True))
+            else:
+                self.g0, self.g1 = self.a0, self.a1
 
     def wait(self):
-        for w in self.works:
-            w.wait()
+        with _Prof("gather_wait"):
+            for w in self.works:
+                w.wait()
         self.works = []
 
 
@@ -630,7 +633,8 @@ class _InfoNCE(torch.autograd.Function):
                     rowcol(a0, g0, 1, 1)     # intra-view blocks: only the no-grad diagnostics loss_x / loss_y need them
                     rowcol(a1, g1, 2, 1)     # (the reference's row max is the self-similarity 1/T = the fixed shift)
             if world > 1:
-                dist.all_reduce(cs if diagnostics else cs[0])
+                with _Prof("colsum_allreduce"):
+                    dist.all_reduce(cs if diagnostics else cs[0])
             mfix = torch.full((Bl,), shift, dtype=torch.float32, device=dev)
             l_c1 = cs[0, off:off + Bl].contiguous()
             if diagnostics:
@@ -662,11 +666,12 @@ class _InfoNCE(torch.autograd.Function):
             check(lib.dmf_infonce_finalize(ptr(st[6]), ptr(st[7]), ptr(st[9]), ptr(st[10]), ptr(st[8]), ptr(st[11]), Bl,
                                            1.0 / (2 * Bg), 1.0 / Bg, 1, ptr(lse[1]), ptr(out3), stream()))
         if world > 1:
-            if reduce:
-                dist.all_reduce(out3)
-            gath = torch.empty(world, 2, Bl, dtype=torch.float32, device=dev)      # one collective for both views
-            dist.all_gather_into_tensor(gath, lse)
-            lse_all = gath.permute(1, 0, 2).reshape(2, Bg).contiguous()
+            with _Prof("lse_gather"):
+                if reduce:
+                    dist.all_reduce(out3)
+                gath = torch.empty(world, 2, Bl, dtype=torch.float32, device=dev)      # one collective for both views
+                dist.all_gather_into_tensor(gath, lse)
+                lse_all = gath.permute(1, 0, 2).reshape(2, Bg).contiguous()
         else:
             lse_all = lse
         ctx.save_for_backward(a0, a1, g0, g1, lse, lse_all)
@@ -683,7 +688,8 @@ class _InfoNCE(torch.autograd.Function):
         dz0 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
         dz1 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
         if dt == 1:
-            g0T, g1T = transpose_bf16(g0), transpose_bf16(g1)
+            with _Prof("transpose_gathered"):
+                g0T, g1T = transpose_bf16(g0), transpose_bf16(g1)
         else:
             g0T = g1T = None
         with _Prof("infonce_bwd"):
@@ -728,7 +734,8 @@ class _RowNormalize(torch.autograd.Function):
         R, D = x.shape
         y = torch.empty_like(x)
         inv = torch.empty(R, dtype=torch.float32, device=x.device)
-        check(lib.dmf_row_normalize_fwd(ptr(x), D, R, D, eps, ptr(y), D, 0, 0, ptr(inv), stream()))
+        with _Prof("head_fwd"):
+            check(lib.dmf_row_normalize_fwd(ptr(x), D, R, D, eps, ptr(y), D, 0, 0, ptr(inv), stream()))
         ctx.save_for_backward(y, inv)
         return y
 
@@ -738,7 +745,8 @@ class _RowNormalize(torch.autograd.Function):
         dy = _f32c(dy)
         R, D = y.shape
         dx = torch.empty_like(y)
-        check(lib.dmf_row_normalize_bwd(ptr(y), D, ptr(inv), ptr(dy), D, R, D, ptr(dx), D, 0, stream()))
+        with _Prof("head_bwd"):
+            check(lib.dmf_row_normalize_bwd(ptr(y), D, ptr(inv), ptr(dy), D, R, D, ptr(dx), D, 0, stream()))
         return dx, None
 
 
@@ -754,7 +762,8 @@ class _VmfSample(torch.autograd.Function):
         e, w, v = _f32c(e), _f32c(w), _f32c(v)
         R, D = e.shape
         z = torch.empty_like(e)
-        check(lib.dmf_vmf_fwd(ptr(e), D, ptr(w), ptr(v), R, D, ptr(z), D, 0, 0, stream()))
+        with _Prof("head_fwd"):
+            check(lib.dmf_vmf_fwd(ptr(e), D, ptr(w), ptr(v), R, D, ptr(z), D, 0, 0, stream()))
         ctx.save_for_backward(e, w, v)
         return z
 
@@ -764,7 +773,8 @@ class _VmfSample(torch.autograd.Function):
         dz = _f32c(dz)
         R, D = e.shape
         de = torch.empty_like(e)
-        check(lib.dmf_vmf_bwd(ptr(e), D, ptr(w), ptr(v), ptr(dz), D, R, D, ptr(de), D, 0, stream()))
+        with _Prof("head_bwd"):
+            check(lib.dmf_vmf_bwd(ptr(e), D, ptr(w), ptr(v), ptr(dz), D, R, D, ptr(de), D, 0, stream()))
         return de, None, None
 
 

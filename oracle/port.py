@@ -174,7 +174,7 @@ def supcon(z0: Tensor, z1: Tensor, T: float = 0.07) -> Tuple[Tensor, Tensor, Ten
     cf = torch.cat([z0, z1], dim=0)                                # :53
     adc = torch.matmul(cf, cf.T) / T                               # :64-66
     logits = adc - adc.max(dim=1, keepdim=True).values.detach()    # :68-69
-    eye = torch.eye(B, dtype=z0.dtype)
+    eye = torch.eye(B, dtype=z0.dtype, device=z0.device)
     mask = eye.repeat(2, 2)                                        # :72
     lmask = torch.ones_like(mask)
     lmask[:B, :B] = 0
@@ -213,7 +213,7 @@ def vmf_rsample(e: Tensor, w: Tensor, v: Tensor) -> Tensor:
     loc = e / e.norm(dim=-1, keepdim=True)
     w_ = torch.sqrt(torch.clamp(1 - w ** 2, 1e-10))
     x = torch.cat((w, w_ * v), -1)
-    e1 = torch.zeros(e.shape[-1], dtype=e.dtype)
+    e1 = torch.zeros(e.shape[-1], dtype=e.dtype, device=e.device)
     e1[0] = 1.0
     u = e1 - loc
     u = u / (u.norm(dim=-1, keepdim=True) + 1e-5)

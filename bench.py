@@ -254,6 +254,11 @@ def run_gpu(args, rank, world, local_rank):
     Bl = hi - lo
     prec = args.precision
 
+    # K1 / K3 rooflines first: each kernel timed ALONE on the still-cool GPU (their denominators are the burst peaks)
+    roof_k1 = roof_k3 = None
+    if world == 1 and not args.no_kernel_rooflines:
+        roof_k1, roof_k3 = kernel_rooflines(dev, Bl, peaks())
+
     torch.manual_seed(0)                      # identical replicated parameters on every rank
     model = pkg.DisentangledSSL(output_dim=DIMS, hidden_dim=HID, embed_dim=EMB, a=1.0, vmfkappa=1, precision=prec,
                                 noise_mode="device").to(dev)
@@ -547,9 +552,6 @@ def run_gpu(args, rank, world, local_rank):
     # rooflines of the other two kernel families, measured live (CUDA events, kernels timed alone -> burst peak):
     #   K1 grouped MLP GEMM at the C5 layer shapes (2 groups, M = 2 x per-GPU batch), K3 evidence fusion + EDL loss in
     #   the mode training uses (gradient + conflict term) at the C4 shape B = 2^22, V = 4, C = 42
-    roof_k1 = roof_k3 = None
-    if world == 1 and not args.no_kernel_rooflines:
-        roof_k1, roof_k3 = kernel_rooflines(dev, Bl, pk)
     # algorithmic FLOPs of one step: K2 = 2 critic calls with the no-grad diagnostics (8 B^2 D each) + the 2
     # specific-critic calls whose diagnostics the reference discards (6 B^2 D each: cross block fwd 2 + bwd 4);
     # K1 = 48.2 MFLOP/sample; ortho Grams forward only (lmd = 0: logged, weight exactly zero) 8 D^2 per sample

@@ -159,66 +159,129 @@ __global__ void vmf_bwd_kernel(const float* __restrict__ E, long long lde, const
   }
 }
 
+// Counter-hash RNG (splitmix64): every thread starts at a hashed position of the 2^64 cycle.  The device draws are
+// distribution-equal to the reference's samplers, never stream-equal, so the generator only has to be good and cheap:
+// one 64-bit mix (two 64-bit multiplies) per 32 random bits, against ten Philox rounds per four words plus the
+// full-precision Box-Muller of curand_normal.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+struct HashRng {
+  unsigned long long s;
+  __device__ __forceinline__ HashRng(unsigned long long seed, unsigned long long offset, unsigned long long stream) {
+    s = mix64(mix64(seed + 0x9E3779B97F4A7C15ull * (offset + 1)) ^ (stream * 0xD1B54A32D192ED03ull + 0x8CB92BA72F3D8DD7ull));
+  }
+  __device__ __forceinline__ unsigned long long next64() {
+    s += 0x9E3779B97F4A7C15ull;
+    return mix64(s);
+  }
+  __device__ __forceinline__ float uniform() {            // (0, 1), 24 bits
+    return ((float)(next64() >> 40) + 0.5f) * (1.0f / 16777216.0f);
+  }
+  // two independent N(0,1) from one 64-bit word (Box-Muller on fast intrinsics: abs. error ~1e-6, far below the
+  // resolution any consumer of this noise has)
+  __device__ __forceinline__ float2 normal2() {
+    const unsigned long long h = next64();
+    const float u1 = ((float)(unsigned)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = (float)(unsigned)(h & 0xFFFFFFull) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    return make_float2(r * cs, r * sn);
+  }
+};
+
 // Device-side vMF noise: distribution-equal to VonMisesFisher.__sample_w_rej + the tangent normal
-// draw (models/classifiers.py:349-431), not stream-equal.  One warp per row; Philox4x32-10.
-__device__ float gamma_mt(curandStatePhilox4_32_10_t* st, float alpha) {
+// draw (models/classifiers.py:349-431), not stream-equal.  One warp per row.
+__device__ float gamma_mt(HashRng* st, float alpha) {
   // Marsaglia-Tsang; alpha < 1 boosted
   float boost = 1.0f;
   if (alpha < 1.0f) {
-    boost = powf(curand_uniform(st), 1.0f / alpha);
+    boost = powf(st->uniform(), 1.0f / alpha);
     alpha += 1.0f;
   }
   const float d = alpha - 1.0f / 3.0f;
   const float c = rsqrtf(9.0f * d);
   for (int it = 0; it < 64; ++it) {
-    const float x = curand_normal(st);
+    const float x = st->normal2().x;
     float vv = 1.0f + c * x;
     if (vv <= 0.f) continue;
     vv = vv * vv * vv;
-    const float u = curand_uniform(st);
+    const float u = st->uniform();
     if (logf(u) < 0.5f * x * x + d - d * vv + d * logf(vv)) return d * vv * boost;
   }
   return d * boost;
 }
 
-__global__ void vmf_draw_kernel(float* __restrict__ nw, float* __restrict__ nv, int rows, int D, float kappa,
-                                unsigned long long seed, unsigned long long offset) {
+__global__ void __launch_bounds__(256) vmf_draw_kernel(float* __restrict__ nw, float* __restrict__ nv, int rows, int D, float kappa,
+                                                       unsigned long long seed, unsigned long long offset) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  curandStatePhilox4_32_10_t st;
-  curand_init(seed, (unsigned long long)row * 32 + lane, offset, &st);
+  HashRng st(seed, offset, (unsigned long long)row * 32 + lane);
   float* v = nv + (long long)row * (D - 1);
-  float ss = 0.f;
-  for (int k = lane; k < D - 1; k += 32) {
-    const float z = curand_normal(&st);
-    v[k] = z;
-    ss = fmaf(z, z, ss);
-  }
-  ss = warp_sum(ss);
-  const float inv = rsqrtf(fmaxf(ss, 1e-30f));
-  for (int k = lane; k < D - 1; k += 32) v[k] *= inv;
-  if (lane == 0) {
-    const float m1 = (float)(D - 1);
-    const float c = sqrtf(4.0f * kappa * kappa + m1 * m1);
-    const float b_true = (-2.0f * kappa + c) / m1;
-    const float b_app = m1 / (4.0f * kappa);
-    const float s = fminf(fmaxf(kappa - 10.0f, 0.f), 1.0f);
-    const float b = b_app * s + b_true * (1.0f - s);
-    const float a = (m1 + 2.0f * kappa + c) / 4.0f;
-    const float d = (4.0f * a * b) / (1.0f + b) - m1 * logf(m1);
-    float w = 0.f;
-    for (int it = 0; it < 256; ++it) {
-      const float g1 = gamma_mt(&st, 0.5f * m1), g2 = gamma_mt(&st, 0.5f * m1);
-      const float eb = g1 / (g1 + g2);
-      const float u = curand_uniform(&st);
-      const float den = 1.0f - (1.0f - b) * eb;
-      w = (1.0f - (1.0f + b) * eb) / den;
-      const float t = (2.0f * a * b) / den;
-      if (m1 * logf(t) - t + d > logf(u)) break;
+  const int n = D - 1;
+  if (n <= 1024) {
+    // the lane's <= 32 tangent coordinates stay in registers: one pass, one coalesced write
+    float z[32];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      if (32 * i < n) {                                   // warp-uniform
+        const float2 g = st.normal2();
+        z[i] = (lane + 32 * i < n) ? g.x : 0.f;
+        z[i + 1] = (lane + 32 * (i + 1) < n) ? g.y : 0.f;
+        ss = fmaf(z[i], z[i], fmaf(z[i + 1], z[i + 1], ss));
+      } else {
+        z[i] = z[i + 1] = 0.f;
+      }
     }
-    nw[row] = w;
+    ss = warp_sum(ss);
+    const float inv = rsqrtf(fmaxf(ss, 1e-30f));
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int k = lane + 32 * i;
+      if (k < n) v[k] = z[i] * inv;
+    }
+  } else {
+    float ss = 0.f;
+    for (int k = lane; k < n; k += 32) {
+      const float zz = st.normal2().x;
+      v[k] = zz;
+      ss = fmaf(zz, zz, ss);
+    }
+    ss = warp_sum(ss);
+    const float inv = rsqrtf(fmaxf(ss, 1e-30f));
+    for (int k = lane; k < n; k += 32) v[k] *= inv;
   }
+  // rejection sampler for w: every lane runs an independent trial per round and the lowest accepting lane wins
+  // (the first accepted draw of an iid sequence in a fixed order has exactly the target distribution)
+  const float m1 = (float)(D - 1);
+  const float c = sqrtf(4.0f * kappa * kappa + m1 * m1);
+  const float b_true = (-2.0f * kappa + c) / m1;
+  const float b_app = m1 / (4.0f * kappa);
+  const float sgate = fminf(fmaxf(kappa - 10.0f, 0.f), 1.0f);
+  const float b = b_app * sgate + b_true * (1.0f - sgate);
+  const float a = (m1 + 2.0f * kappa + c) / 4.0f;
+  const float d = (4.0f * a * b) / (1.0f + b) - m1 * logf(m1);
+  float w = 0.f;
+  for (int it = 0; it < 64; ++it) {
+    const float g1 = gamma_mt(&st, 0.5f * m1), g2 = gamma_mt(&st, 0.5f * m1);
+    const float eb = g1 / (g1 + g2);
+    const float u = st.uniform();
+    const float den = 1.0f - (1.0f - b) * eb;
+    w = (1.0f - (1.0f + b) * eb) / den;
+    const float t = (2.0f * a * b) / den;
+    const bool acc = m1 * logf(t) - t + d > logf(u);
+    const unsigned am = __ballot_sync(0xffffffffu, acc);
+    if (am) {
+      w = __shfl_sync(0xffffffffu, w, __ffs(am) - 1);
+      break;
+    }
+  }
+  if (lane == 0) nw[row] = w;
 }
 
 
@@ -243,15 +306,11 @@ __global__ void __launch_bounds__(256) augment_kernel(const float* __restrict__ 
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  curandStatePhilox4_32_10_t st;
-  curand_init(seed, (unsigned long long)row * 32 + lane, offset, &st);
-  // per-row choice from lane 0's stream (unbiased: rejection of the top 2^32 mod 3 values)
-  unsigned r = 0;
-  if (lane == 0) {
-    do { r = curand(&st); } while (r >= 4294967295u - (4294967295u % 3u));
-    r %= 3u;
-  }
-  const int t = (int)__shfl_sync(0xffffffffu, r, 0);
+  HashRng st(seed, offset, (unsigned long long)row * 32 + lane);
+  // per-row choice: one hashed word per row, mapped to {0,1,2} by a multiply-shift (bias 2^-32)
+  const unsigned rw = (unsigned)(mix64(mix64(seed ^ 0xC2B2AE3D27D4EB4Full) + offset * 0x9E3779B97F4A7C15ull +
+                                       (unsigned long long)row * 0xD1B54A32D192ED03ull) >> 32);
+  const int t = (int)(((unsigned long long)rw * 3ull) >> 32);
   if (choice_out && lane == 0) choice_out[row] = t;
   const float* x = X + (long long)row * ldx;
   float* y = Y + (long long)row * ldy;
@@ -269,12 +328,16 @@ __global__ void __launch_bounds__(256) augment_kernel(const float* __restrict__ 
   if (t == 0) {
     if (cached) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int k = lane + 32 * i;
-        if (k < D) y[k] = xv[i] + noise_scale * curand_normal(&st);
+      for (int i = 0; i < 32; i += 2) {
+        if (32 * i < D) {                                 // warp-uniform
+          const float2 g = st.normal2();
+          const int k = lane + 32 * i;
+          if (k < D) y[k] = fmaf(noise_scale, g.x, xv[i]);
+          if (k + 32 < D) y[k + 32] = fmaf(noise_scale, g.y, xv[i + 1]);
+        }
       }
     } else {
-      for (int k = lane; k < D; k += 32) y[k] = x[k] + noise_scale * curand_normal(&st);
+      for (int k = lane; k < D; k += 32) y[k] = fmaf(noise_scale, st.normal2().x, x[k]);
     }
   } else if (t == 1 && n_drop > 0 && D <= 1024) {
     // D <= 1024: the <= 32 keys of this lane are hashed ONCE into registers; every bisection step is then 32

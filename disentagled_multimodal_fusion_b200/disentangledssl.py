@@ -152,29 +152,32 @@ class DisentangledSSL(LightningModule):
         vv1 = torch.cat([noise[0][1], noise[2][1]], 0)
         w2 = torch.cat([noise[1][0], noise[3][0]], 0)
         vv2 = torch.cat([noise[1][1], noise[3][1]], 0)
-        Z1 = ops.vmf_rsample(E1, w1, vv1)
-        Z2 = ops.vmf_rsample(E2, w2, vv2)
-        P1n, P2n = ops.row_normalize(P1), ops.row_normalize(P2)
+        # bf16 path: the head kernels also write the bf16 copies the InfoNCE tiles (and the NCCL all-gathers) consume
+        pr = self.precision
+        wb = pr == "bf16"
+        Z1, Z2 = ops.vmf_rsample(E1, w1, vv1, want_bf16=wb), ops.vmf_rsample(E2, w2, vv2, want_bf16=wb)
+        P1n, P2n = ops.row_normalize(P1, want_bf16=wb), ops.row_normalize(P2, want_bf16=wb)
+        if wb:
+            (Z1, Z1b), (Z2, Z2b), (P1n, P1b), (P2n, P2b) = Z1, Z2, P1n, P2n
+            bfs = [(Z1b[:B], Z2b[:B]), (Z1b[B:], Z2b[B:]), (P1b[:B], P1b[B:]), (P2b[:B], P2b[B:])]
+        else:
+            bfs = [None] * 4
         # all four critic inputs exist now: launch their embedding all-gathers up front (asynchronous NCCL), so
         # the gathers of calls 2-4 overlap the similarity tiles of call 1
-        pr = self.precision
         pairs = [(Z1[:B], Z2[:B]), (Z1[B:], Z2[B:]), (P1n[:B], P1n[B:]), (P2n[:B], P2n[B:])]
-        pres = [ops.GatheredPair(a, b, pr) for a, b in pairs]
+        pres = [ops.GatheredPair(a, b, pr, bf16=bf) for (a, b), bf in zip(pairs, bfs)]
         # data parallel: every critic call returns this rank's PARTIAL sums; they are all-reduced ONCE below
         # (all combinations are linear and the gradients do not depend on the loss value)
         dp = ops._dist_on()
-        kw = dict(unit_norm=True, reduce=not dp)
-        joint_loss, loss_x, loss_y = self.critic.pair(*pairs[0], pre=pres[0], **kw)
-        joint_loss_v, loss_x_v, loss_y_v = self.critic.pair(*pairs[1], pre=pres[1], **kw)
-        joint_loss = 0.5 * (joint_loss + joint_loss_v)
-        loss_x = 0.5 * (loss_x + loss_x_v)
-        loss_y = 0.5 * (loss_y + loss_y_v)
+        # ONE op for the four critic calls (the reference discards loss_x / loss_y of the two specific-critic calls:
+        # their intra-view blocks are skipped); under data parallelism the four calls share one column-sum all-reduce
+        # and one LSE all-gather
+        out = self.critic.multi(pairs, pres=pres, unit_norm=True, reduce=not dp, diagnostics=[True, True, False, False])
+        joint_loss = 0.5 * (out[0, 0] + out[1, 0])
+        loss_x = 0.5 * (out[0, 1] + out[1, 1]).detach()
+        loss_y = 0.5 * (out[0, 2] + out[1, 2]).detach()
         loss_shared = joint_loss
-
-        # the reference discards loss_x / loss_y of the two specific-critic calls: skip their intra-view blocks
-        specific_loss_x1, _, _ = self.critic.pair(*pairs[2], pre=pres[2], diagnostics=False, **kw)
-        specific_loss_x2, _, _ = self.critic.pair(*pairs[3], pre=pres[3], diagnostics=False, **kw)
-        loss_specific = specific_loss_x1 + specific_loss_x2
+        loss_specific = out[2, 0] + out[3, 0]
 
         lmd = self.lmd_scheduler(self.iterations) if self.lmd_end_value > 0 else self.lmd_start_value
 

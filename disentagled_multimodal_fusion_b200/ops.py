@@ -571,11 +571,15 @@ class GatheredPair:
     A module that knows all its critic inputs early (DisentangledSSL) creates the four pairs up front so that
     the gathers of calls 2..4 overlap the tiles of call 1."""
 
-    def __init__(self, z0: Tensor, z1: Tensor, precision: str):
+    def __init__(self, z0: Tensor, z1: Tensor, precision: str, bf16: Optional[Tuple[Tensor, Tensor]] = None):
+        """``bf16`` = bf16 copies of (z0, z1) already written by the producing kernels (vMF / row-normalise epilogue)."""
         L.require_device()
         with _Prof("gather_launch"):
             z0, z1 = _f32c(z0.detach()), _f32c(z1.detach())
-            self.a0, self.a1 = (cast_bf16(z0), cast_bf16(z1)) if precision == "bf16" else (z0, z1)
+            if precision == "bf16" and bf16 is not None:
+                self.a0, self.a1 = bf16
+            else:
+                self.a0, self.a1 = (cast_bf16(z0), cast_bf16(z1)) if precision == "bf16" else (z0, z1)
             self.works = []
             if _dist_on():
                 world = dist.get_world_size()
@@ -595,24 +599,29 @@ class GatheredPair:
 
 
 class _InfoNCE(torch.autograd.Function):
+    """forward(cfg, z0_0, z1_0, z0_1, z1_1, ...) -> out [ncalls, 3] = (loss, loss_x, loss_y) per critic call.
+    cfg = (temperature, precision, bound, pres, reduce, diag_flags).  All calls of a step go through ONE invocation so
+    that, under data parallelism, the column sums of every call are all-reduced by ONE collective and the row LSEs of
+    every call are all-gathered by ONE collective (the kernels of all calls run first)."""
+
     @staticmethod
-    def forward(ctx, z0, z1, temperature, precision, bound, pre, reduce, diagnostics=True):
+    def forward(ctx, cfg, *zs):
         L.require_device()
-        z0, z1 = _f32c(z0), _f32c(z1)
-        Bl, D = z0.shape
-        dev = z0.device
+        temperature, precision, bound, pres, reduce, diag_flags = cfg
+        nc = len(zs) // 2
+        zs = [_f32c(z) for z in zs]
+        Bl, D = zs[0].shape
+        dev = zs[0].device
         world = dist.get_world_size() if _dist_on() else 1
         rank = dist.get_rank() if world > 1 else 0
         Bg = Bl * world
         dt = 1 if precision == "bf16" else 0
-        if pre is None:      # embeddings all-gathered over NVLink so every rank sees global negatives
-            pre = GatheredPair(z0, z1, precision)
-        pre.wait()
-        a0, a1, g0, g1 = pre.a0, pre.a1, pre.g0, pre.g1
+        if pres is None:      # embeddings all-gathered over NVLink so every rank sees global negatives
+            pres = [GatheredPair(zs[2 * c], zs[2 * c + 1], precision) for c in range(nc)]
         scale = 1.0 / temperature
         off = rank * Bl
-        out3 = torch.zeros(3, dtype=torch.float32, device=dev)
-        lse = torch.empty(2, Bl, dtype=torch.float32, device=dev)
+        out3 = torch.zeros(nc, 3, dtype=torch.float32, device=dev)
+        lse = torch.empty(nc, 2, Bl, dtype=torch.float32, device=dev)
         # the choice must be the SAME on every rank (the two paths issue different collective sequences): it may
         # depend on the shard size, never on this rank's row offset (off = rank * Bl is a multiple of 256 iff Bl is)
         fused = bound is not None and dt == 1 and D % 64 == 0 and D <= 512 and (world == 1 or Bl % 256 == 0)
@@ -620,34 +629,43 @@ class _InfoNCE(torch.autograd.Function):
             # unit-norm embeddings: fixed shift, row AND column sums from one pass over S01, symmetric
             # intra-view blocks on a half window (two B x B blocks of work instead of four)
             shift = float(bound)
-            rs = torch.zeros(3, Bl, dtype=torch.float32, device=dev)
-            cs = torch.zeros(3, Bg, dtype=torch.float32, device=dev)
-            dg = torch.empty(3, Bl, dtype=torch.float32, device=dev)
+            nrow = [3 if d else 1 for d in diag_flags]
+            rbase = [sum(nrow[:c]) for c in range(nc)]
+            rs = torch.zeros(sum(nrow), Bl, dtype=torch.float32, device=dev)
+            cs = torch.zeros(sum(nrow), Bg, dtype=torch.float32, device=dev)
+            dg = torch.empty(sum(nrow), Bl, dtype=torch.float32, device=dev)
 
             def rowcol(A, Bm, k, sym):
                 check(lib.dmf_infonce_rowcol_sums(ptr(A), A.stride(0), Bl, ptr(Bm), Bm.stride(0), Bg, D, scale, shift, sym,
                                                   off, ptr(rs[k]), ptr(cs[k]), off, ptr(dg[k]), stream()))
-            with _Prof("rowlse_x4"):
-                rowcol(a0, g1, 0, 0)     # cross block: rows -> view-0 anchors, columns -> view-1 anchors
-                if diagnostics:
-                    rowcol(a0, g0, 1, 1)     # intra-view blocks: only the no-grad diagnostics loss_x / loss_y need them
-                    rowcol(a1, g1, 2, 1)     # (the reference's row max is the self-similarity 1/T = the fixed shift)
+            for c in range(nc):
+                pres[c].wait()
+                a0, a1, g0, g1 = pres[c].a0, pres[c].a1, pres[c].g0, pres[c].g1
+                b = rbase[c]
+                with _Prof("rowlse_x4"):
+                    rowcol(a0, g1, b, 0)         # cross block: rows -> view-0 anchors, columns -> view-1 anchors
+                    if diag_flags[c]:
+                        rowcol(a0, g0, b + 1, 1)     # intra-view blocks: only the no-grad diagnostics loss_x / loss_y need them
+                        rowcol(a1, g1, b + 2, 1)     # (the reference's row max is the self-similarity 1/T = the fixed shift)
             if world > 1:
                 with _Prof("colsum_allreduce"):
-                    dist.all_reduce(cs if diagnostics else cs[0])
+                    dist.all_reduce(cs)              # ONE collective for the column sums of every call
             mfix = torch.full((Bl,), shift, dtype=torch.float32, device=dev)
-            l_c1 = cs[0, off:off + Bl].contiguous()
-            if diagnostics:
-                l_i0 = rs[1] + cs[1, off:off + Bl]
-                l_i1 = rs[2] + cs[2, off:off + Bl]
-            else:                            # callers that discard loss_x / loss_y (out3[1:] is then meaningless)
-                l_i0, l_i1 = rs[0], l_c1
-                dg[1].copy_(dg[0])
-                dg[2].copy_(dg[0])
-            check(lib.dmf_infonce_finalize(ptr(mfix), ptr(rs[0]), ptr(mfix), ptr(l_i0), ptr(dg[0]), ptr(dg[1]), Bl,
-                                           1.0 / (2 * Bg), 1.0 / Bg, 0, ptr(lse[0]), ptr(out3), stream()))
-            check(lib.dmf_infonce_finalize(ptr(mfix), ptr(l_c1), ptr(mfix), ptr(l_i1), ptr(dg[0]), ptr(dg[2]), Bl,
-                                           1.0 / (2 * Bg), 1.0 / Bg, 1, ptr(lse[1]), ptr(out3), stream()))
+            with _Prof("finalize"):
+                for c in range(nc):
+                    b = rbase[c]
+                    l_c1 = cs[b, off:off + Bl].contiguous()
+                    if diag_flags[c]:
+                        l_i0 = rs[b + 1] + cs[b + 1, off:off + Bl]
+                        l_i1 = rs[b + 2] + cs[b + 2, off:off + Bl]
+                        d1, d2 = dg[b + 1], dg[b + 2]
+                    else:                            # callers that discard loss_x / loss_y (out3[c, 1:] is then meaningless)
+                        l_i0, l_i1 = rs[b], l_c1
+                        d1 = d2 = dg[b]
+                    check(lib.dmf_infonce_finalize(ptr(mfix), ptr(rs[b]), ptr(mfix), ptr(l_i0), ptr(dg[b]), ptr(d1), Bl,
+                                                   1.0 / (2 * Bg), 1.0 / Bg, 0, ptr(lse[c, 0]), ptr(out3[c]), stream()))
+                    check(lib.dmf_infonce_finalize(ptr(mfix), ptr(l_c1), ptr(mfix), ptr(l_i1), ptr(dg[b]), ptr(d2), Bl,
+                                                   1.0 / (2 * Bg), 1.0 / Bg, 1, ptr(lse[c, 1]), ptr(out3[c]), stream()))
         else:
             st = torch.empty(12, Bl, dtype=torch.float32, device=dev)
             wsb = lib.dmf_rowlse_workspace_bytes(Bl, Bg) if dt == 1 else 0
@@ -656,51 +674,74 @@ class _InfoNCE(torch.autograd.Function):
             def rowlse(A, Bm, mo, lo, do):
                 check(lib.dmf_rowlse(ptr(A), A.stride(0), Bl, ptr(Bm), Bm.stride(0), Bg, D, scale, ptr(st[mo]), ptr(st[lo]),
                                      off, ptr(st[do]), ptr(ws), wsb, dt, stream()))
-            with _Prof("rowlse_x4"):
-                rowlse(a0, g1, 0, 1, 2)      # anchors z0 vs all z1: cross block, diag = positive
-                rowlse(a0, g0, 3, 4, 5)      # anchors z0 vs all z0: intra-view block, diag = self similarity
-                rowlse(a1, g0, 6, 7, 8)
-                rowlse(a1, g1, 9, 10, 11)
-            check(lib.dmf_infonce_finalize(ptr(st[0]), ptr(st[1]), ptr(st[3]), ptr(st[4]), ptr(st[2]), ptr(st[5]), Bl,
-                                           1.0 / (2 * Bg), 1.0 / Bg, 0, ptr(lse[0]), ptr(out3), stream()))
-            check(lib.dmf_infonce_finalize(ptr(st[6]), ptr(st[7]), ptr(st[9]), ptr(st[10]), ptr(st[8]), ptr(st[11]), Bl,
-                                           1.0 / (2 * Bg), 1.0 / Bg, 1, ptr(lse[1]), ptr(out3), stream()))
+            for c in range(nc):
+                pres[c].wait()
+                a0, a1, g0, g1 = pres[c].a0, pres[c].a1, pres[c].g0, pres[c].g1
+                with _Prof("rowlse_x4"):
+                    rowlse(a0, g1, 0, 1, 2)      # anchors z0 vs all z1: cross block, diag = positive
+                    rowlse(a0, g0, 3, 4, 5)      # anchors z0 vs all z0: intra-view block, diag = self similarity
+                    rowlse(a1, g0, 6, 7, 8)
+                    rowlse(a1, g1, 9, 10, 11)
+                check(lib.dmf_infonce_finalize(ptr(st[0]), ptr(st[1]), ptr(st[3]), ptr(st[4]), ptr(st[2]), ptr(st[5]), Bl,
+                                               1.0 / (2 * Bg), 1.0 / Bg, 0, ptr(lse[c, 0]), ptr(out3[c]), stream()))
+                check(lib.dmf_infonce_finalize(ptr(st[6]), ptr(st[7]), ptr(st[9]), ptr(st[10]), ptr(st[8]), ptr(st[11]), Bl,
+                                               1.0 / (2 * Bg), 1.0 / Bg, 1, ptr(lse[c, 1]), ptr(out3[c]), stream()))
         if world > 1:
             with _Prof("lse_gather"):
                 if reduce:
                     dist.all_reduce(out3)
-                gath = torch.empty(world, 2, Bl, dtype=torch.float32, device=dev)      # one collective for both views
+                gath = torch.empty(world, nc, 2, Bl, dtype=torch.float32, device=dev)   # one collective: all calls, both views
                 dist.all_gather_into_tensor(gath, lse)
-                lse_all = gath.permute(1, 0, 2).reshape(2, Bg).contiguous()
+                lse_all = gath.permute(1, 2, 0, 3).reshape(nc, 2, Bg).contiguous()
         else:
             lse_all = lse
-        ctx.save_for_backward(a0, a1, g0, g1, lse, lse_all)
-        ctx.meta = (Bl, Bg, D, scale, off, dt)
+        saved = []
+        for c in range(nc):
+            saved += [pres[c].a0, pres[c].a1, pres[c].g0, pres[c].g1]
+        ctx.save_for_backward(lse, lse_all, *saved)
+        ctx.meta = (nc, Bl, Bg, D, scale, off, dt)
         return out3
 
     @staticmethod
     def backward(ctx, gout):
-        a0, a1, g0, g1, lse, lse_all = ctx.saved_tensors
-        Bl, Bg, D, scale, off, dt = ctx.meta
-        dev = a0.device
-        gs = gout[0:1].contiguous().float()         # only the loss has a gradient; diagnostics are no-grad
+        lse, lse_all, *saved = ctx.saved_tensors
+        nc, Bl, Bg, D, scale, off, dt = ctx.meta
+        dev = lse.device
+        gout = gout.contiguous().float()
         coef = scale / (2.0 * Bg)
-        dz0 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
-        dz1 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
-        if dt == 1:
-            with _Prof("transpose_gathered"):
-                g0T, g1T = transpose_bf16(g0), transpose_bf16(g1)
-        else:
-            g0T = g1T = None
-        with _Prof("infonce_bwd"):
-            check(lib.dmf_infonce_bwd(ptr(a0), a0.stride(0), Bl, ptr(lse[0]), ptr(g1), g1.stride(0), ptr(g1T),
-                                      g1T.stride(0) if g1T is not None else 0, Bg, ptr(lse_all[1]), D, scale, coef, ptr(gs),
-                                      off, ptr(dz0), D, 0, dt, stream()))
-        with _Prof("infonce_bwd"):
-            check(lib.dmf_infonce_bwd(ptr(a1), a1.stride(0), Bl, ptr(lse[1]), ptr(g0), g0.stride(0), ptr(g0T),
-                                      g0T.stride(0) if g0T is not None else 0, Bg, ptr(lse_all[0]), D, scale, coef, ptr(gs),
-                                      off, ptr(dz1), D, 0, dt, stream()))
-        return dz0, dz1, None, None, None, None, None, None
+        grads = []
+        for c in range(nc):
+            a0, a1, g0, g1 = saved[4 * c: 4 * c + 4]
+            gs = gout[c, 0:1]                           # only the loss has a gradient; diagnostics are no-grad
+            dz0 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
+            dz1 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
+            if dt == 1:
+                with _Prof("transpose_gathered"):
+                    g0T, g1T = transpose_bf16(g0), transpose_bf16(g1)
+            else:
+                g0T = g1T = None
+            with _Prof("infonce_bwd"):
+                check(lib.dmf_infonce_bwd(ptr(a0), a0.stride(0), Bl, ptr(lse[c, 0]), ptr(g1), g1.stride(0), ptr(g1T),
+                                          g1T.stride(0) if g1T is not None else 0, Bg, ptr(lse_all[c, 1]), D, scale, coef, ptr(gs),
+                                          off, ptr(dz0), D, 0, dt, stream()))
+            with _Prof("infonce_bwd"):
+                check(lib.dmf_infonce_bwd(ptr(a1), a1.stride(0), Bl, ptr(lse[c, 1]), ptr(g0), g0.stride(0), ptr(g0T),
+                                          g0T.stride(0) if g0T is not None else 0, Bg, ptr(lse_all[c, 0]), D, scale, coef, ptr(gs),
+                                          off, ptr(dz1), D, 0, dt, stream()))
+            grads += [dz0, dz1]
+        return (None, *grads)
+
+
+def infonce_multi(pairs: Sequence[Tuple[Tensor, Tensor]], temperature: float = 0.07, precision: str = "fp32",
+                  unit_norm: bool = False, pres: Optional[Sequence["GatheredPair"]] = None, reduce: bool = True,
+                  diagnostics: Optional[Sequence[bool]] = None) -> Tensor:
+    """All critic calls of a step in ONE op: returns out [ncalls, 3] = (loss, loss_x, loss_y) per call (rows of calls
+    with ``diagnostics[c] == False`` carry the loss only).  Same semantics per call as ``infonce``; under
+    torch.distributed the column sums / row LSEs / loss scalars of all calls share one collective each."""
+    bound = (1.0 / float(temperature)) if unit_norm else None
+    flags = tuple(bool(d) for d in (diagnostics if diagnostics is not None else [True] * len(pairs)))
+    flat = [z for p in pairs for z in p]
+    return _InfoNCE.apply((float(temperature), precision, bound, list(pres) if pres is not None else None, reduce, flags), *flat)
 
 
 def infonce(z0: Tensor, z1: Tensor, temperature: float = 0.07, precision: str = "fp32",
@@ -716,8 +757,8 @@ def infonce(z0: Tensor, z1: Tensor, temperature: float = 0.07, precision: str = 
     ``diagnostics=False``: the caller discards loss_x / loss_y (the reference's specific-critic calls,
     models/disentangledssl.py:143-144); the unit-norm bf16 path then skips the two intra-view blocks (half of the
     forward work) and returns None for them."""
-    bound = (1.0 / float(temperature)) if unit_norm else None
-    out = _InfoNCE.apply(z0, z1, float(temperature), precision, bound, pre, reduce, diagnostics)
+    out = infonce_multi([(z0, z1)], temperature, precision, unit_norm, [pre] if pre is not None else None, reduce,
+                        [diagnostics])[0]
     if not diagnostics:
         return out[0], None, None
     return out[0], out[1].detach(), out[2].detach()
@@ -728,59 +769,68 @@ def infonce(z0: Tensor, z1: Tensor, temperature: float = 0.07, precision: str = 
 # ----------------------------------------------------------------------------------------
 class _RowNormalize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, eps):
+    def forward(ctx, x, eps, want_bf16=False):
         L.require_device()
         x = _f32c(x)
         R, D = x.shape
         y = torch.empty_like(x)
+        yb = torch.empty(R, D, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
         inv = torch.empty(R, dtype=torch.float32, device=x.device)
         with _Prof("head_fwd"):
-            check(lib.dmf_row_normalize_fwd(ptr(x), D, R, D, eps, ptr(y), D, 0, 0, ptr(inv), stream()))
+            check(lib.dmf_row_normalize_fwd(ptr(x), D, R, D, eps, ptr(y), D, ptr(yb), D, ptr(inv), stream()))
         ctx.save_for_backward(y, inv)
+        if want_bf16:
+            ctx.mark_non_differentiable(yb)
+            return y, yb
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, *unused):
         y, inv = ctx.saved_tensors
         dy = _f32c(dy)
         R, D = y.shape
         dx = torch.empty_like(y)
         with _Prof("head_bwd"):
             check(lib.dmf_row_normalize_bwd(ptr(y), D, ptr(inv), ptr(dy), D, R, D, ptr(dx), D, 0, stream()))
-        return dx, None
+        return dx, None, None
 
 
-def row_normalize(x: Tensor, eps: float = 1e-12) -> Tensor:
-    """F.normalize(x, dim=-1)."""
-    return _RowNormalize.apply(x, eps)
+def row_normalize(x: Tensor, eps: float = 1e-12, want_bf16: bool = False):
+    """F.normalize(x, dim=-1); ``want_bf16`` also returns a bf16 copy written by the same kernel pass."""
+    return _RowNormalize.apply(x, eps, want_bf16)
 
 
 class _VmfSample(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, e, w, v):
+    def forward(ctx, e, w, v, want_bf16=False):
         L.require_device()
         e, w, v = _f32c(e), _f32c(w), _f32c(v)
         R, D = e.shape
         z = torch.empty_like(e)
+        zb = torch.empty(R, D, dtype=torch.bfloat16, device=e.device) if want_bf16 else None
         with _Prof("head_fwd"):
-            check(lib.dmf_vmf_fwd(ptr(e), D, ptr(w), ptr(v), R, D, ptr(z), D, 0, 0, stream()))
+            check(lib.dmf_vmf_fwd(ptr(e), D, ptr(w), ptr(v), R, D, ptr(z), D, ptr(zb), D, stream()))
         ctx.save_for_backward(e, w, v)
+        if want_bf16:
+            ctx.mark_non_differentiable(zb)
+            return z, zb
         return z
 
     @staticmethod
-    def backward(ctx, dz):
+    def backward(ctx, dz, *unused):
         e, w, v = ctx.saved_tensors
         dz = _f32c(dz)
         R, D = e.shape
         de = torch.empty_like(e)
         with _Prof("head_bwd"):
             check(lib.dmf_vmf_bwd(ptr(e), D, ptr(w), ptr(v), ptr(dz), D, R, D, ptr(de), D, 0, stream()))
-        return de, None, None
+        return de, None, None, None
 
 
-def vmf_rsample(e: Tensor, w: Tensor, v: Tensor) -> Tensor:
-    """ProbabilisticEncoder('vmf')(e)[0].rsample() with the noise (w [B,1], v [B,D-1]) supplied."""
-    return _VmfSample.apply(e, w, v)
+def vmf_rsample(e: Tensor, w: Tensor, v: Tensor, want_bf16: bool = False):
+    """ProbabilisticEncoder('vmf')(e)[0].rsample() with the noise (w [B,1], v [B,D-1]) supplied; ``want_bf16`` also
+    returns a bf16 copy of the sample written by the same kernel pass."""
+    return _VmfSample.apply(e, w, v, want_bf16)
 
 
 class _OrthoLoss(torch.autograd.Function):

@@ -308,12 +308,15 @@ def run_gpu(args, rank, world, local_rank):
         loss, logs = model(inp["x1"], inp["x2"], inp["v1"], inp["v2"], noise=noise_bufs)
         bb.zero_grad()
         loss.backward()
-        bb.allreduce_grads()
-        bb.adam_step(1e-4, capturable=capturable)
+        # the backbone's gradient all-reduce runs UNDER the probe's forward / backward (the probe reads the backbone
+        # this step's forward pass used; both optimizers step at the end)
+        pending = bb.allreduce_grads(async_op=True)
         ploss, _, _, _ = probe.shared_step([inp["x1"], inp["x2"], inp["y"]])
         hd.zero_grad()
         ploss.backward()
         hd.allreduce_grads()
+        bb.wait_grads(pending)
+        bb.adam_step(1e-4, capturable=capturable)
         hd.adam_step(3e-3, weight_decay=1e-4, decoupled=True, capturable=capturable)
         return loss.detach() + ploss.detach()
 

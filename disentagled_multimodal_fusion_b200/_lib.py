@@ -84,6 +84,7 @@ _SIGS = {
     "dmf_infonce_finalize": ([c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_f, c_i, c_p, c_p, c_p], c_i),
     "dmf_infonce_bwd": ([c_p, c_ll, c_i, c_p, c_p, c_ll, c_p, c_ll, c_i, c_p, c_i, c_f, c_f, c_p, c_ll, c_p, c_ll,
                          c_i, c_i, c_p], c_i),
+    "dmf_infonce_bwd_needs_transposed": ([c_i], c_i),
     "dmf_row_normalize_fwd": ([c_p, c_ll, c_i, c_i, c_f, c_p, c_ll, c_p, c_ll, c_p, c_p], c_i),
     "dmf_row_normalize_bwd": ([c_p, c_ll, c_p, c_p, c_ll, c_i, c_i, c_p, c_ll, c_i, c_p], c_i),
     "dmf_sumsq_f32": ([c_p, c_ll, c_p, c_p], c_i),

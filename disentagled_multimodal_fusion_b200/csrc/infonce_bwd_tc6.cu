@@ -13,7 +13,10 @@
 // Per 256-column tile t and CTA rank r (j0 = first column, all MMAs M = 128 / N = 256 / K = 16):
 //   S(t)   = anchors[64 x D] (smem, resident)  x  Bm[j0 + 128 r .. +128, D]^T       8 ring stages [128 j x 64 d]
 //   W(t)   = softmax warps: TMEM -> exp2 -> bf16 -> smem (K-major, 128B swizzle), the A operand of
-//   O     += W(t)[64 x 256]  x  BmT[d, j0 .. j0 + 256)^T   two N = 256 halves h    8 ring stages [128 d x 64 j]
+//   O     += W(t)[64 x 256]  x  Bm[j0 .. j0 + 256, d]      two N = 256 halves h    8 ring stages [128 j x 64 d]
+// The second product reads Bm through the SAME tensor map as the first: its B operand is taken MN-major (the 64
+// contiguous d of a tile row are the N dimension, the 128 tile rows j the K dimension; two adjacent stages = the
+// CTA's 128 d of one output half), so no transposed copy of the column block is ever needed.
 // One unified 8-stage ring of 16 KB operand tiles, consumed in the order S(0) S(1) PV(0) S(2) PV(1) ...
 // W goes through shared memory (not TMEM): the TMEM A operand of a 2-SM M = 128 MMA must be duplicated on both
 // lane halves, i.e. every softmax warp would have to hand its half tile to the warp of the opposite lane half.
@@ -49,8 +52,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2_6(float lo, float hi) {
 // DBG (timing experiments, tools builds only): 1 = no softmax math / W stores, 2 = no PV MMAs, 4 = no S MMAs
 template <int DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(B6_THREADS, 1)
-infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const __grid_constant__ CUtensorMap tmBT, int Ma, int Nb, int D, int num_kb, float scale,
+infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Ma, int Nb, int D, int num_kb, float scale,
                        const float* __restrict__ lseA, const float* __restrict__ lseB, float coef,
                        const float* __restrict__ gscale, long long diag_offset, const uint16_t* __restrict__ Bm,
                        long long ldb, float* __restrict__ dA, long long ldda, int accumulate) {
@@ -89,7 +91,6 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
-    tc::tma_prefetch_desc(&tmBT);
     tc::mbar_init(a_full, 1);
     for (int s = 0; s < B6_STAGES; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
     for (int b = 0; b < 2; ++b) { tc::mbar_init(s_full + b, 1); tc::mbar_init(w_full + b, 16); }
@@ -126,17 +127,21 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     };
     auto load_v = [&](int t) {
+      // PV operand: for each half jh of the tile rows and each output half h, the CTA's 128 d-columns as two
+      // [128 j x 64 d] tiles in ADJACENT stages (stage index even: every phase uses an even number of stages)
       const int j0 = (tz0 + t) * B6_NT;
-      for (int jc = 0; jc < 4; ++jc)
-        for (int h = 0; h < nh; ++h) {
-          tc::mbar_wait(empty_bar + stage, phase ^ 1);
-          if (tc::elect_one()) {
-            if (leader) tc::mbar_expect_tx(full_bar + stage, 2 * B6_STAGE);
-            tc2::tma_load_2d_pair(ring + stage * B6_STAGE, &tmBT, j0 + jc * 64, h * 256 + (int)rank * 128, full_bar + stage);
+      for (int jh = 0; jh < 2; ++jh)
+        for (int h = 0; h < nh; ++h)
+          for (int c = 0; c < 2; ++c) {
+            tc::mbar_wait(empty_bar + stage, phase ^ 1);
+            if (tc::elect_one()) {
+              if (leader) tc::mbar_expect_tx(full_bar + stage, 2 * B6_STAGE);
+              tc2::tma_load_2d_pair(ring + stage * B6_STAGE, &tmB, h * 256 + (int)rank * 128 + c * 64, j0 + jh * 128,
+                                    full_bar + stage);
+            }
+            __syncwarp();
+            if (++stage == B6_STAGES) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == B6_STAGES) { stage = 0; phase ^= 1; }
-        }
     };
     // consumption order of the MMA thread: S(0), S(1), PV(0), S(2), PV(1), ...
     if (ntiles > 0) load_s(0);
@@ -148,9 +153,11 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (leader) {
       // MMA issuer: whole warp, uniform control flow; one elected lane issues the tcgen05 instructions
       constexpr uint32_t idesc = tc::make_idesc_bf16(128, 256, 0, 0);
+      constexpr uint32_t idesc_pv = tc::make_idesc_bf16(128, 256, 0, 1);        // B operand MN-major
       const uint64_t adesc0 = tc::make_smem_desc(tc::smem_u32(smemA), 16, 1024);
       const uint64_t wdesc0 = tc::make_smem_desc(tc::smem_u32(smemW), 16, 1024);
       const uint64_t rdesc0 = tc::make_smem_desc(tc::smem_u32(ring), 16, 1024);
+      const uint64_t vdesc0 = tc::make_smem_desc(tc::smem_u32(ring), B6_STAGE, 1024);   // MN-major: LBO = next 64-d chunk
       tc::mbar_wait(a_full, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -179,22 +186,30 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (t + 1 < ntiles) issue_s(t + 1);
         tc::mbar_wait(w_full + (t & 1), ((uint32_t)t >> 1) & 1);
         tc::tc_fence_after_sync();
-        for (int jc = 0; jc < 4; ++jc)
+        for (int jh = 0; jh < 2; ++jh)
           for (int h = 0; h < nh; ++h) {
+            // two adjacent stages = [128 j] x [2 x 64 d] of this output half: MN-major B operand, LBO = stage pitch
             tc::mbar_wait(full_bar + stage, phase);
+            tc::mbar_wait(full_bar + stage + 1, phase);
             tc::tc_fence_after_sync();
-            const uint64_t wd = wdesc0 + (uint64_t)((jc * B6_KB) >> 4);
-            const uint64_t vd = rdesc0 + (uint64_t)((stage * B6_STAGE) >> 4);
+            const uint64_t vd = vdesc0 + (uint64_t)((stage * B6_STAGE) >> 4);
             if (tc::elect_one()) {
               if (!(DBG & 2)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  tc2::umma_ss2(tmem_O + (uint32_t)(h * 128), wd + 2 * k, vd + 2 * k, idesc, (t | jc | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 8; ++k) {
+                  // W columns j = 128 jh + 16 k .. +15: k-block 2 jh + (k >> 2), 32-byte step (k & 3) inside it;
+                  // B rows j advance by 16 x 128 B = 2048 B per step
+                  const uint64_t wd = wdesc0 + (uint64_t)((((2 * jh + (k >> 2)) * B6_KB) + (k & 3) * 32) >> 4);
+                  tc2::umma_ss2(tmem_O + (uint32_t)(h * 128), wd, vd + (uint64_t)((k * 2048) >> 4), idesc_pv,
+                                (t | jh | k) != 0 ? 1u : 0u);
+                }
               }
               tc2::umma_commit2(empty_bar + stage);
+              tc2::umma_commit2(empty_bar + stage + 1);
             }
             __syncwarp();
-            if (++stage == B6_STAGES) { stage = 0; phase ^= 1; }
+            stage += 2;
+            if (stage == B6_STAGES) { stage = 0; phase ^= 1; }
           }
         if (tc::elect_one()) tc2::umma_commit2(pv_done);
         __syncwarp();
@@ -312,12 +327,11 @@ int dmf_infonce_bwd_bf16_tc6(const void* A, long long lda, int Ma, const float* 
   if (D != 256 && D != 512) return -100;
   if ((reinterpret_cast<uintptr_t>(dA) & 15) != 0 || (ldda & 3) != 0) return -100;
   const int num_kb = D / 64;
-  CUtensorMap tmA, tmB, tmBT;
+  (void)BmT; (void)ldbt;                                       // not needed: the second product reads Bm MN-major
+  CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_2d(&tmA, A, Ma, D, lda, 64);        // each CTA keeps 64 anchor rows
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmB, Bm, Nb, D, ldb, 128);          // each CTA loads 128 of the 256 tile rows
-  if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmBT, BmT, D, Nb, ldbt, 128);       // each CTA loads 128 of the 256 d-rows of an output half
+  rc = make_tmap_bf16_2d(&tmB, Bm, Nb, D, ldb, 128);          // [128 rows x 64 cols] boxes for both products
   if (rc) return rc;
   int dbg = 0;
 #ifdef DMF_TC6_DBG
@@ -361,7 +375,7 @@ int dmf_infonce_bwd_bf16_tc6(const void* A, long long lda, int Ma, const float* 
     if (e != cudaSuccess) return fail((int)e, "dmf_infonce_bwd(bf16 m128): memset: %s", cudaGetErrorString(e));
   }
   dim3 grid(2 * blocks, 1, nsplit);
-  kern<<<grid, B6_THREADS, B6_SMEM, s>>>(tmA, tmB, tmBT, Ma, Nb, D, num_kb, scale, lseA, lseB, coef, gscale, diag_offset,
+  kern<<<grid, B6_THREADS, B6_SMEM, s>>>(tmA, tmB, Ma, Nb, D, num_kb, scale, lseA, lseB, coef, gscale, diag_offset,
                                          (const uint16_t*)Bm, ldb, dA, ldda, accumulate);
   return launched("dmf_infonce_bwd(bf16 m128)");
 }

@@ -450,6 +450,13 @@ static int pick_nsplit(int row_blocks, int col_tiles) {
   return best;
 }
 
+// 1 when dmf_infonce_bwd (bf16) needs the transposed column block BmT for width D (the M = 128 pair kernel, D = 256 or
+// 512 with a 16-byte aligned dA whose row pitch is a multiple of 4, reads Bm alone), 0 otherwise.
+extern "C" int dmf_infonce_bwd_needs_transposed(int D) {
+  if (getenv("DMF_BWD_V1") || getenv("DMF_BWD_V2") || getenv("DMF_BWD_V3")) return 1;
+  return (D == 256 || D == 512) ? 0 : 1;
+}
+
 extern "C" size_t dmf_rowlse_workspace_bytes(int Ma, int Nb) {
   (void)Nb;
   return (size_t)8 * 2 * sizeof(float) * (size_t)(Ma > 0 ? Ma : 0);
@@ -517,7 +524,6 @@ int dmf_infonce_bwd_bf16_tc(const void* A, long long lda, int Ma, const float* l
                             cudaStream_t s) {
   DMF_REQUIRE(D % 64 == 0 && D >= 64 && D <= 64 * NT_MAX_KB, "dmf_infonce_bwd(bf16): D=%d must be a multiple of 64 in [64,%d]",
               D, 64 * NT_MAX_KB);
-  DMF_REQUIRE(BmT, "dmf_infonce_bwd(bf16): needs the transposed column block BmT [D, Nb]");
   {
     static int use_v1 = -1, use_v2 = -1, use_v3 = -1;
     if (use_v1 < 0) { use_v1 = getenv("DMF_BWD_V1") ? 1 : 0; use_v2 = getenv("DMF_BWD_V2") ? 1 : 0; use_v3 = getenv("DMF_BWD_V3") ? 1 : 0; }
@@ -527,6 +533,8 @@ int dmf_infonce_bwd_bf16_tc(const void* A, long long lda, int Ma, const float* l
                                                diag_offset, dA, ldda, accumulate, s);
       if (rc6 != -100) return rc6;
     }
+    DMF_REQUIRE(BmT, "dmf_infonce_bwd(bf16): this shape (D not in {256, 512} or unaligned dA) needs the transposed column "
+                     "block BmT [D, Nb]; see dmf_infonce_bwd_needs_transposed");
     if (!use_v1 && !use_v2 && !accumulate && D == 512) {
       // 4-CTA clusters: S recomputed once per row block, W exchanged between the two slice pairs over DSMEM
       const int rc5 = dmf_infonce_bwd_bf16_tc5(A, lda, Ma, lseA, Bm, ldb, BmT, ldbt, Nb, lseB, D, scale, coef, gscale,

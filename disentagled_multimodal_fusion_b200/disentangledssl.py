@@ -74,10 +74,12 @@ class DisentangledSSL(LightningModule):
         self.shared_embedding_dim = 2 * embed_dim   # width of get_embedding()[0]
 
     # ---------- models/disentangledssl.py:67-80
-    def _encode(self, rows1, rows2):
+    def _encode(self, rows1, rows2, after_shared=None):
         """shared + private encoders on row-stacked inputs of the two modalities (one grouped launch
         per layer): returns (E1, E2, P1, P2).  bf16 path: inputs are cast once into the
-        [rows, d + D] concat buffers that feed both the shared (K = d) and the private (K = d + D) MLP."""
+        [rows, d + D] concat buffers that feed both the shared (K = d) and the private (K = d + D) MLP.
+        ``after_shared(E1, E2)`` runs between the two encoder stacks (the forward pass launches the vMF heads and the
+        all-gathers of the shared critic calls there, so that they overlap the private encoders)."""
         D = self.embed_dim
         if self.precision == "bf16":
             need_t = torch.is_grad_enabled()
@@ -103,11 +105,15 @@ class DisentangledSSL(LightningModule):
                       out_bf16=[bufs[0][:, dims[0]:], bufs[1][:, dims[1]:]],
                       out_bf16T=[bufTs[0][dims[0]:], bufTs[1][dims[1]:]] if need_t else None)
             E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="bf16", opts=o1)
+            if after_shared is not None:
+                after_shared(E1, E2)
             o2 = dict(xTs=list(bufTs) if need_t else None, extras_prefilled=True)
             P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], bufs, extras=[E1, E2], precision="bf16", opts=o2)
         else:
             ins = [torch.cat(rows1, 0) if len(rows1) > 1 else rows1[0], torch.cat(rows2, 0) if len(rows2) > 1 else rows2[0]]
             E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="fp32")
+            if after_shared is not None:
+                after_shared(E1, E2)
             P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], ins, extras=[E1, E2], precision="fp32")
         return E1, E2, P1, P2
 
@@ -145,27 +151,36 @@ class DisentangledSSL(LightningModule):
             noise = self.draw_noise(B, dev)
         # stack original + augmented rows: one group per modality; private encoders are conditioned
         # on the shared code (layer-0 input = [x | e])
-        E1, E2, P1, P2 = self._encode([x1, v1], [x2, v2])                       # [2B, D] each
-
-        # vMF reparameterised samples (noise rows follow the stacking: modality 1 <- draws 0,2; modality 2 <- 1,3)
-        w1 = torch.cat([noise[0][0], noise[2][0]], 0)
-        vv1 = torch.cat([noise[0][1], noise[2][1]], 0)
-        w2 = torch.cat([noise[1][0], noise[3][0]], 0)
-        vv2 = torch.cat([noise[1][1], noise[3][1]], 0)
-        # bf16 path: the head kernels also write the bf16 copies the InfoNCE tiles (and the NCCL all-gathers) consume
         pr = self.precision
-        wb = pr == "bf16"
-        Z1, Z2 = ops.vmf_rsample(E1, w1, vv1, want_bf16=wb), ops.vmf_rsample(E2, w2, vv2, want_bf16=wb)
+        wb = pr == "bf16"          # bf16 path: the head kernels also write the bf16 copies the InfoNCE tiles consume
+        st = {}
+
+        def heads_shared(E1, E2):
+            # vMF reparameterised samples (noise rows follow the stacking: modality 1 <- draws 0,2; modality 2 <- 1,3)
+            w1 = torch.cat([noise[0][0], noise[2][0]], 0)
+            vv1 = torch.cat([noise[0][1], noise[2][1]], 0)
+            w2 = torch.cat([noise[1][0], noise[3][0]], 0)
+            vv2 = torch.cat([noise[1][1], noise[3][1]], 0)
+            Z1, Z2 = ops.vmf_rsample(E1, w1, vv1, want_bf16=wb), ops.vmf_rsample(E2, w2, vv2, want_bf16=wb)
+            if wb:
+                (Z1, Z1b), (Z2, Z2b) = Z1, Z2
+                bf = [(Z1b[:B], Z2b[:B]), (Z1b[B:], Z2b[B:])]
+            else:
+                bf = [None, None]
+            st["pairs"] = [(Z1[:B], Z2[:B]), (Z1[B:], Z2[B:])]
+            # the shared critic inputs exist now: launch their embedding all-gathers (asynchronous NCCL) BEFORE the
+            # private encoders run, so that the gathers overlap those GEMMs
+            st["pres"] = [ops.GatheredPair(a, b, pr, bf16=f) for (a, b), f in zip(st["pairs"], bf)]
+        E1, E2, P1, P2 = self._encode([x1, v1], [x2, v2], after_shared=heads_shared)                       # [2B, D] each
         P1n, P2n = ops.row_normalize(P1, want_bf16=wb), ops.row_normalize(P2, want_bf16=wb)
         if wb:
-            (Z1, Z1b), (Z2, Z2b), (P1n, P1b), (P2n, P2b) = Z1, Z2, P1n, P2n
-            bfs = [(Z1b[:B], Z2b[:B]), (Z1b[B:], Z2b[B:]), (P1b[:B], P1b[B:]), (P2b[:B], P2b[B:])]
+            (P1n, P1b), (P2n, P2b) = P1n, P2n
+            bf = [(P1b[:B], P1b[B:]), (P2b[:B], P2b[B:])]
         else:
-            bfs = [None] * 4
-        # all four critic inputs exist now: launch their embedding all-gathers up front (asynchronous NCCL), so
-        # the gathers of calls 2-4 overlap the similarity tiles of call 1
-        pairs = [(Z1[:B], Z2[:B]), (Z1[B:], Z2[B:]), (P1n[:B], P1n[B:]), (P2n[:B], P2n[B:])]
-        pres = [ops.GatheredPair(a, b, pr, bf16=bf) for (a, b), bf in zip(pairs, bfs)]
+            bf = [None, None]
+        pairs23 = [(P1n[:B], P1n[B:]), (P2n[:B], P2n[B:])]
+        pairs = st["pairs"] + pairs23
+        pres = st["pres"] + [ops.GatheredPair(a, b, pr, bf16=f) for (a, b), f in zip(pairs23, bf)]
         # data parallel: every critic call returns this rank's PARTIAL sums; they are all-reduced ONCE below
         # (all combinations are linear and the gradients do not depend on the loss value)
         dp = ops._dist_on()

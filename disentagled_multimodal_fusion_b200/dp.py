@@ -87,13 +87,23 @@ class FlatParams:
             p.grad = self.grad[o:o + k].view_as(p.data)
             o += k
 
-    def allreduce_grads(self):
-        """SUM over ranks (losses are normalised by the global batch, so no division here)."""
+    def allreduce_grads(self, async_op: bool = False):
+        """SUM over ranks (losses are normalised by the global batch, so no division here).  ``async_op=True`` only
+        LAUNCHES the collective (NCCL's stream) and returns a handle: call ``wait_grads(handle)`` before the optimizer
+        step -- other work (e.g. the probe's forward / backward) can run under the all-reduce."""
         from . import ops
         rank, ws = world()
         if ws > 1:
             with ops._Prof("grad_allreduce"):
-                dist.all_reduce(self.grad)
+                return dist.all_reduce(self.grad, async_op=async_op)
+        return None
+
+    @staticmethod
+    def wait_grads(handle):
+        from . import ops
+        if handle is not None:
+            with ops._Prof("grad_allreduce_wait"):
+                handle.wait()
 
     def adam_step(self, lr: float, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, capturable=False):
         """Fused flat-buffer Adam / AdamW.  ``capturable=True`` keeps the step count and the learning rate in device

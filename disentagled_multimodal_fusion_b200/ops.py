@@ -715,10 +715,10 @@ class _InfoNCE(torch.autograd.Function):
             gs = gout[c, 0:1]                           # only the loss has a gradient; diagnostics are no-grad
             dz0 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
             dz1 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
-            if dt == 1:
+            if dt == 1 and lib.dmf_infonce_bwd_needs_transposed(D):
                 with _Prof("transpose_gathered"):
                     g0T, g1T = transpose_bf16(g0), transpose_bf16(g1)
-            else:
+            else:       # fp32 path, or the bf16 kernel that reads the column block MN-major (D = 256 / 512)
                 g0T = g1T = None
             with _Prof("infonce_bwd"):
                 check(lib.dmf_infonce_bwd(ptr(a0), a0.stride(0), Bl, ptr(lse[c, 0]), ptr(g1), g1.stride(0), ptr(g1T),

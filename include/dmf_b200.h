@@ -150,7 +150,9 @@ int dmf_infonce_bwd(const void* A, long long lda, int Ma, const float* lseA,
                     const void* Bm, long long ldb, const void* BmT, long long ldbt, int Nb, const float* lseB, int D,
                     float scale, float coef, const float* gscale, long long diag_offset,
                     float* dA, long long ldda, int accumulate, int dtype, dmf_stream_t s);
-/* BmT: the bf16 path also needs the transposed column block [D, Nb] (dmf_transpose_bf16); NULL for fp32 */
+/* BmT: the transposed column block [D, Nb] (dmf_transpose_bf16).  NULL for fp32, and for the bf16 path whenever
+ * dmf_infonce_bwd_needs_transposed(D) returns 0 (D = 256 / 512: the kernel reads Bm as an MN-major operand). */
+int dmf_infonce_bwd_needs_transposed(int D);
 
 /* ------------------------------------------------------------------ K4 ortho Gram pieces
  * ortho_loss (models/losses.py:104-110) = || normalize(z1)^T normalize(zs) ||_F.

@@ -239,6 +239,175 @@ def gpu_eager_context(dev, B):
 
 
 # ------------------------------------------------------------------------------------------------
+# BASELINE.json configs C1-C4 (small, launch-bound shapes): samples/s + launches/step beside the CPU port at the SAME batch
+# ------------------------------------------------------------------------------------------------
+SMALL = {
+    "c1": dict(workload="C1 HandWritten-shape DMVAE (6 views, h=512, e=200, a=1e-5, B=100) + evidential probe (V=7, C=10, hidden 128, cml)",
+               dims=[240, 76, 216, 47, 64, 6], e=200, B=100, C=10, head="probe", agg="cml", fused=1),
+    "c2": dict(workload="C2 run_synthetic DMVAE (2 views x 32-d, h=512, e=16, B=4096) + evidential probe (V=3, C=3, fused=0)",
+               dims=[32, 32], e=16, B=4096, C=3, head="probe", agg="cml", fused=0),
+    "c3": dict(workload="C3 CUB-shape (GoogLeNet 1024-d + doc2vec 300-d, C=10, B=100): DMVAE step + LateFusion with "
+                        "discounted-belief (Dempster-Shafer conflict) fusion",
+               dims=[1024, 300], e=200, B=100, C=10, head="latefusion", agg="dbf", fused=1),
+    "c4": dict(workload="C4 LUMA-shape evidential fusion only: evidences [B=64, V=4, C=42] -> fused evidence + AvgTrustedLoss + gradient",
+               dims=None, e=0, B=64, C=42, V=4, head="edl", agg="cml", fused=1),
+}
+
+
+def run_small_config(args):
+    import disentagled_multimodal_fusion_b200 as pkg
+    from disentagled_multimodal_fusion_b200 import ops, _lib
+    from disentagled_multimodal_fusion_b200.dp import FlatParams
+    from oracle import port        # CPU baseline leg only (timed beside, never on the product path)
+    cfg = SMALL[args.config]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    _lib.require_device()
+    B, C = cfg["B"], cfg["C"]
+    g = torch.Generator().manual_seed(1234)
+    y = torch.randint(0, C, (B,), generator=g)
+    K, W = max(args.steps, 20), max(args.warmup, 3)
+
+    if cfg["head"] == "edl":
+        V = cfg["V"]
+        evid_h = torch.exp(torch.clamp(torch.randn(B, V, C, generator=g) * 2, -10, 10))
+        evid = evid_h.to(dev).requires_grad_()
+        yd = y.to(dev)
+
+        def gstep():
+            evid.grad = None
+            loss, fe, _ = ops.edl_fused_loss(evid, yd, cfg["agg"], 5, 50, fused=cfg["fused"])
+            loss.backward()
+            return loss
+        ev_c = evid_h.clone().requires_grad_()
+
+        def cstep():
+            ev_c.grad = None
+            loss = port.avg_trusted_loss(ev_c, y, port.fuse(ev_c, cfg["agg"]), cfg["fused"], 5, 50)
+            loss.backward()
+            return loss
+        h2d = evid_h.numel() * 4 + B * 8
+        host_in, dev_in = [evid_h.pin_memory(), y.pin_memory()], None
+    else:
+        dims, e = cfg["dims"], cfg["e"]
+        xs_h = [torch.rand(B, d, generator=g) for d in dims]
+        torch.manual_seed(0)
+        model = pkg.DMVAE(output_dim=dims, a=1e-5, hidden_dim=512, embed_dim=e).to(dev)
+        if cfg["head"] == "probe":
+            head = pkg.EvidentialProbeModule(model, num_classes=C, input_dim=e, hidden_dim=(128,), dropout=0.0,
+                                             annealing_start=50, aggregation=cfg["agg"], fused=cfg["fused"]).to(dev)
+            head.backbone = model
+            hparams = [p for n, p in head.named_parameters() if not n.startswith("backbone.")]
+        else:
+            head = pkg.LateFusion([(pkg.IdentityEncoder, {}) for _ in dims], dims, C, dropout=0.0, aggregation=cfg["agg"],
+                                  annealing_start=50, hidden_dim=(128,), fused=cfg["fused"]).to(dev)
+            hparams = list(head.parameters())
+        head.criterion.annealing_step = 5
+        bb, hd = FlatParams(model.parameters()), FlatParams(hparams)
+        xs, yd = [x.to(dev) for x in xs_h], y.to(dev)
+
+        def gstep(inp=None):
+            xin = xs if inp is None else inp[:-1]
+            yin = yd if inp is None else inp[-1]
+            loss, _ = model(xin)
+            bb.zero_grad()
+            loss.backward()
+            bb.adam_step(1e-4)
+            pl = head.shared_step([*xin, yin])[0]
+            hd.zero_grad()
+            pl.backward()
+            hd.adam_step(3e-3, weight_decay=1e-4, decoupled=True)
+            return loss.detach() + pl.detach()
+        # CPU port of the same step at the same batch
+        gp = torch.Generator().manual_seed(0)
+        enc = [port.xavier_mlp_params((d, 512, 512), 4 * e, gp) for d in dims]
+        dec = [port.xavier_mlp_params((2 * e, 512, 512), d, gp) for d in dims]
+        if cfg["head"] == "probe":
+            heads = [port.xavier_mlp_params((e, 128), C, gp) for _ in range(len(dims) + 1)]
+        else:
+            heads = [port.xavier_mlp_params((d, 128), C, gp) for d in dims]
+        opt_b = torch.optim.Adam([t for ws, bs in enc + dec for t in ws + bs], lr=1e-4)
+        opt_h = torch.optim.AdamW([t for ws, bs in heads for t in ws + bs], lr=3e-3, weight_decay=1e-4)
+
+        def cstep():
+            noise = [torch.randn(B, e) for _ in range(2 * len(dims) + 1)]
+            loss, _ = port.dmvae_forward(xs_h, enc, dec, noise, 1e-5)
+            opt_b.zero_grad(set_to_none=True)
+            loss.backward()
+            opt_b.step()
+            if cfg["head"] == "probe":
+                with torch.no_grad():
+                    mu, mups = port.dmvae_get_embedding(xs_h, enc)
+                emb = [mu] + mups
+            else:
+                emb = xs_h
+            l2 = port.probe_shared_step(emb, heads, y, cfg["agg"], cfg["fused"], 5, 50)[0]
+            opt_h.zero_grad(set_to_none=True)
+            l2.backward()
+            opt_h.step()
+            return loss
+        h2d = sum(x.numel() * 4 for x in xs_h) + B * 8
+        host_in = [x.pin_memory() for x in xs_h] + [y.pin_memory()]
+        dev_in = [torch.empty_like(x, device=dev) for x in host_in]
+
+    for _ in range(W):
+        gstep()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    gstep()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = _timeit(gstep, K, 0)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # end to end: pinned host batch -> device every step, loss read back on the host every step
+    def e2e_step():
+        if dev_in is not None:
+            for d, h in zip(dev_in, host_in):
+                d.copy_(h, non_blocking=True)
+            out = gstep(dev_in)
+        else:
+            evid.data.copy_(host_in[0], non_blocking=True)
+            out = gstep()
+        return float(out)
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / K
+
+    cores = host_threads()
+    torch.set_float32_matmul_precision("highest")
+    for _ in range(2):
+        cstep()
+    t0 = time.perf_counter()
+    nc = 0
+    while nc < 5 or (time.perf_counter() - t0 < 5.0 and nc < 200):
+        cstep()
+        nc += 1
+    cdt = (time.perf_counter() - t0) / nc
+    line = {
+        "metric": METRIC, "value": B / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "global_batch": B, "launch": "eager", "note": "launch-bound shape: "
+                   "report samples/s and launches/step, not a roofline fraction (SURVEY 8d)"},
+        "clocks": sampler.summary(),
+        "e2e": {"value": B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches) * K, "gpu_launches_per_step": int(launches),
+        "roofline": None,
+        "cpu_baseline": {"value": B / cdt, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": cdt * 1e3,
+                         "sample": f"{nc} full steps of the oracle port at the same batch {B}"},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args, rank, world, local_rank):
@@ -611,6 +780,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c5", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="BASELINE.json config: c5 (default) = the headline workload; c1-c4 = the small launch-bound configs "
+                         "(single GPU; samples/s + launches/step beside the CPU port at the same batch)")
     ap.add_argument("--no-kernel-rooflines", action="store_true", help="skip the live K1 / K3 roofline measurements")
     ap.add_argument("--no-loss-check", dest="loss_check", action="store_false",
                     help="skip the cross-N loss / gradient-norm check step")
@@ -622,6 +794,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.config != "c5":
+        if rank == 0:
+            run_small_config(args)
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

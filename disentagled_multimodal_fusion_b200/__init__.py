@@ -12,6 +12,7 @@ from .disentangledssl import DisentangledSSL  # noqa: F401
 from .dmvae import DMVAE  # noqa: F401
 from .evidential_probe import DisentangledEvidentialProbeModule, EvidentialProbeModule  # noqa: F401
 from .losses import AvgTrustedLoss, SupConLoss, ortho_loss  # noqa: F401
+from .optim import FusedAdam, FusedAdamW  # noqa: F401
 from . import analysis  # noqa: F401
 
 __version__ = "0.1.0"

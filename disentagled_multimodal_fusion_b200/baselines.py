@@ -8,6 +8,7 @@ from torch import nn
 from .classifiers import EvidentialNN, grouped_forward
 from .evidential_probe import _ProbeBase
 from .losses import AvgTrustedLoss
+from .optim import make_optimizer
 from .utils import discounted_belief_fusion, get_avg_fusion, get_cml_fusion
 
 
@@ -44,6 +45,6 @@ class LateFusion(_ProbeBase):
         self.criterion.annealing_step += 1
 
     def configure_optimizers(self):
-        optimizer = self.optimizer(self.parameters(), lr=self.lr)
+        optimizer = make_optimizer(self.optimizer, self.parameters(), lr=self.lr)
         scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode='min', factor=0.1, patience=10)
         return {'optimizer': optimizer, 'lr_scheduler': scheduler, 'monitor': 'val_loss'}

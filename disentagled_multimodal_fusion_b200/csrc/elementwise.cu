@@ -351,33 +351,44 @@ __global__ void __launch_bounds__(256) augment_kernel(const float* __restrict__ 
     }
     // columns k >= D carry the maximum key; they are only counted when mid = 2^32 - 1, which the bisection never
     // needs unless n_drop > D
+    // Bisection on the key value, stopped as soon as EXACTLY n_drop keys lie at or below the probe: any threshold
+    // between the n_drop-th and the next key will do, and that gap is ~2^32 / D wide -- log2(D) + 2 probes on
+    // average instead of 32.  Only a tie at the threshold (probability ~ D^2 / 2^32) runs the bisection to the end.
     unsigned lo = 0u, hi = 0xFFFFFFFFu;
+    bool exact = false;
     while (lo < hi) {
       const unsigned mid = lo + ((hi - lo) >> 1);
       int cnt = 0;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) cnt += (key[i] <= mid && lane + 32 * i < D) ? 1 : 0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      if (cnt >= n_drop) hi = mid; else lo = mid + 1u;
+      for (int i = 0; i < 32; ++i) cnt += key[i] <= mid ? 1 : 0;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt == n_drop) { lo = mid; exact = true; break; }
+      if (cnt > n_drop) hi = mid; else lo = mid + 1u;
     }
-    int below = 0;
+    if (exact) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) below += (key[i] < lo && lane + 32 * i < D) ? 1 : 0;
+      for (int i = 0; i < 32; ++i) {
+        const int k = lane + 32 * i;
+        if (k < D) y[k] = key[i] <= lo ? 0.f : xv[i];
+      }
+    } else {
+      int below = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
-    int ties_left = n_drop - below;
+      for (int i = 0; i < 32; ++i) below += (key[i] < lo && lane + 32 * i < D) ? 1 : 0;
+      below = __reduce_add_sync(0xffffffffu, below);
+      int ties_left = n_drop - below;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int k = lane + 32 * i;
-      if (32 * i < D) {                                   // warp-uniform
-        const bool tie = k < D && key[i] == lo;
-        const unsigned tm = __ballot_sync(0xffffffffu, tie);
-        const int rank_in = __popc(tm & ((1u << lane) - 1u));
-        const bool drop = k < D && (key[i] < lo || (tie && rank_in < ties_left));
-        if (k < D) y[k] = drop ? 0.f : xv[i];
-        ties_left -= __popc(tm);
-        if (ties_left < 0) ties_left = 0;
+      for (int i = 0; i < 32; ++i) {
+        const int k = lane + 32 * i;
+        if (32 * i < D) {                                   // warp-uniform
+          const bool tie = k < D && key[i] == lo;
+          const unsigned tm = __ballot_sync(0xffffffffu, tie);
+          const int rank_in = __popc(tm & ((1u << lane) - 1u));
+          const bool drop = k < D && (key[i] < lo || (tie && rank_in < ties_left));
+          if (k < D) y[k] = drop ? 0.f : xv[i];
+          ties_left -= __popc(tm);
+          if (ties_left < 0) ties_left = 0;
+        }
       }
     }
   } else if (t == 1 && n_drop > 0) {

@@ -214,7 +214,8 @@ class DeviceLoader:
     batch.  Shuffling is distribution-equal to ``DataLoader(shuffle=True)``, not stream-equal."""
 
     def __init__(self, views: Sequence, labels, batch_size: int, device="cuda", indices: Optional[Sequence[int]] = None,
-                 shuffle: bool = False, drop_last: bool = False, seed: int = 0, rank: int = 0, world_size: int = 1):
+                 shuffle: bool = False, drop_last: bool = False, seed: int = 0, rank: Optional[int] = None,
+                 world_size: Optional[int] = None):
         dev = torch.device(device)
         as_t = lambda a, dt: torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).to(dt)   # noqa: E731
         self.views: List[torch.Tensor] = [as_t(v, torch.float32).to(dev).contiguous() for v in views]
@@ -222,6 +223,11 @@ class DeviceLoader:
         n = self.labels.shape[0]
         self.index = torch.arange(n, device=dev) if indices is None else as_t(indices, torch.int64).to(dev)
         self.batch_size, self.shuffle, self.drop_last = int(batch_size), shuffle, drop_last
+        if rank is None or world_size is None:      # default: the torch.distributed process group, if there is one
+            from .dp import world as _world
+            r, w = _world()
+            rank = r if rank is None else rank
+            world_size = w if world_size is None else world_size
         self.rank, self.world_size = rank, world_size
         self.gen = torch.Generator(device=dev)
         self.gen.manual_seed(seed)

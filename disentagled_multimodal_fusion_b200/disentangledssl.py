@@ -15,6 +15,7 @@ from ._lib import require_device
 from .classifiers import IdentityEncoder, Linear, grouped_forward
 from .lightning import LightningModule
 from .losses import SupConLoss
+from .optim import make_optimizer
 from .utils import ExponentialScheduler, augment_data, draw_vmf_noise
 
 
@@ -250,7 +251,7 @@ class DisentangledSSL(LightningModule):
         return x1, x2, v1, v2
 
     def configure_optimizers(self):
-        optimizer = self.optimizer(self.parameters(), lr=self.lr)
+        optimizer = make_optimizer(self.optimizer, self.parameters(), lr=self.lr)   # Adam -> fused flat-buffer Adam on CUDA
         scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=self.num_epochs, eta_min=0, last_epoch=-1)
         return {'optimizer': optimizer,
                 'lr_scheduler': {'scheduler': scheduler, 'interval': 'epoch', 'monitor': 'train_loss'}}

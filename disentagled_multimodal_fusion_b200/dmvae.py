@@ -15,6 +15,7 @@ from . import dp, ops
 from ._lib import lib, check, ptr, stream, ptr_array, require_device
 from .classifiers import IdentityEncoder, Linear, grouped_forward
 from .lightning import LightningModule
+from .optim import make_optimizer
 
 
 class DMVAE(LightningModule):
@@ -124,6 +125,6 @@ class DMVAE(LightningModule):
         return loss
 
     def configure_optimizers(self):
-        opt = self.optimizer_cls(self.parameters(), lr=self.lr)
+        opt = make_optimizer(self.optimizer_cls, self.parameters(), lr=self.lr)   # Adam -> fused flat-buffer Adam on CUDA
         sch = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=self.num_epochs, eta_min=0, last_epoch=-1)
         return {'optimizer': opt, 'lr_scheduler': {'scheduler': sch, 'interval': 'epoch', 'monitor': 'train/loss'}}

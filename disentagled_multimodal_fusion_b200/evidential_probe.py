@@ -13,6 +13,7 @@ from . import dp, ops
 from .classifiers import EvidentialNN, grouped_forward
 from .lightning import Accuracy, LightningModule
 from .losses import AvgTrustedLoss
+from .optim import make_optimizer
 from .utils import get_avg_fusion, get_cml_fusion, get_disentangled_fusion, get_joint_fusion
 
 
@@ -158,7 +159,8 @@ class EvidentialProbeModule(_ProbeBase):
         return self._fused_step(self(batch), batch[-1], fused=self.fused)
 
     def configure_optimizers(self):
-        optimizer = torch.optim.AdamW(self.parameters(), lr=self.lr, weight_decay=1e-4)
+        # trainable parameters only (the frozen backbone copy stays out of the flat buffer); AdamW -> fused AdamW on CUDA
+        optimizer = make_optimizer(torch.optim.AdamW, [p for p in self.parameters() if p.requires_grad], lr=self.lr, weight_decay=1e-4)
         scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=self.trainer.max_epochs, eta_min=1e-6)
         return {'optimizer': optimizer, 'lr_scheduler': scheduler, 'monitor': 'val_loss'}
 
@@ -203,6 +205,6 @@ class DisentangledEvidentialProbeModule(_ProbeBase):
         return self._fused_step(self(x), x[-1], fused=1)
 
     def configure_optimizers(self):
-        optimizer = self.optimizer(self.parameters(), lr=self.lr)
+        optimizer = make_optimizer(self.optimizer, [p for p in self.parameters() if p.requires_grad], lr=self.lr)
         scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode='min', factor=0.1, patience=5)
         return {'optimizer': optimizer, 'lr_scheduler': scheduler, 'monitor': 'val_loss'}

@@ -84,6 +84,7 @@ except Exception:  # noqa: BLE001
             self.logger = logger
             self.model: Optional[LightningModule] = None
             self.callback_metrics: Dict[str, Any] = {}
+            self.last_lr: Optional[float] = None
             self.device = torch.device("cuda", torch.cuda.current_device()) if (
                 accelerator in ("auto", "gpu", "cuda") and torch.cuda.is_available()) else torch.device("cpu")
 
@@ -127,6 +128,7 @@ except Exception:  # noqa: BLE001
                             sched.step(float(m))
                     else:
                         sched.step()
+                self.last_lr = float(opt.param_groups[0]["lr"])
             return self
 
         @torch.no_grad()

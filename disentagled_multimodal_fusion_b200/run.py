@@ -23,6 +23,16 @@ CFG_PATH = Path(os.environ.get("DMF_CONFIG", Path(__file__).resolve().parent.par
 cfg = yaml.safe_load(open(CFG_PATH)) if CFG_PATH.is_file() else {}
 
 
+def load_config(path):
+    """(Re)load the YAML the dot-path getter ``C`` reads -- e.g. one of the reference's own ``configs/*.yaml``, which
+    parse unchanged (including the pasted-text quirk of synthetic_config.yaml that turns its ``data`` block into a
+    top-level ``yamldata`` key, so that every ``C('data.common_med.*')`` falls back to its in-code default)."""
+    global cfg, CFG_PATH
+    CFG_PATH = Path(path)
+    cfg = yaml.safe_load(open(CFG_PATH)) or {}
+    return cfg
+
+
 def C(path, default=None):
     """Dot-path getter with default: ``C('probes.dropout_p', 0.1)``."""
     cur = cfg

@@ -380,7 +380,66 @@ def gen_datasets():
     save("datasets", **rows)
 
 
+# ----------------------------------------------------------------------------------------
+# 11. DMVAE at the BASELINE.json sizes (C1 HandWritten h=512 e=200 B=100 on real rows, C3 CUB 1024/300, C2 synthetic
+#     B=4096).  The weights are NOT stored (C1 alone has 9.4 M parameters): the CUDA mirror's initialisation is
+#     seed-equal to the reference's (tests/test_cpu_host.py::test_dmvae_init_stream_and_keys), so the fixture keeps the
+#     seed, the inputs, the explicit noise, the outputs and -- per parameter -- the gradient norm plus 64 sampled
+#     entries at fixed indices.                                          models/dmvae.py:128-188, run.py:179-208
+# ----------------------------------------------------------------------------------------
+def grad_samples(n, k=64):
+    g = np.random.RandomState(n % (2 ** 31 - 1))
+    return np.sort(g.choice(n, size=min(k, n), replace=False)).astype(np.int64)
+
+
+def gen_dmvae_full():
+    with in_reference_cwd():
+        hw = ns.dataset.HandWritten()
+        cub = ns.dataset.CUB()
+    syn = ns.dataset.SimpleTwoModalPlus(n_samples=10000, n_classes=3, d_signal=16, d_spurious=16, rho=0.5,
+                                         shared_class_frac=0.5, seed=0)
+
+    def rows_of(ds, idx):
+        return [torch.from_numpy(np.stack([ds[i][v] for i in idx])).float() for v in range(ds.num_views)]
+    cases = {
+        "c1_hw": (rows_of(hw, np.arange(0, 2000, 20)[:100]), 512, 200, 1e-5),
+        "c3_cub": (rows_of(cub, np.arange(0, 600, 6)[:100]), 512, 200, 1e-5),
+        "c2_syn": ([syn.X1[:4096].float(), syn.X2[:4096].float()], 512, 16, 1e-5),
+    }
+    for tag, (xs, h, e, a) in cases.items():
+        dims = [int(x.shape[1]) for x in xs]
+        B = xs[0].shape[0]
+        torch.manual_seed(3)
+        m = ns.dmvae.DMVAE(output_dim=dims, a=a, hidden_dim=h, embed_dim=e)
+        torch.manual_seed(99)
+        with _RecordRandnLike() as rr:
+            loss, logs = m(xs)
+        loss.backward()
+        out = {f"x{i}": x for i, x in enumerate(xs)}
+        out.update({f"noise{i}": n for i, n in enumerate(rr.rec)})
+        out["loss"] = loss
+        for k in ("loss_joint_recon", "loss_cross_recon", "kl_private", "kl_shared_poe", "kl_shared_uni_sum"):
+            out["log." + k] = np.float32(logs[k])
+        for k, p_ in m.named_parameters():
+            gflat = p_.grad.reshape(-1)
+            idx = grad_samples(gflat.numel())
+            out["gnorm." + k] = np.float64(gflat.double().norm())
+            out["gidx." + k] = idx
+            out["gval." + k] = gflat[torch.from_numpy(idx)]
+            out["wsum." + k] = np.float64(p_.detach().double().sum())     # pins the seed-regenerated weights
+        mu_poe, mu_p = m.get_embedding(xs)
+        out["emb_shared"] = mu_poe
+        out.update({f"emb_private{i}": t for i, t in enumerate(mu_p)})
+        out["meta"] = np.array([h, e, B, 3], dtype=np.int64)              # last = init seed
+        out["dims"] = np.array(dims, dtype=np.int64)
+        out["a"] = np.float64(a)
+        save("dmvae_full_" + tag, **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "full":
+        gen_dmvae_full()
+        sys.exit(0)
     gen_activation()
     gen_edl()
     gen_supcon()
@@ -391,3 +450,4 @@ if __name__ == "__main__":
     gen_vmf()
     gen_eval()
     gen_datasets()
+    gen_dmvae_full()

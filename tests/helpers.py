@@ -41,3 +41,15 @@ def mlp_params_from_sd(sd, prefix, idxs, device="cpu", grad=False):
     ws = [T(sd[f"{prefix}.layers.{i}.weight"], device, grad) for i in idxs]
     bs = [T(sd[f"{prefix}.layers.{i}.bias"], device, grad) for i in idxs]
     return ws, bs
+
+
+def check_sampled_grads(named_grads, g, tol):
+    """fixtures at the BASELINE sizes keep, per parameter, the gradient norm and 64 sampled entries"""
+    for k, gr in named_grads.items():
+        flat = gr.reshape(-1)
+        ref_norm = float(g["gnorm." + k])
+        assert abs(float(flat.double().norm()) - ref_norm) <= tol * max(ref_norm, 1e-12), ("gnorm", k)
+        idx = torch.from_numpy(g["gidx." + k]).to(flat.device)
+        ref = T(g["gval." + k], flat.device)
+        scale = max(float(ref.abs().max()), ref_norm / max(flat.numel(), 1) ** 0.5, 1e-20)
+        assert float((flat[idx] - ref).abs().max()) <= 4 * tol * scale, ("gval", k)

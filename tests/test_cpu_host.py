@@ -257,6 +257,30 @@ def test_device_loader_contract_cpu():
     assert [len(t) for t in one] == [5, 5, 5, 5]          # a 1-row tail cannot be sharded over 2 ranks: skipped
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/configs"), reason="reference tree not present (GPU box)")
+def test_reference_configs_load_unchanged():
+    """The reference's own configs/*.yaml parse unchanged through run.load_config / run.C, including
+    quirk D6: configs/synthetic_config.yaml:7-8 holds pasted chat text, so its generator presets sit under a top-level
+    ``yamldata`` key and every C('data.common_med.*') falls back to the in-code default."""
+    from disentagled_multimodal_fusion_b200 import run
+    keep = run.CFG_PATH
+    try:
+        cfg = run.load_config("/root/reference/configs/config.yaml")
+        assert run.C("dataloader.batch_size") == 100 and run.C("dmvae.embed_dim") == 200 and run.C("dmvae.hidden_dim") == 512
+        assert run.C("optim.dataset_lr.Scene") == 0.01 and run.C("probes.model_hidden_dim") == [128]
+        assert run.C("data.conflict.ratio_conflict") == 1.0 and run.C("dmvae.a") == 1e-5
+        assert set(cfg) >= {"experiment", "dataloader", "data", "optim", "dmvae", "probes", "trainer"}
+        cfg = run.load_config("/root/reference/configs/synthetic_config.yaml")
+        assert "yamldata" in cfg and "data" not in cfg                       # quirk D6
+        assert run.C("data.common_med.n_samples", 123) == 123                # -> in-code default
+        assert run.C("yamldata.common_med.n_samples") == 10000
+        assert run.C("dmvae.embed_dim") == 16 and run.C("dmvae.output_dim") == [32, 32]
+        for name in ("luma_config.yaml", "luma_compile_config.yaml"):
+            assert isinstance(run.load_config("/root/reference/configs/" + name), dict)
+    finally:
+        run.load_config(keep)
+
+
 def test_run_helpers():
     """run.C dot-path getter with defaults, _get_dataset error behaviour, build_factories wiring (run.py:29-50,135-175)."""
     from disentagled_multimodal_fusion_b200 import run

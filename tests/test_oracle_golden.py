@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import port
-from tests.helpers import T, assert_close, load_golden, mlp_params_from_sd
+from tests.helpers import T, assert_close, check_sampled_grads, load_golden, mlp_params_from_sd
 
 torch.set_num_threads(1)
 TOL = 2e-6
@@ -94,6 +94,49 @@ def test_dmvae(tag):
     assert_close(mu, g["emb_shared"], TOL, "emb_shared")
     for i in range(N):
         assert_close(mups[i], g[f"emb_private{i}"], TOL, "emb_private")
+
+
+@pytest.mark.parametrize("tag", ["c1_hw", "c3_cub", "c2_syn"])
+def test_dmvae_full_size(tag):
+    """DMVAE at the BASELINE.json sizes (C1 HandWritten rows h=512 e=200 B=100; C3 CUB 1024/300; C2 synthetic B=4096).
+    The weights are regenerated from the init seed (the mirror's init stream is seed-equal to the reference's) and
+    pinned through their per-tensor sums."""
+    import disentagled_multimodal_fusion_b200 as pkg
+    g = load_golden("dmvae_full_" + tag)
+    h, e, B, seed = (int(v) for v in g["meta"])
+    dims = [int(d) for d in g["dims"]]
+    N = len(dims)
+    torch.manual_seed(seed)
+    m = pkg.DMVAE(output_dim=dims, a=float(g["a"]), hidden_dim=h, embed_dim=e)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    for k, v in m.named_parameters():
+        assert abs(float(v.detach().double().sum()) - float(g["wsum." + k])) < 1e-9 * max(1.0, abs(float(g["wsum." + k]))) + 1e-9, k
+    torch.set_num_threads(max(1, min(8, torch.get_num_threads() if torch.get_num_threads() > 1 else 8)))
+    try:
+        enc = [mlp_params_from_sd(sd, f"encoders.{i}", (0, 2, 4), grad=True) for i in range(N)]
+        dec = [mlp_params_from_sd(sd, f"decoders.{i}", (0, 2, 4), grad=True) for i in range(N)]
+        xs = [T(g[f"x{i}"]) for i in range(N)]
+        noise = [T(g[f"noise{i}"]) for i in range(2 * N + 1)]
+        loss, logs = port.dmvae_forward(xs, enc, dec, noise, float(g["a"]))
+        assert_close(loss, g["loss"], 1e-5, "loss")
+        for k in ("loss_joint_recon", "loss_cross_recon", "kl_private", "kl_shared_poe", "kl_shared_uni_sum"):
+            assert_close(logs[k], g["log." + k], 1e-5, k)
+        loss.backward()
+        grads = {}
+        for i in range(N):
+            for li, idx in enumerate((0, 2, 4)):
+                grads[f"encoders.{i}.layers.{idx}.weight"] = enc[i][0][li].grad
+                grads[f"encoders.{i}.layers.{idx}.bias"] = enc[i][1][li].grad
+                grads[f"decoders.{i}.layers.{idx}.weight"] = dec[i][0][li].grad
+                grads[f"decoders.{i}.layers.{idx}.bias"] = dec[i][1][li].grad
+        check_sampled_grads(grads, g, 2e-5)
+        with torch.no_grad():
+            mu, mups = port.dmvae_get_embedding(xs, enc)
+        assert_close(mu, g["emb_shared"], 1e-5, "emb_shared")
+        for i in range(N):
+            assert_close(mups[i], g[f"emb_private{i}"], 1e-5, "emb_private")
+    finally:
+        torch.set_num_threads(1)
 
 
 @pytest.mark.parametrize("tag", ["small", "wide"])

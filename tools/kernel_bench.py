@@ -64,6 +64,18 @@ def main():
                                               scale, scale / (2 * B), ptr(one), 0, ptr(dz), D, 0, 1, stream()))
         ms = timeit(g)
         print(f"infonce_bwd_tc B={B} D={D}: {ms:.3f} ms  algorithmic {2*B*B*D/ms/1e9:.1f} TFLOP/s, executed {(D//128)*(2*B*B*D + 2*B*B*128)/ms/1e9:.1f} TFLOP/s")
+    if a.what in ("all", "aug"):
+        x = torch.randn(B, 1024, device=dev)
+        y = torch.empty_like(x)
+        ms = timeit(lambda: ops.augment(x, 7, 0, out=y))
+        print(f"augment B={B} D=1024: {ms:.3f} ms  {2 * x.numel() * 4 / ms / 1e6:.1f} GB/s")
+        w = torch.empty(B, 1, device=dev); v = torch.empty(B, D - 1, device=dev)
+        ms = timeit(lambda: ops.vmf_draw(B, D, 1.0, 11, 0, dev, out=(w, v)))
+        print(f"vmf_draw B={B} D={D}: {ms:.3f} ms  {v.numel() * 4 / ms / 1e6:.1f} GB/s")
+        xs = torch.randn(2 * B, 1024, device=dev)
+        buf = torch.empty(2 * B, 1536, dtype=torch.bfloat16, device=dev); bufT = torch.empty(1536, 2 * B, dtype=torch.bfloat16, device=dev)
+        ms = timeit(lambda: ops.cast_dual_bf16(xs, buf, 1536, bufT, 2 * B))
+        print(f"cast_dual [{2*B},1024]: {ms:.3f} ms  {xs.numel() * 8 / ms / 1e6:.1f} GB/s")
     if a.what in ("all", "gemm"):
         M = 2 * B
         for (K, N) in ((1024, 512), (512, 512), (1536, 512)):

@@ -44,33 +44,46 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): ONE background
+    `nvidia-smi -lms 200` process whose output is parsed at the end (no periodic fork from the timing process)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        super().__init__(daemon=True)
         self.index = index
+        self.proc = None
+        self.samples, self.reasons, self.sm_max = [], set(), None
         self.stop_flag = False
-        self.samples = []
-        self.reasons = set()
-        self.sm_max = None
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def join(self, timeout=None):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=timeout or 5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+            out = ""
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.sm_max = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower() == "active":
-                        self.reasons.add(n)
-            except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.1)
+                self.samples.append(float(f[0]))
+                self.sm_max = float(f[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(self.NAMES, f[2:]):
+                if v.lower() == "active":
+                    self.reasons.add(n)
 
     def summary(self):
         s = sorted(self.samples)
@@ -306,17 +319,17 @@ def run_small_config(args):
         bb, hd = FlatParams(model.parameters()), FlatParams(hparams)
         xs, yd = [x.to(dev) for x in xs_h], y.to(dev)
 
-        def gstep(inp=None):
+        def gstep(inp=None, capturable=False):
             xin = xs if inp is None else inp[:-1]
             yin = yd if inp is None else inp[-1]
             loss, _ = model(xin)
             bb.zero_grad()
             loss.backward()
-            bb.adam_step(1e-4)
+            bb.adam_step(1e-4, capturable=capturable)
             pl = head.shared_step([*xin, yin])[0]
             hd.zero_grad()
             pl.backward()
-            hd.adam_step(3e-3, weight_decay=1e-4, decoupled=True)
+            hd.adam_step(3e-3, weight_decay=1e-4, decoupled=True, capturable=capturable)
             return loss.detach() + pl.detach()
         # CPU port of the same step at the same batch
         gp = torch.Generator().manual_seed(0)
@@ -348,7 +361,7 @@ def run_small_config(args):
             return loss
         h2d = sum(x.numel() * 4 for x in xs_h) + B * 8
         host_in = [x.pin_memory() for x in xs_h] + [y.pin_memory()]
-        dev_in = [torch.empty_like(x, device=dev) for x in host_in]
+        dev_in = [x.to(dev) for x in host_in]
 
     for _ in range(W):
         gstep()
@@ -357,18 +370,34 @@ def run_small_config(args):
     gstep()
     torch.cuda.synchronize()
     launches = _lib.launch_count() - l0
+    ms_eager = _timeit(gstep, K, 0)
+    # the same step as ONE CUDA graph (forward, backward, fused optimizers; torch's graph-safe Philox state feeds the
+    # reparameterisation noise): these shapes are launch-bound, the graph removes the host from the loop
+    launch_mode, replay = "eager", gstep
+    if args.graph != "off" and cfg["head"] != "edl":
+        try:
+            from disentagled_multimodal_fusion_b200.dp import GraphedStep
+            graphed = GraphedStep(lambda: gstep(dev_in, capturable=True), warmup=2, stream=torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            replay, launch_mode = graphed, "cuda_graph"
+        except Exception as ex:  # noqa: BLE001
+            if args.graph == "on":
+                raise
+            launch_mode = f"eager (graph capture failed: {type(ex).__name__})"
+            torch.cuda.synchronize()
+    for _ in range(3):
+        replay()
     sampler = ClockSampler(0)
     sampler.start()
-    ms = _timeit(gstep, K, 0)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    ms = _timeit(replay, K, 0)
+    sampler.join(timeout=3)
 
     # end to end: pinned host batch -> device every step, loss read back on the host every step
     def e2e_step():
         if dev_in is not None:
             for d, h in zip(dev_in, host_in):
                 d.copy_(h, non_blocking=True)
-            out = gstep(dev_in)
+            out = replay() if launch_mode == "cuda_graph" else gstep(dev_in)
         else:
             evid.data.copy_(host_in[0], non_blocking=True)
             out = gstep()
@@ -395,8 +424,9 @@ def run_small_config(args):
     line = {
         "metric": METRIC, "value": B / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "global_batch": B, "launch": "eager", "note": "launch-bound shape: "
+        "config": {"workload": cfg["workload"], "global_batch": B, "launch": launch_mode, "note": "launch-bound shape: "
                    "report samples/s and launches/step, not a roofline fraction (SURVEY 8d)"},
+        "eager_ms_per_step": ms_eager,
         "clocks": sampler.summary(),
         "e2e": {"value": B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches) * K, "gpu_launches_per_step": int(launches),
@@ -615,8 +645,7 @@ def run_gpu(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms = timed(args.steps, run_value)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.join(timeout=3)
     value = Bg * args.steps / (ms / 1e3)
     # per-phase device time of the LAST timed replay (event nodes inside the graph), max over ranks
     phases = None
@@ -797,7 +826,9 @@ def main():
         return
     if args.config != "c5":
         if rank == 0:
-            run_small_config(args)
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(torch.cuda.Stream(device=0)):      # see dp.GraphedStep: capture needs a non-default stream
+                run_small_config(args)
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

@@ -38,8 +38,9 @@ class DisentangledSSL(LightningModule):
                  ortho_norm=True, condzs=True, usezsx=False, initialization='xavier', epochs=50,
                  precision="fp32", noise_mode="reference"):
         super().__init__()
-        if distribution != 'vmf' or not condzs or usezsx:
-            raise NotImplementedError("hot path covers the reference defaults: distribution='vmf', condzs=True, usezsx=False")
+        if distribution not in ('vmf', 'normal'):
+            raise ValueError(f"distribution must be 'vmf' or 'normal', got {distribution!r}")
+        self.distribution = distribution
         self.optimizer = optimizer
         self.num_epochs = epochs
         x1_dim, x2_dim = int(output_dim[0]), int(output_dim[1])
@@ -69,8 +70,9 @@ class DisentangledSSL(LightningModule):
         self.encoder_x2s = mk(x2_dim)
         self.phead1 = ProbabilisticEncoder(nn.Identity(), distribution=distribution, vmfkappa=vmfkappa)
         self.phead2 = ProbabilisticEncoder(nn.Identity(), distribution=distribution, vmfkappa=vmfkappa)
-        self.encoder_x1 = mk(x1_dim + embed_dim)
-        self.encoder_x2 = mk(x2_dim + embed_dim)
+        # models/disentangledssl.py:57-62: the private encoders are conditioned on the shared code unless condzs=False
+        self.encoder_x1 = mk(x1_dim + embed_dim if condzs else x1_dim)
+        self.encoder_x2 = mk(x2_dim + embed_dim if condzs else x2_dim)
         self.critic = SupConLoss(precision=precision)
         self.shared_embedding_dim = 2 * embed_dim   # width of get_embedding()[0]
 
@@ -108,14 +110,19 @@ class DisentangledSSL(LightningModule):
             E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="bf16", opts=o1)
             if after_shared is not None:
                 after_shared(E1, E2)
-            o2 = dict(xTs=list(bufTs) if need_t else None, extras_prefilled=True)
-            P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], bufs, extras=[E1, E2], precision="bf16", opts=o2)
+            if self.condzs:
+                o2 = dict(xTs=list(bufTs) if need_t else None, extras_prefilled=True)
+                P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], bufs, extras=[E1, E2], precision="bf16", opts=o2)
+            else:       # unconditioned private encoders read the same bf16 input columns as the shared ones
+                o2 = dict(xTs=[bufTs[0][:dims[0]], bufTs[1][:dims[1]]] if need_t else None)
+                P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], ins, precision="bf16", opts=o2)
         else:
             ins = [torch.cat(rows1, 0) if len(rows1) > 1 else rows1[0], torch.cat(rows2, 0) if len(rows2) > 1 else rows2[0]]
             E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="fp32")
             if after_shared is not None:
                 after_shared(E1, E2)
-            P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], ins, extras=[E1, E2], precision="fp32")
+            P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], ins, extras=[E1, E2] if self.condzs else None,
+                                     precision="fp32")
         return E1, E2, P1, P2
 
     @torch.no_grad()
@@ -130,6 +137,14 @@ class DisentangledSSL(LightningModule):
         """Noise of the four rsample() calls in the reference order (zs1, zs2, zsv1, zsv2).  ``out`` (device mode):
         list of four (w, v) buffer pairs to refill in place."""
         D = self.embed_dim
+        if self.distribution == "normal":
+            # Independent(Normal(mu, 1)).rsample() = mu + randn(mu.shape) (models/classifiers.py:456-459): four draws in
+            # the reference order on the parameters' device (seed-equal to the reference on the same device)
+            if out is not None:
+                for t in out:
+                    t.normal_()
+                return out
+            return [torch.randn(B, D, device=device) for _ in range(4)]
         if self.noise_mode == "device":
             self.noise_seed += 1
             return [ops.vmf_draw(B, D, self.vmfkappa, 0x5EED + self.noise_seed, i, device, out=None if out is None else out[i])
@@ -156,39 +171,62 @@ class DisentangledSSL(LightningModule):
         wb = pr == "bf16"          # bf16 path: the head kernels also write the bf16 copies the InfoNCE tiles consume
         st = {}
 
+        normal = self.distribution == "normal"
+
         def heads_shared(E1, E2):
-            # vMF reparameterised samples (noise rows follow the stacking: modality 1 <- draws 0,2; modality 2 <- 1,3)
-            w1 = torch.cat([noise[0][0], noise[2][0]], 0)
-            vv1 = torch.cat([noise[0][1], noise[2][1]], 0)
-            w2 = torch.cat([noise[1][0], noise[3][0]], 0)
-            vv2 = torch.cat([noise[1][1], noise[3][1]], 0)
-            Z1, Z2 = ops.vmf_rsample(E1, w1, vv1, want_bf16=wb), ops.vmf_rsample(E2, w2, vv2, want_bf16=wb)
-            if wb:
-                (Z1, Z1b), (Z2, Z2b) = Z1, Z2
-                bf = [(Z1b[:B], Z2b[:B]), (Z1b[B:], Z2b[B:])]
-            else:
+            if normal:
+                # unit-variance Gaussian head: z = e + eps (noise rows follow the stacking: modality 1 <- draws 0,2)
+                Z1 = E1 + torch.cat([noise[0], noise[2]], 0)
+                Z2 = E2 + torch.cat([noise[1], noise[3]], 0)
                 bf = [None, None]
+            else:
+                # vMF reparameterised samples (noise rows follow the stacking: modality 1 <- draws 0,2; modality 2 <- 1,3)
+                w1 = torch.cat([noise[0][0], noise[2][0]], 0)
+                vv1 = torch.cat([noise[0][1], noise[2][1]], 0)
+                w2 = torch.cat([noise[1][0], noise[3][0]], 0)
+                vv2 = torch.cat([noise[1][1], noise[3][1]], 0)
+                Z1, Z2 = ops.vmf_rsample(E1, w1, vv1, want_bf16=wb), ops.vmf_rsample(E2, w2, vv2, want_bf16=wb)
+                if wb:
+                    (Z1, Z1b), (Z2, Z2b) = Z1, Z2
+                    bf = [(Z1b[:B], Z2b[:B]), (Z1b[B:], Z2b[B:])]
+                else:
+                    bf = [None, None]
             st["pairs"] = [(Z1[:B], Z2[:B]), (Z1[B:], Z2[B:])]
             # the shared critic inputs exist now: launch their embedding all-gathers (asynchronous NCCL) BEFORE the
             # private encoders run, so that the gathers overlap those GEMMs
             st["pres"] = [ops.GatheredPair(a, b, pr, bf16=f) for (a, b), f in zip(st["pairs"], bf)]
         E1, E2, P1, P2 = self._encode([x1, v1], [x2, v2], after_shared=heads_shared)                       # [2B, D] each
-        P1n, P2n = ops.row_normalize(P1, want_bf16=wb), ops.row_normalize(P2, want_bf16=wb)
-        if wb:
+        # specific critic inputs: normalize(z) or, with usezsx, normalize([z | e]) (models/disentangledssl.py:128-140)
+        C1, C2 = (torch.cat([P1, E1], 1), torch.cat([P2, E2], 1)) if self.usezsx else (P1, P2)
+        # the tensor-core InfoNCE tiles cover widths that are multiples of 64 up to 512; a wider [z | e] critic input
+        # (usezsx with 2 * embed_dim > 512) runs the exact fp32 tiles instead
+        Dc = C1.shape[1]
+        pr_spec = pr if (pr != "bf16" or (Dc % 64 == 0 and Dc <= 512)) else "fp32"
+        wbs = pr_spec == "bf16"
+        P1n, P2n = ops.row_normalize(C1, want_bf16=wbs), ops.row_normalize(C2, want_bf16=wbs)
+        if wbs:
             (P1n, P1b), (P2n, P2b) = P1n, P2n
             bf = [(P1b[:B], P1b[B:]), (P2b[:B], P2b[B:])]
         else:
             bf = [None, None]
         pairs23 = [(P1n[:B], P1n[B:]), (P2n[:B], P2n[B:])]
         pairs = st["pairs"] + pairs23
-        pres = st["pres"] + [ops.GatheredPair(a, b, pr, bf16=f) for (a, b), f in zip(pairs23, bf)]
+        pres = st["pres"] + [ops.GatheredPair(a, b, pr_spec, bf16=f) for (a, b), f in zip(pairs23, bf)]
         # data parallel: every critic call returns this rank's PARTIAL sums; they are all-reduced ONCE below
         # (all combinations are linear and the gradients do not depend on the loss value)
         dp = ops._dist_on()
         # ONE op for the four critic calls (the reference discards loss_x / loss_y of the two specific-critic calls:
         # their intra-view blocks are skipped); under data parallelism the four calls share one column-sum all-reduce
         # and one LSE all-gather
-        out = self.critic.multi(pairs, pres=pres, unit_norm=True, reduce=not dp, diagnostics=[True, True, False, False])
+        if normal or pr_spec != pr:
+            # Gaussian samples are not unit vectors (the shared calls then take the exact online-max kernels), and the
+            # two groups may run at different precisions: one op per group
+            o_sh = self.critic.multi(pairs[:2], pres=pres[:2], unit_norm=not normal, reduce=not dp, diagnostics=[True, True])
+            o_sp = self.critic.multi(pairs[2:], pres=pres[2:], unit_norm=True, reduce=not dp, diagnostics=[False, False],
+                                     precision=pr_spec)
+            out = torch.cat([o_sh, o_sp], 0)
+        else:
+            out = self.critic.multi(pairs, pres=pres, unit_norm=True, reduce=not dp, diagnostics=[True, True, False, False])
         joint_loss = 0.5 * (out[0, 0] + out[1, 0])
         loss_x = 0.5 * (out[0, 1] + out[1, 1]).detach()
         loss_y = 0.5 * (out[0, 2] + out[1, 2]).detach()
@@ -203,6 +241,8 @@ class DisentangledSSL(LightningModule):
             # launch + one all-reduce for the four calls (rows of P are already normalised for the critic)
             with torch.no_grad(), ops._Prof("ortho"):
                 E1n, E2n = ops.row_normalize(E1), ops.row_normalize(E2)
+                if self.usezsx:     # the critic normalised [z | e]; the ortho term needs normalize(z)
+                    P1n, P2n = ops.row_normalize(P1), ops.row_normalize(P2)
                 ov = ops.ortho_values_nograd([(P1n[:B], E1n[:B]), (P2n[:B], E2n[:B]), (P1n[B:], E1n[B:]), (P2n[B:], E2n[B:])],
                                              self.precision)
                 loss_ortho = 0.5 * (ov[0] + ov[1]) + 0.5 * (ov[2] + ov[3])

@@ -42,10 +42,10 @@ class SupConLoss(nn.Module):
         return r * loss, r * lx, r * ly
 
 
-    def multi(self, pairs, pres=None, unit_norm=False, reduce=True, diagnostics=None):
+    def multi(self, pairs, pres=None, unit_norm=False, reduce=True, diagnostics=None, precision=None):
         """Several (z0, z1) critic calls in one op: [ncalls, 3] = (loss, loss_x, loss_y) rows (ops.infonce_multi)."""
-        out = ops.infonce_multi(pairs, self.temperature, self.precision, unit_norm=unit_norm, pres=pres, reduce=reduce,
-                                diagnostics=diagnostics)
+        out = ops.infonce_multi(pairs, self.temperature, precision or self.precision, unit_norm=unit_norm, pres=pres,
+                                reduce=reduce, diagnostics=diagnostics)
         return (self.temperature / self.base_temperature) * out
 
 

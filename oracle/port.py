@@ -328,27 +328,44 @@ def dmvae_get_embedding(xs, enc, poe_temperature: float = 1.5):
 # --------------------------------------------------------------------------------------
 # a7  DisentangledSSL                                  models/disentangledssl.py:67-160
 # --------------------------------------------------------------------------------------
-def dssl_forward(x1, x2, v1, v2, p: Dict[str, Tuple[list, list]], noise: Sequence[Tuple[Tensor, Tensor]],
-                 a: float = 1.0, lmd: float = 0.0, T: float = 0.07
-                 ) -> Tuple[Tensor, Dict[str, Tensor]]:
-    """``DisentangledSSL.forward`` (condzs=True, usezsx=False, distribution='vmf').
+def dssl_forward(x1, x2, v1, v2, p: Dict[str, Tuple[list, list]], noise: Sequence,
+                 a: float = 1.0, lmd: float = 0.0, T: float = 0.07, condzs: bool = True, usezsx: bool = False,
+                 distribution: str = "vmf") -> Tuple[Tensor, Dict[str, Tensor]]:
+    """``DisentangledSSL.forward`` models/disentangledssl.py:82-160.
     ``p`` maps 'x1s','x2s','x1','x2' -> (weights, biases) of encoder_x1s/x2s/x1/x2.
-    ``noise`` = [(w,v)]*4 in the reference's rsample order (:100-103): zs1, zs2, zsv1, zsv2."""
+    ``noise`` in the reference's rsample order (:100-103: zs1, zs2, zsv1, zsv2): four (w, v) pairs for
+    distribution='vmf', four standard-normal tensors [B, D] for 'normal' (Independent(Normal(mu, 1)).rsample() =
+    mu + eps, models/classifiers.py:456-459).  ``condzs`` (:116-125): private encoders see [x | e] or x alone;
+    ``usezsx`` (:128-137): the specific critic compares normalize([z | e]) instead of normalize(z)."""
     e1, e2 = mlp(x1, *p["x1s"]), mlp(x2, *p["x2s"])                # :90-93
     e1v, e2v = mlp(v1, *p["x1s"]), mlp(v2, *p["x2s"])
-    zs1, zs2 = vmf_rsample(e1, *noise[0]), vmf_rsample(e2, *noise[1])
-    zsv1, zsv2 = vmf_rsample(e1v, *noise[2]), vmf_rsample(e2v, *noise[3])
+    if distribution == "vmf":
+        zs1, zs2 = vmf_rsample(e1, *noise[0]), vmf_rsample(e2, *noise[1])
+        zsv1, zsv2 = vmf_rsample(e1v, *noise[2]), vmf_rsample(e2v, *noise[3])
+    elif distribution == "normal":
+        zs1, zs2, zsv1, zsv2 = e1 + noise[0], e2 + noise[1], e1v + noise[2], e2v + noise[3]
+    else:
+        raise ValueError(distribution)
     j, lx, ly = supcon(zs1, zs2, T)                                # :106-113
     jv, lxv, lyv = supcon(zsv1, zsv2, T)
     joint = 0.5 * (j + jv)
     loss_x, loss_y = 0.5 * (lx + lxv), 0.5 * (ly + lyv)
-    z1x1 = mlp(torch.cat([x1, e1], 1), *p["x1"])                   # :116-120
-    z1xv1 = mlp(torch.cat([v1, e1v], 1), *p["x1"])
-    z2x2 = mlp(torch.cat([x2, e2], 1), *p["x2"])
-    z2xv2 = mlp(torch.cat([v2, e2v], 1), *p["x2"])
-    n = lambda t: F.normalize(t, dim=-1)                           # :139-143
-    s1, _, _ = supcon(n(z1x1), n(z1xv1), T)
-    s2, _, _ = supcon(n(z2x2), n(z2xv2), T)
+    if condzs:                                                     # :116-125
+        z1x1 = mlp(torch.cat([x1, e1], 1), *p["x1"])
+        z1xv1 = mlp(torch.cat([v1, e1v], 1), *p["x1"])
+        z2x2 = mlp(torch.cat([x2, e2], 1), *p["x2"])
+        z2xv2 = mlp(torch.cat([v2, e2v], 1), *p["x2"])
+    else:
+        z1x1, z1xv1 = mlp(x1, *p["x1"]), mlp(v1, *p["x1"])
+        z2x2, z2xv2 = mlp(x2, *p["x2"]), mlp(v2, *p["x2"])
+    n = lambda t: F.normalize(t, dim=-1)                           # :128-143
+    if usezsx:
+        c1 = (n(torch.cat([z1x1, e1], 1)), n(torch.cat([z1xv1, e1v], 1)))
+        c2 = (n(torch.cat([z2x2, e2], 1)), n(torch.cat([z2xv2, e2v], 1)))
+    else:
+        c1, c2 = (n(z1x1), n(z1xv1)), (n(z2x2), n(z2xv2))
+    s1, _, _ = supcon(*c1, T)
+    s2, _, _ = supcon(*c2, T)
     specific = s1 + s2
     ortho = 0.5 * (ortho_loss(z1x1, e1) + ortho_loss(z2x2, e2)) + \
         0.5 * (ortho_loss(z1xv1, e1v) + ortho_loss(z2xv2, e2v))    # :154-155
@@ -359,11 +376,14 @@ def dssl_forward(x1, x2, v1, v2, p: Dict[str, Tuple[list, list]], noise: Sequenc
     return loss, logs
 
 
-def dssl_get_embedding(x1, x2, p):
+def dssl_get_embedding(x1, x2, p, condzs: bool = True):
     """``DisentangledSSL.get_embedding`` models/disentangledssl.py:67-80."""
     zs1, zs2 = mlp(x1, *p["x1s"]), mlp(x2, *p["x2s"])
-    z1 = mlp(torch.cat([x1, zs1], 1), *p["x1"])
-    z2 = mlp(torch.cat([x2, zs2], 1), *p["x2"])
+    if condzs:
+        z1 = mlp(torch.cat([x1, zs1], 1), *p["x1"])
+        z2 = mlp(torch.cat([x2, zs2], 1), *p["x2"])
+    else:
+        z1, z2 = mlp(x1, *p["x1"]), mlp(x2, *p["x2"])
     return torch.cat([zs1, zs2], 1), [z1, z2]
 
 

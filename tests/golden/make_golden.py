@@ -424,6 +424,7 @@ def gen_dmvae_full():
             gflat = p_.grad.reshape(-1)
             idx = grad_samples(gflat.numel())
             out["gnorm." + k] = np.float64(gflat.double().norm())
+            out["gmax." + k] = np.float64(gflat.abs().max())
             out["gidx." + k] = idx
             out["gval." + k] = gflat[torch.from_numpy(idx)]
             out["wsum." + k] = np.float64(p_.detach().double().sum())     # pins the seed-regenerated weights
@@ -436,7 +437,52 @@ def gen_dmvae_full():
         save("dmvae_full_" + tag, **out)
 
 
+# ----------------------------------------------------------------------------------------
+# 12. DisentangledSSL, non-default branches: condzs=False, usezsx=True, distribution='normal'
+#     models/disentangledssl.py:57-62,116-137, models/classifiers.py:456-459
+# ----------------------------------------------------------------------------------------
+def gen_dssl_variants():
+    for tag, kw in {"nocond": dict(condzs=False), "zsx": dict(usezsx=True), "normal": dict(distribution="normal"),
+                    "normal_nocond_zsx": dict(distribution="normal", condzs=False, usezsx=True)}.items():
+        dims, h, e, B, a = [24, 40], 32, 16, 32, 0.5
+        with cuda_identity_shim():
+            torch.manual_seed(5)
+            m = ns.disentangledssl.DisentangledSSL(output_dim=dims, hidden_dim=h, embed_dim=e, a=a, lmd_start_value=0.25, **kw)
+            g = torch.Generator().manual_seed(23)
+            x1, x2 = torch.randn(B, dims[0], generator=g), torch.randn(B, dims[1], generator=g)
+            v1 = x1 + 0.01 * torch.randn(B, dims[0], generator=g)
+            v2 = x2 + 0.01 * torch.randn(B, dims[1], generator=g)
+            torch.manual_seed(1234)
+            loss, logs = m(x1, x2, v1, v2)
+            loss.backward()
+            torch.manual_seed(1234)        # replay the reference's draw order to obtain the explicit noise
+            if kw.get("distribution", "vmf") == "vmf":
+                noise = [port.draw_vmf_noise(B, e, 1.0) for _ in range(4)]
+            else:                          # Independent(Normal(mu, 1)).rsample(): eps = randn(mu.shape), four draws in order
+                noise = [torch.randn(B, e) for _ in range(4)]
+            emb_s, emb_p = m.get_embedding([x1, x2])
+        out = state_arrays(m)
+        out.update({f"grad.{k}": p.grad for k, p in m.named_parameters()})
+        out.update(x1=x1, x2=x2, v1=v1, v2=v2, loss=loss, emb_shared=emb_s, emb_private0=emb_p[0], emb_private1=emb_p[1])
+        for i, nz in enumerate(noise):
+            if isinstance(nz, tuple):
+                out[f"noise_w{i}"], out[f"noise_v{i}"] = nz
+            else:
+                out[f"noise_eps{i}"] = nz
+        for k in ("shared", "clip", "loss_x", "loss_y", "specific", "ortho", "lmd"):
+            out["log." + k] = np.float32(logs[k])
+        out["meta"] = np.array([h, e, B], dtype=np.int64)
+        out["dims"] = np.array(dims, dtype=np.int64)
+        out["a"] = np.float64(a)
+        out["flags"] = np.array([int(kw.get("condzs", True)), int(kw.get("usezsx", False)),
+                                 int(kw.get("distribution", "vmf") == "normal")], dtype=np.int64)
+        save("dssl_var_" + tag, **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "dssl_variants":
+        gen_dssl_variants()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "full":
         gen_dmvae_full()
         sys.exit(0)
@@ -451,3 +497,4 @@ if __name__ == "__main__":
     gen_eval()
     gen_datasets()
     gen_dmvae_full()
+    gen_dssl_variants()

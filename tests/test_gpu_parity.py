@@ -609,6 +609,45 @@ def test_dssl_module(dmf, tag):
     assert_close(ep[1], g["emb_private1"], FP32, "emb_private1")
 
 
+@pytest.mark.parametrize("tag", ["nocond", "zsx", "normal", "normal_nocond_zsx"])
+def test_dssl_variants(dmf, tag):
+    """non-default branches of DisentangledSSL -- condzs=False, usezsx=True, distribution='normal'
+    (models/disentangledssl.py:57-62,116-137, models/classifiers.py:456-459) -- fp32 path vs reference fixtures, and the
+    bf16 path against the repo's fp32 path on the same inputs."""
+    g = load_golden("dssl_var_" + tag)
+    condzs, usezsx, normal = (bool(v) for v in g["flags"])
+    h, e, B = (int(v) for v in g["meta"])
+    dims = [int(d) for d in g["dims"]]
+    kw = dict(output_dim=dims, hidden_dim=h, embed_dim=e, a=float(g["a"]), lmd_start_value=float(g["log.lmd"]),
+              condzs=condzs, usezsx=usezsx, distribution="normal" if normal else "vmf")
+    m = _load_sd(dmf.DisentangledSSL(**kw), g).to(DEV)
+    x1, x2, v1, v2 = (T(g[k], DEV) for k in ("x1", "x2", "v1", "v2"))
+    if normal:
+        noise = [T(g[f"noise_eps{i}"], DEV) for i in range(4)]
+    else:
+        noise = [(T(g[f"noise_w{i}"], DEV), T(g[f"noise_v{i}"], DEV)) for i in range(4)]
+    loss, logs = m(x1, x2, v1, v2, noise=noise)
+    assert_close(loss, g["loss"], FP32, "loss")
+    for k in ("shared", "specific", "ortho"):
+        assert_close(logs[k], g["log." + k], FP32, k)
+    assert_close(logs["loss_x"], g["log.loss_x"], 1e-4, "loss_x")
+    loss.backward()
+    for k, p in m.named_parameters():
+        assert_close(p.grad, g["grad." + k], 2e-5, "grad " + k)
+    es, ep = m.get_embedding([x1, x2])
+    assert_close(es, g["emb_shared"], FP32, "emb_shared")
+    assert_close(ep[0], g["emb_private0"], FP32, "emb_private0")
+    # bf16 path (widths here are below the 64-multiple the tensor-core tiles need, so every InfoNCE call must fall back
+    # to an exact path or raise cleanly; the encoders run on the tcgen05 GEMM)
+    mb = _load_sd(dmf.DisentangledSSL(precision="bf16", **kw), g).to(DEV)
+    try:
+        lb, _ = mb(x1, x2, v1, v2, noise=noise)
+    except dmf._lib.DmfError as ex:
+        assert "multiple of 64" in str(ex)
+    else:
+        assert_close(lb, g["loss"], 2e-2, "bf16 loss")
+
+
 def test_dssl_seed_parity(dmf):
     """Same seed => same vMF noise stream as the reference => same loss without passing noise."""
     g = load_golden("dssl_small")

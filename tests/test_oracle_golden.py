@@ -139,6 +139,36 @@ def test_dmvae_full_size(tag):
         torch.set_num_threads(1)
 
 
+def _dssl_noise(g):
+    if "noise_eps0" in g:
+        return [T(g[f"noise_eps{i}"]) for i in range(4)]
+    return [(T(g[f"noise_w{i}"]), T(g[f"noise_v{i}"])) for i in range(4)]
+
+
+@pytest.mark.parametrize("tag", ["nocond", "zsx", "normal", "normal_nocond_zsx"])
+def test_dssl_variants(tag):
+    """non-default branches of DisentangledSSL (condzs=False, usezsx=True, distribution='normal')"""
+    g = load_golden("dssl_var_" + tag)
+    condzs, usezsx, normal = (bool(v) for v in g["flags"])
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    names = {"x1s": "encoder_x1s", "x2s": "encoder_x2s", "x1": "encoder_x1", "x2": "encoder_x2"}
+    p = {k: mlp_params_from_sd(sd, n, (0, 2, 4), grad=True) for k, n in names.items()}
+    x1, x2, v1, v2 = (T(g[k]) for k in ("x1", "x2", "v1", "v2"))
+    loss, logs = port.dssl_forward(x1, x2, v1, v2, p, _dssl_noise(g), a=float(g["a"]), lmd=float(g["log.lmd"]), condzs=condzs,
+                                   usezsx=usezsx, distribution="normal" if normal else "vmf")
+    assert_close(loss, g["loss"], TOL, "loss")
+    for k in ("shared", "specific", "ortho"):
+        assert_close(logs[k], g["log." + k], TOL, k)
+    loss.backward()
+    for k, n in names.items():
+        for li, idx in enumerate((0, 2, 4)):
+            assert_close(p[k][0][li].grad, g[f"grad.{n}.layers.{idx}.weight"], 2e-5, f"{n} wgrad {idx}")
+    with torch.no_grad():
+        es, ep = port.dssl_get_embedding(x1, x2, p, condzs=condzs)
+    assert_close(es, g["emb_shared"], TOL, "emb_shared")
+    assert_close(ep[0], g["emb_private0"], TOL, "emb_private0")
+
+
 @pytest.mark.parametrize("tag", ["small", "wide"])
 def test_dssl(tag):
     g = load_golden("dssl_" + tag)

@@ -686,15 +686,16 @@ def run_gpu(args, rank, world, local_rank):
     d2h_ev = [torch.cuda.Event(), torch.cuda.Event()]
     d2h_pending = [False, False]
 
-    def e2e_step():
+    def e2e_step(copy=True, sync=True):
         # Every step: H2D of the NEXT batch on the copy stream (overlaps this step's compute), this step's
         # graph launch, an asynchronous D2H copy of its loss into pinned memory, and the host READ of the
         # previous step's loss (after its copy event) -- the usual one-step-lagged logging of a training loop,
         # so the host never idles the GPU while it waits for a scalar.
         i = state["i"]
-        torch.cuda.current_stream().wait_event(ready[i])
-        copy_stream.wait_stream(torch.cuda.current_stream())   # next copy must not overwrite a buffer in use
-        prefetch(i ^ 1)
+        if copy:
+            torch.cuda.current_stream().wait_event(ready[i])
+            copy_stream.wait_stream(torch.cuda.current_stream())   # next copy must not overwrite a buffer in use
+            prefetch(i ^ 1)
         model.draw_noise(Bl, dev, out=noise_bufs)
         augment_views(bufs[i])
         out = gsteps[i]() if gsteps[i] is not None else step(bufs[i])
@@ -702,7 +703,7 @@ def run_gpu(args, rank, world, local_rank):
         d2h_ev[i].record()
         d2h_pending[i] = True
         j = i ^ 1
-        if d2h_pending[j]:
+        if sync and d2h_pending[j]:
             d2h_ev[j].synchronize()
             state["losses"].append(float(d2h[j][0]))
             d2h_pending[j] = False
@@ -719,6 +720,16 @@ def run_gpu(args, rank, world, local_rank):
     ms_e2e = timed(args.steps, e2e_step)
     e2e_drain()
     e2e_value = Bg * args.steps / (ms_e2e / 1e3)
+    e2e_diag = None
+    if args.e2e_diag:
+        # where does the end-to-end arm lose time against the device-resident one?  Same loop without the H2D copies,
+        # and with the copies but without the per-step host read of the loss.
+        ms_nocopy = timed(args.steps, lambda: e2e_step(copy=False))
+        e2e_drain()
+        prefetch(state["i"])
+        ms_nosync = timed(args.steps, lambda: e2e_step(sync=False))
+        e2e_drain()
+        e2e_diag = {"ms_per_step_no_h2d": ms_nocopy / args.steps, "ms_per_step_no_host_read": ms_nosync / args.steps}
 
     if rank != 0:
         return
@@ -793,7 +804,7 @@ def run_gpu(args, rank, world, local_rank):
         "step_tflops_algorithmic": step_flops / 1e12,
         "step_frac_of_sustained_bf16": step_flops / (ms / args.steps * 1e-3) / 1e12 / (pk["tf_sust"] * world),
         "roofline": roof, "roofline_k1": roof_k1, "roofline_k3": roof_k3, "cpu_baseline": cpu,
-        "loss_check": lcheck, "phase_ms": phases,
+        "loss_check": lcheck, "phase_ms": phases, "e2e_diag": e2e_diag,
         "step_ms": {"value": step_marks[0], "e2e": step_marks[-1]},
     }
     print(json.dumps(line), flush=True)
@@ -812,6 +823,7 @@ def main():
     ap.add_argument("--config", default="c5", choices=["c1", "c2", "c3", "c4", "c5"],
                     help="BASELINE.json config: c5 (default) = the headline workload; c1-c4 = the small launch-bound configs "
                          "(single GPU; samples/s + launches/step beside the CPU port at the same batch)")
+    ap.add_argument("--e2e-diag", action="store_true", help="extra end-to-end loops without H2D / without the host read")
     ap.add_argument("--no-kernel-rooflines", action="store_true", help="skip the live K1 / K3 roofline measurements")
     ap.add_argument("--no-loss-check", dest="loss_check", action="store_false",
                     help="skip the cross-N loss / gradient-norm check step")

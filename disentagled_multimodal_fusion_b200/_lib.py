@@ -92,6 +92,9 @@ _SIGS = {
     "dmf_vmf_bwd": ([c_p, c_ll, c_p, c_p, c_p, c_ll, c_i, c_i, c_p, c_ll, c_i, c_p], c_i),
     "dmf_vmf_draw": ([c_p, c_p, c_i, c_i, c_f, c_ull, c_ull, c_p], c_i),
     "dmf_augment": ([c_p, c_ll, c_p, c_ll, c_i, c_i, c_f, c_i, c_ull, c_ull, c_p, c_p], c_i),
+    "dmf_vmf_draw_ctr": ([c_p, c_p, c_i, c_i, c_f, c_ull, c_ull, c_p, c_p], c_i),
+    "dmf_augment_ctr": ([c_p, c_ll, c_p, c_ll, c_i, c_i, c_f, c_i, c_ull, c_ull, c_p, c_p, c_p], c_i),
+    "dmf_counter_add": ([c_p, c_ull, c_p], c_i),
     "dmf_dmvae_head_fwd": ([C.POINTER(c_p), c_p, c_i, c_i, c_i, c_f, C.POINTER(c_p), c_p, c_p], c_i),
     "dmf_dmvae_head_bwd": ([C.POINTER(c_p), c_p, C.POINTER(c_p), c_i, c_i, c_i, c_f, c_p, C.POINTER(c_p), c_p], c_i),
     "dmf_dmvae_poe_mean": ([C.POINTER(c_p), c_i, c_i, c_i, c_f, c_p, c_p], c_i),

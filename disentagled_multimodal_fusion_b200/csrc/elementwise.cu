@@ -216,10 +216,12 @@ __device__ float gamma_mt(HashRng* st, float alpha) {
 }
 
 __global__ void __launch_bounds__(256) vmf_draw_kernel(float* __restrict__ nw, float* __restrict__ nv, int rows, int D, float kappa,
-                                                       unsigned long long seed, unsigned long long offset) {
+                                                       unsigned long long seed, unsigned long long offset,
+                                                       const unsigned long long* __restrict__ ctr) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (ctr) seed += *ctr * 0xA0761D6478BD642Full;      // device-resident draw counter (CUDA-graph replays draw fresh noise)
   HashRng st(seed, offset, (unsigned long long)row * 32 + lane);
   float* v = nv + (long long)row * (D - 1);
   const int n = D - 1;
@@ -302,10 +304,11 @@ __device__ __forceinline__ unsigned aug_key(unsigned long long seed, unsigned lo
 
 __global__ void __launch_bounds__(256) augment_kernel(const float* __restrict__ X, long long ldx, float* __restrict__ Y, long long ldy, int rows,
                                int D, float noise_scale, int n_drop, unsigned long long seed, unsigned long long offset,
-                               int* __restrict__ choice_out) {
+                               int* __restrict__ choice_out, const unsigned long long* __restrict__ ctr) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (ctr) seed += *ctr * 0xA0761D6478BD642Full;      // device-resident draw counter (CUDA-graph replays draw fresh noise)
   HashRng st(seed, offset, (unsigned long long)row * 32 + lane);
   // per-row choice: one hashed word per row, mapped to {0,1,2} by a multiply-shift (bias 2^-32)
   const unsigned rw = (unsigned)(mix64(mix64(seed ^ 0xC2B2AE3D27D4EB4Full) + offset * 0x9E3779B97F4A7C15ull +
@@ -878,8 +881,21 @@ extern "C" int dmf_vmf_draw(float* nw, float* nv, int rows, int D, float kappa, 
                             unsigned long long offset, dmf_stream_t s) {
   DMF_REQUIRE(nw && nv && rows >= 0 && D >= 2 && D != 3 && kappa > 0.f, "dmf_vmf_draw: bad arguments (D=3 uses the host sampler)");
   if (rows == 0) return 0;
-  vmf_draw_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(nw, nv, rows, D, kappa, seed, offset);
+  vmf_draw_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(nw, nv, rows, D, kappa, seed, offset, nullptr);
   return launched("dmf_vmf_draw");
+}
+extern "C" int dmf_vmf_draw_ctr(float* nw, float* nv, int rows, int D, float kappa, unsigned long long seed,
+                                unsigned long long offset, const unsigned long long* counter, dmf_stream_t s) {
+  DMF_REQUIRE(nw && nv && counter && rows >= 0 && D >= 2 && D != 3 && kappa > 0.f, "dmf_vmf_draw_ctr: bad arguments");
+  if (rows == 0) return 0;
+  vmf_draw_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(nw, nv, rows, D, kappa, seed, offset, counter);
+  return launched("dmf_vmf_draw_ctr");
+}
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+extern "C" int dmf_counter_add(unsigned long long* counter, unsigned long long inc, dmf_stream_t s) {
+  DMF_REQUIRE(counter, "dmf_counter_add: null counter");
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)s>>>(counter, inc);
+  return launched("dmf_counter_add");
 }
 
 
@@ -889,8 +905,17 @@ extern "C" int dmf_augment(const float* X, long long ldx, float* Y, long long ld
   DMF_REQUIRE(X && Y && rows >= 0 && D >= 1 && drop_scale >= 1, "dmf_augment: bad arguments");
   if (rows == 0) return 0;
   augment_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(X, ldx, Y, ldy, rows, D, noise_scale, D / drop_scale, seed,
-                                                            offset, choice_out);
+                                                            offset, choice_out, nullptr);
   return launched("dmf_augment");
+}
+extern "C" int dmf_augment_ctr(const float* X, long long ldx, float* Y, long long ldy, int rows, int D, float noise_scale,
+                               int drop_scale, unsigned long long seed, unsigned long long offset, int* choice_out,
+                               const unsigned long long* counter, dmf_stream_t s) {
+  DMF_REQUIRE(X && Y && counter && rows >= 0 && D >= 1 && drop_scale >= 1, "dmf_augment_ctr: bad arguments");
+  if (rows == 0) return 0;
+  augment_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>(X, ldx, Y, ldy, rows, D, noise_scale, D / drop_scale, seed,
+                                                            offset, choice_out, counter);
+  return launched("dmf_augment_ctr");
 }
 
 static int fill_views(ViewPtrs& P, const float* const* in, const float* const* in2, float* const* out, int N) {

@@ -153,21 +153,37 @@ def _grad_slot(p: Tensor) -> Optional[Tensor]:
     return g
 
 
-def vmf_draw(rows: int, D: int, kappa: float, seed: int, offset: int, device, out=None) -> Tuple[Tensor, Tensor]:
+def rng_counter(device) -> Tensor:
+    """A device-resident 64-bit draw counter for the ``ctr=`` argument of ``vmf_draw`` / ``augment``: the draws are keyed
+    by (seed, counter), and ``counter_add`` bumps it ON THE DEVICE -- so a training step captured once into a CUDA
+    graph draws fresh noise on every replay."""
+    return torch.zeros(1, dtype=torch.int64, device=device)
+
+
+def counter_add(ctr: Tensor, inc: int = 1) -> None:
+    L.require_device()
+    check(lib.dmf_counter_add(ptr(ctr), int(inc), stream()))
+
+
+def vmf_draw(rows: int, D: int, kappa: float, seed: int, offset: int, device, out=None, ctr: Optional[Tensor] = None
+             ) -> Tuple[Tensor, Tensor]:
     """Device-side vMF noise (distribution-equal to the reference sampler, not stream-equal).  ``out`` = (w, v)
-    pre-allocated buffers to draw into (fixed addresses for CUDA-graph replay)."""
+    pre-allocated buffers to draw into (fixed addresses for CUDA-graph replay); ``ctr`` = device draw counter."""
     L.require_device()
     if out is None:
         w = torch.empty(rows, 1, dtype=torch.float32, device=device)
         v = torch.empty(rows, D - 1, dtype=torch.float32, device=device)
     else:
         w, v = out
-    check(lib.dmf_vmf_draw(ptr(w), ptr(v), rows, D, float(kappa), seed, offset, stream()))
+    if ctr is not None:
+        check(lib.dmf_vmf_draw_ctr(ptr(w), ptr(v), rows, D, float(kappa), seed, offset, ptr(ctr), stream()))
+    else:
+        check(lib.dmf_vmf_draw(ptr(w), ptr(v), rows, D, float(kappa), seed, offset, stream()))
     return w, v
 
 
 def augment(x: Tensor, seed: int, offset: int = 0, noise_scale: float = 0.01, drop_scale: int = 10,
-            return_choice: bool = False, out: Optional[Tensor] = None):
+            return_choice: bool = False, out: Optional[Tensor] = None, ctr: Optional[Tensor] = None):
     """Device-side ``augment_data`` (utils.py:118-151): per row noise / random column drop / identity with
     probability 1/3 each.  Distribution-equal to the reference's host loop, not stream-equal."""
     L.require_device()
@@ -175,8 +191,12 @@ def augment(x: Tensor, seed: int, offset: int = 0, noise_scale: float = 0.01, dr
     B, D = x.shape
     y = torch.empty_like(x) if out is None else out        # ``out``: fixed buffer refilled in place (CUDA-graph replays)
     ch = torch.empty(B, dtype=torch.int32, device=x.device) if return_choice else None
-    check(lib.dmf_augment(ptr(x), x.stride(0), ptr(y), y.stride(0), B, D, float(noise_scale), int(drop_scale), int(seed),
-                          int(offset), ptr(ch), stream()))
+    if ctr is not None:
+        check(lib.dmf_augment_ctr(ptr(x), x.stride(0), ptr(y), y.stride(0), B, D, float(noise_scale), int(drop_scale),
+                                  int(seed), int(offset), ptr(ch), ptr(ctr), stream()))
+    else:
+        check(lib.dmf_augment(ptr(x), x.stride(0), ptr(y), y.stride(0), B, D, float(noise_scale), int(drop_scale), int(seed),
+                              int(offset), ptr(ch), stream()))
     return (y, ch) if return_choice else y
 
 

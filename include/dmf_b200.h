@@ -184,6 +184,17 @@ int dmf_vmf_draw(float* noise_w, float* noise_v, int rows, int D, float kappa, u
 int dmf_augment(const float* X, long long ldx, float* Y, long long ldy, int rows, int D, float noise_scale,
                 int drop_scale, unsigned long long seed, unsigned long long offset, int* choice_out, dmf_stream_t s);
 
+/* The same two draws keyed additionally by a DEVICE-resident 64-bit counter (seed' = seed + *counter * odd constant),
+ * so that a training step captured once into a CUDA graph draws fresh noise on every replay: capture
+ * {dmf_augment_ctr, dmf_vmf_draw_ctr, ..., dmf_counter_add(counter, 1)}.  (The reference draws on the host:
+ * utils.py:118-151, models/classifiers.py:314-431.)                                                             */
+int dmf_vmf_draw_ctr(float* noise_w, float* noise_v, int rows, int D, float kappa, unsigned long long seed,
+                     unsigned long long offset, const unsigned long long* counter, dmf_stream_t s);
+int dmf_augment_ctr(const float* X, long long ldx, float* Y, long long ldy, int rows, int D, float noise_scale,
+                    int drop_scale, unsigned long long seed, unsigned long long offset, int* choice_out,
+                    const unsigned long long* counter, dmf_stream_t s);
+int dmf_counter_add(unsigned long long* counter, unsigned long long inc, dmf_stream_t s);
+
 /* ------------------------------------------------------------------ DMVAE head + objectives
  * Replaces chunk/exp/randn_like/PoE/KL of models/dmvae.py:74-112,142-150,170-172.
  * stats [N][B,4e] (mu_s, lv_s, mu_p, lv_p), noise [2N+1][B,e] in the reference draw order.

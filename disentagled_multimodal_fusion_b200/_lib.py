@@ -54,7 +54,7 @@ class TcGemmDesc(C.Structure):
                 ("mask_bf16", c_p), ("ldmask", c_ll),
                 ("M", c_i), ("N", c_i), ("K", c_i),
                 ("out_bf16_t", c_p), ("ldo_t", c_ll),
-                ("split_k", c_i)]
+                ("split_k", c_i), ("mn_major", c_i)]
 
 
 class EdlParams(C.Structure):

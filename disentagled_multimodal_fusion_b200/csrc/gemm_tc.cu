@@ -187,7 +187,7 @@ static int launch_tc(const TcGemmParams& P, int tiles, cudaStream_t st) {
 extern "C" int dmf_grouped_gemm_bf16_tc(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, dmf_stream_t s) {
   DMF_REQUIRE(groups && n_groups >= 1, "dmf_grouped_gemm_bf16_tc: no groups");
   // validate, then route: CTA-pair persistent kernel when every group can feed 256-row x 256-col tiles
-  bool pair_ok = true;
+  bool pair_ok = true, any_mn = false;
   for (int i = 0; i < n_groups; ++i) {
     const dmf_tc_gemm_desc& d = groups[i];
     DMF_REQUIRE(d.M >= 0 && d.N >= 0 && d.K >= 1, "dmf_grouped_gemm_bf16_tc: bad dims in group %d", i);
@@ -195,7 +195,10 @@ extern "C" int dmf_grouped_gemm_bf16_tc(const dmf_tc_gemm_desc* groups, int n_gr
     DMF_REQUIRE(d.A && d.B && (d.out_f32 || d.out_bf16 || d.out_bf16_t), "dmf_grouped_gemm_bf16_tc: null pointer in group %d", i);
     DMF_REQUIRE(epilogue != DMF_EPI_RELU_MASK || d.mask_bf16, "dmf_grouped_gemm_bf16_tc: RELU_MASK needs mask (group %d)", i);
     if (d.M < 512 || d.N < 128) pair_ok = false;
+    any_mn = any_mn || d.mn_major != 0;
+    DMF_REQUIRE(!d.mn_major || ((d.lda & 7) == 0 && (d.ldb & 7) == 0), "dmf_grouped_gemm_bf16_tc: mn_major needs row pitches that are multiples of 8 (group %d)", i);
   }
+  DMF_REQUIRE(!any_mn || pair_ok, "dmf_grouped_gemm_bf16_tc: mn_major operands need M >= 512 and N >= 128 in every group");
   if (pair_ok) return launch_gemm_tc2(groups, n_groups, epilogue, (cudaStream_t)s);
   for (int base = 0; base < n_groups; base += kMaxTcGroups) {
     TcGemmParams P;

@@ -32,6 +32,7 @@ constexpr size_t G2_SMEM_BYTES = 1024 + (size_t)G2_STAGES * 2 * G2_TILE + 8 * kE
 struct G2Group {
   TcEpi epi;
   int K;
+  int mn;              // both operands MN-major (A [K, M], B [K, N]): 64 x 64 boxes, two per operand and stage
   int tiles_n, splits, kb_per_split, num_kb;
   int atomic;          // fp32 output accumulated with red.add (split-K partial tiles, or accumulate-into-C mode)
   int item_start;
@@ -113,8 +114,19 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
           tc::mbar_wait(empty_bar + stage, phase ^ 1);
           if (tc::elect_one()) {
             if (leader) tc::mbar_expect_tx(full_bar + stage, 4 * G2_TILE);      // A + B-half of BOTH CTAs
-            tc2::tma_load_2d_pair(smemA + stage * G2_TILE, &P.tmA[it.gi], kb * 64, it.m0 + (int)rank * 128, full_bar + stage);
-            tc2::tma_load_2d_pair(smemB + stage * G2_TILE, &P.tmB[it.gi], kb * 64, it.n0 + (int)rank * 128, full_bar + stage);
+            if (!P.g[it.gi].mn) {
+              tc2::tma_load_2d_pair(smemA + stage * G2_TILE, &P.tmA[it.gi], kb * 64, it.m0 + (int)rank * 128, full_bar + stage);
+              tc2::tma_load_2d_pair(smemB + stage * G2_TILE, &P.tmB[it.gi], kb * 64, it.n0 + (int)rank * 128, full_bar + stage);
+            } else {
+              // MN-major: the stage holds [64 k-rows] x [2 x 64 contiguous m (or n)] per operand, chunks 8 KB apart
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                tc2::tma_load_2d_pair(smemA + stage * G2_TILE + c * (G2_TILE / 2), &P.tmA[it.gi],
+                                      it.m0 + (int)rank * 128 + c * 64, kb * 64, full_bar + stage);
+                tc2::tma_load_2d_pair(smemB + stage * G2_TILE + c * (G2_TILE / 2), &P.tmB[it.gi],
+                                      it.n0 + (int)rank * 128 + c * 64, kb * 64, full_bar + stage);
+              }
+            }
           }
           __syncwarp();
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
@@ -125,8 +137,12 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
     if (leader) {
       // whole warp, uniform control flow; one elected lane issues the tcgen05 instructions
       constexpr uint32_t idesc = tc::make_idesc_bf16(256, G2_BN, 0, 0);
+      constexpr uint32_t idesc_mn = tc::make_idesc_bf16(256, G2_BN, 1, 1);
       const uint64_t adesc0 = tc::make_smem_desc(tc::smem_u32(smemA), 16, 1024);
       const uint64_t bdesc0 = tc::make_smem_desc(tc::smem_u32(smemB), 16, 1024);
+      // MN-major view of a stage: LBO = distance of the two 64-wide chunks, SBO = next 8 k-rows; UMMA_K = 16 rows = 2 KB
+      const uint64_t adesc0_mn = tc::make_smem_desc(tc::smem_u32(smemA), G2_TILE / 2, 1024);
+      const uint64_t bdesc0_mn = tc::make_smem_desc(tc::smem_u32(smemB), G2_TILE / 2, 1024);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t n = 0;
@@ -136,15 +152,18 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
         tc::mbar_wait(acc_empty + buf, ((n >> 1) & 1) ^ 1);
         tc::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * G2_BN;
+        const bool mn = P.g[it.gi].mn != 0;
+        const uint32_t id = mn ? idesc_mn : idesc;
+        const uint64_t kstep = mn ? (uint64_t)(2048 >> 4) : (uint64_t)2;
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           tc::mbar_wait(full_bar + stage, phase);
           tc::tc_fence_after_sync();
-          const uint64_t ad = adesc0 + (uint64_t)((stage * G2_TILE) >> 4);
-          const uint64_t bd = bdesc0 + (uint64_t)((stage * G2_TILE) >> 4);
+          const uint64_t ad = (mn ? adesc0_mn : adesc0) + (uint64_t)((stage * G2_TILE) >> 4);
+          const uint64_t bd = (mn ? bdesc0_mn : bdesc0) + (uint64_t)((stage * G2_TILE) >> 4);
           if (tc::elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc2::umma_ss2(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+              tc2::umma_ss2(d_tmem, ad + kstep * k, bd + kstep * k, id, (kb > it.kb0 || k > 0) ? 1u : 0u);
             tc2::umma_commit2(empty_bar + stage);
           }
           __syncwarp();
@@ -218,11 +237,15 @@ int launch_gemm_tc2(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, 
     for (int i = 0; i < cnt; ++i) {
       const dmf_tc_gemm_desc& d = groups[base + i];
       if (d.M == 0 || d.N == 0) continue;
-      int rc = make_tmap_bf16_2d(&P.tmA[P.n], d.A, d.M, d.K, d.lda, 128);
+      // MN-major operands: the global tensors are [K, M] / [K, N]; boxes of 64 k-rows x 64 columns
+      int rc = d.mn_major ? make_tmap_bf16_2d(&P.tmA[P.n], d.A, d.K, d.M, d.lda, 64)
+                          : make_tmap_bf16_2d(&P.tmA[P.n], d.A, d.M, d.K, d.lda, 128);
       if (rc) return rc;
-      rc = make_tmap_bf16_2d(&P.tmB[P.n], d.B, d.N, d.K, d.ldb, 128);
+      rc = d.mn_major ? make_tmap_bf16_2d(&P.tmB[P.n], d.B, d.K, d.N, d.ldb, 64)
+                      : make_tmap_bf16_2d(&P.tmB[P.n], d.B, d.N, d.K, d.ldb, 128);
       if (rc) return rc;
       G2Group& g = P.g[P.n];
+      g.mn = d.mn_major ? 1 : 0;
       g.epi.out_f32 = d.out_f32; g.epi.ldo_f32 = d.ldo_f32;
       g.epi.out_bf16 = d.out_bf16; g.epi.ldo_bf16 = d.ldo_bf16;
       g.epi.out_t = d.out_bf16_t; g.epi.ldo_t = d.ldo_t;

@@ -50,8 +50,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2_6(float lo, float hi) {
 }
 
 // DBG (timing experiments, tools builds only): 1 = no softmax math / W stores, 2 = no PV MMAs, 4 = no S MMAs
-template <int DBG>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(B6_THREADS, 1)
+// CL = CTAs per cluster: 2 = one pair; 4 = TWO pairs (256 anchor rows) that consume the SAME column-tile stream: every ring
+// stage is fetched from L2 once and multicast into both pairs (the pairs take turns issuing), which halves the L2 -> SM
+// operand traffic -- the pair kernel needs 64 B/clk/SM of it at full MMA rate, more than the L2 delivers chip-wide.
+template <int DBG, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(B6_THREADS, 1)
 infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Ma, int Nb, int D, int num_kb, float scale,
                        const float* __restrict__ lseA, const float* __restrict__ lseB, float coef,
                        const float* __restrict__ gscale, long long diag_offset, const uint16_t* __restrict__ Bm,
@@ -77,10 +80,15 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = tc2::cluster_ctarank();
+  const uint32_t crank = tc2::cluster_ctarank();
+  const uint32_t rank = crank & 1;                           // rank inside the CTA pair (cta_group::2)
+  const uint32_t pairi = crank >> 1;                         // pair inside the cluster (0 when CL == 2)
   const bool leader = rank == 0;
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * pairi));  // commit targets: both CTAs of this pair
+  constexpr uint16_t all_mask = (uint16_t)((1u << CL) - 1);  // ring-stage release: every CTA of the cluster
+  const uint16_t mc_mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));   // CL == 4: same-rank CTA of both pairs
   const int nh = D >> 8;                                     // N = 256 halves of the output row (D = 256 or 512)
-  const int m0 = (blockIdx.x >> 1) * 128 + (int)rank * 64;   // first anchor row of THIS CTA
+  const int m0 = ((int)blockIdx.x / CL) * (64 * CL) + (int)crank * 64;   // first anchor row of THIS CTA
   // column split (gridDim.z): this cluster covers tiles [tz0, tz0 + ntiles) and red.adds its partial rows
   const int total_tiles = (Nb + B6_NT - 1) / B6_NT;
   const int tiles_per_split = (total_tiles + (int)gridDim.z - 1) / (int)gridDim.z;
@@ -92,7 +100,7 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
     tc::mbar_init(a_full, 1);
-    for (int s = 0; s < B6_STAGES; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < B6_STAGES; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, CL / 2); }
     for (int b = 0; b < 2; ++b) { tc::mbar_init(s_full + b, 1); tc::mbar_init(w_full + b, 16); }
     tc::mbar_init(pv_done, 1);
     tc::mbar_init(acc_full, 1);
@@ -120,7 +128,9 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tc::mbar_wait(empty_bar + stage, phase ^ 1);
         if (tc::elect_one()) {
           if (leader) tc::mbar_expect_tx(full_bar + stage, 2 * B6_STAGE);
-          tc2::tma_load_2d_pair(ring + stage * B6_STAGE, &tmB, kb * 64, jrow, full_bar + stage);
+          if (CL == 2) tc2::tma_load_2d_pair(ring + stage * B6_STAGE, &tmB, kb * 64, jrow, full_bar + stage);
+          else if ((uint32_t)(stage & 1) == pairi)
+            tc2::tma_load_2d_pair_mc(ring + stage * B6_STAGE, &tmB, kb * 64, jrow, full_bar + stage, mc_mask);
         }
         __syncwarp();
         if (++stage == B6_STAGES) { stage = 0; phase ^= 1; }
@@ -136,8 +146,12 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             tc::mbar_wait(empty_bar + stage, phase ^ 1);
             if (tc::elect_one()) {
               if (leader) tc::mbar_expect_tx(full_bar + stage, 2 * B6_STAGE);
-              tc2::tma_load_2d_pair(ring + stage * B6_STAGE, &tmB, h * 256 + (int)rank * 128 + c * 64, j0 + jh * 128,
-                                    full_bar + stage);
+              if (CL == 2)
+                tc2::tma_load_2d_pair(ring + stage * B6_STAGE, &tmB, h * 256 + (int)rank * 128 + c * 64, j0 + jh * 128,
+                                      full_bar + stage);
+              else if ((uint32_t)(stage & 1) == pairi)
+                tc2::tma_load_2d_pair_mc(ring + stage * B6_STAGE, &tmB, h * 256 + (int)rank * 128 + c * 64, j0 + jh * 128,
+                                         full_bar + stage, mc_mask);
             }
             __syncwarp();
             if (++stage == B6_STAGES) { stage = 0; phase ^= 1; }
@@ -173,12 +187,12 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
               for (int k = 0; k < 4; ++k) tc2::umma_ss2(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            tc2::umma_commit2(empty_bar + stage);
+            tc2::umma_commit2(empty_bar + stage, all_mask);
           }
           __syncwarp();
           if (++stage == B6_STAGES) { stage = 0; phase ^= 1; }
         }
-        if (tc::elect_one()) tc2::umma_commit2(s_full + (t & 1));
+        if (tc::elect_one()) tc2::umma_commit2(s_full + (t & 1), pair_mask);
         __syncwarp();
       };
       if (ntiles > 0) issue_s(0);
@@ -204,17 +218,17 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                                 (t | jh | k) != 0 ? 1u : 0u);
                 }
               }
-              tc2::umma_commit2(empty_bar + stage);
-              tc2::umma_commit2(empty_bar + stage + 1);
+              tc2::umma_commit2(empty_bar + stage, all_mask);
+              tc2::umma_commit2(empty_bar + stage + 1, all_mask);
             }
             __syncwarp();
             stage += 2;
             if (stage == B6_STAGES) { stage = 0; phase ^= 1; }
           }
-        if (tc::elect_one()) tc2::umma_commit2(pv_done);
+        if (tc::elect_one()) tc2::umma_commit2(pv_done, pair_mask);
         __syncwarp();
       }
-      if (tc::elect_one()) tc2::umma_commit2(acc_full);
+      if (tc::elect_one()) tc2::umma_commit2(acc_full, pair_mask);
       __syncwarp();
     }
   } else {
@@ -229,7 +243,7 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const float c0 = __ldg(lseB) * kLog2e6;                         // common exponent offset
     const float la2 = (row < Ma) ? __ldg(lseA + row) * kLog2e6 : c0;
     const float ai = ex2f6(la2 - c0);
-    const uint32_t w_full_leader = tc2::mapa(tc::smem_u32(w_full), 0);
+    const uint32_t w_full_leader = tc2::mapa(tc::smem_u32(w_full), crank & ~1u);
     // this thread's row inside a W k-block (K-major, 128-byte rows, 16-byte chunks XOR-swizzled by row & 7)
     uint8_t* wrow = smemW + ((cb >> 6) * B6_KB) + rloc * 128;
     const int sx = rloc & 7;
@@ -333,38 +347,60 @@ int dmf_infonce_bwd_bf16_tc6(const void* A, long long lda, int Ma, const float* 
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, Bm, Nb, D, ldb, 128);          // [128 rows x 64 cols] boxes for both products
   if (rc) return rc;
+  // cluster size: two pairs sharing one multicast column-tile stream unless the row set is a single pair's worth
+  static int cl_env = -1;
+  if (cl_env < 0) { const char* e = getenv("DMF_TC6_CL"); cl_env = e ? atoi(e) : 0; }
+  // Measured (B = 65536, D = 512): CL = 4 is SLOWER, 6.43 ms against 5.75 ms, and so is its TMA-only variant (5.29 against
+  // 4.17 ms; 33 resident 4-CTA clusters = 132 of 148 SMs).  The stream is bound by what one SM can TAKE IN (~58 B/clk/SM
+  // with all MMAs compiled out), not by the L2 slices, so halving the L2 reads buys nothing.  CL = 4 stays opt-in.
+  const int CL = (cl_env == 4 && Ma > 128) ? 4 : 2;
   int dbg = 0;
 #ifdef DMF_TC6_DBG
   { const char* e = getenv("DMF_TC6_DBG"); dbg = e ? atoi(e) : 0; }   // tools builds only (wrong results)
 #endif
-  auto kern = infonce_bwd_tc6_kernel<0>;
+  using kern_t = decltype(&infonce_bwd_tc6_kernel<0, 2>);
+  kern_t kern = CL == 4 ? infonce_bwd_tc6_kernel<0, 4> : infonce_bwd_tc6_kernel<0, 2>;
 #ifdef DMF_TC6_DBG
   switch (dbg) {
-    case 1: kern = infonce_bwd_tc6_kernel<1>; break;
-    case 2: kern = infonce_bwd_tc6_kernel<2>; break;
-    case 4: kern = infonce_bwd_tc6_kernel<4>; break;
-    case 6: kern = infonce_bwd_tc6_kernel<6>; break;
-    case 7: kern = infonce_bwd_tc6_kernel<7>; break;
+    case 1: kern = CL == 4 ? infonce_bwd_tc6_kernel<1, 4> : infonce_bwd_tc6_kernel<1, 2>; break;
+    case 2: kern = CL == 4 ? infonce_bwd_tc6_kernel<2, 4> : infonce_bwd_tc6_kernel<2, 2>; break;
+    case 4: kern = CL == 4 ? infonce_bwd_tc6_kernel<4, 4> : infonce_bwd_tc6_kernel<4, 2>; break;
+    case 6: kern = CL == 4 ? infonce_bwd_tc6_kernel<6, 4> : infonce_bwd_tc6_kernel<6, 2>; break;
+    case 7: kern = CL == 4 ? infonce_bwd_tc6_kernel<7, 4> : infonce_bwd_tc6_kernel<7, 2>; break;
     default: break;
   }
 #endif
-  static bool attr[8] = {false, false, false, false, false, false, false, false};
-  if (!attr[dbg & 7]) {
+  // resident clusters (set the attribute, then ask the occupancy API once per variant)
+  static int slots_tab[2][8] = {{0}};
+  int& slots = slots_tab[CL == 4][dbg & 7];
+  if (!slots) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B6_SMEM);
     if (e != cudaSuccess) return fail((int)e, "dmf_infonce_bwd(bf16 m128): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr[dbg & 7] = true;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL * 64, 1, 1);
+    cfg.blockDim = dim3(B6_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = B6_SMEM;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nc = 0;
+    e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+    if (e != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = CL == 4 ? 32 : 74; }
+    slots = nc;
+    if (getenv("DMF_VERBOSE")) fprintf(stderr, "dmf: infonce_bwd m128 CL=%d: %d resident clusters\n", CL, nc);
   }
-  const int blocks = (Ma + 127) / 128;
-  // Column split: when the row blocks do not fill whole waves of the 74 resident clusters (small local batches of a
+  const int blocks = (Ma + 64 * CL - 1) / (64 * CL);
+  // Column split: when the row blocks do not fill whole waves of the resident clusters (small local batches of a
   // data-parallel run), split the column set over gridDim.z; partial rows are accumulated with red.add.
   int nsplit = 1;
   const int total_tiles = (Nb + B6_NT - 1) / B6_NT;
   {
-    double best = (double)blocks / (double)(((blocks + 73) / 74) * 74);
+    double best = (double)blocks / (double)(((blocks + slots - 1) / slots) * slots);
     for (int ns = 2; ns <= 16 && best < 0.97; ++ns) {
       if (total_tiles / ns < 8) break;
       const int items = blocks * ns;
-      const double eff = (double)items / (double)(((items + 73) / 74) * 74);
+      const double eff = (double)items / (double)(((items + slots - 1) / slots) * slots);
       if (eff > best + 0.03) { best = eff; nsplit = ns; }
     }
     const int tps = (total_tiles + nsplit - 1) / nsplit;
@@ -374,7 +410,7 @@ int dmf_infonce_bwd_bf16_tc6(const void* A, long long lda, int Ma, const float* 
     cudaError_t e = cudaMemset2DAsync(dA, (size_t)ldda * sizeof(float), 0, (size_t)D * sizeof(float), (size_t)Ma, s);
     if (e != cudaSuccess) return fail((int)e, "dmf_infonce_bwd(bf16 m128): memset: %s", cudaGetErrorString(e));
   }
-  dim3 grid(2 * blocks, 1, nsplit);
+  dim3 grid(CL * blocks, 1, nsplit);
   kern<<<grid, B6_THREADS, B6_SMEM, s>>>(tmA, tmB, Ma, Nb, D, num_kb, scale, lseA, lseB, coef, gscale, diag_offset,
                                          (const uint16_t*)Bm, ldb, dA, ldda, accumulate);
   return launched("dmf_infonce_bwd(bf16 m128)");

@@ -47,6 +47,17 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       "l"(reinterpret_cast<uint64_t>(d)), "r"(bar_leader), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same load MULTICAST to the CTAs in `mask` (same shared-memory offset in each); every destination CTA's bytes
+// complete the mbarrier at this offset in the leader of ITS pair.
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* d, int c0, int c1, uint64_t* bar,
+                                                    uint16_t mask) {
+  const uint32_t bar_leader = tc::smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(tc::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(d)), "r"(bar_leader), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
@@ -66,11 +77,12 @@ __device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint6
       : "memory");
 }
 // arrive (once all prior MMAs of this thread retired) on the barrier at the same offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit2(uint64_t* bar) {
+// (mask = cluster ranks that receive the arrival; 3 = the two CTAs of a 2-CTA cluster)
+__device__ __forceinline__ void umma_commit2(uint64_t* bar, uint16_t mask = 3) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           tc::smem_u32(bar)),
-      "h"((uint16_t)3)
+      "h"(mask)
       : "memory");
 }
 }  // namespace tc2

@@ -85,7 +85,9 @@ class DisentangledSSL(LightningModule):
         all-gathers of the shared critic calls there, so that they overlap the private encoders)."""
         D = self.embed_dim
         if self.precision == "bf16":
-            need_t = torch.is_grad_enabled()
+            # transposed copies of the inputs feed the layer-0 wgrad only where it cannot read them MN-major
+            l0 = [m.weights()[0].shape for m in (self.encoder_x1s, self.encoder_x2s, self.encoder_x1, self.encoder_x2)]
+            need_t = torch.is_grad_enabled() and not all(ops.wgrad_mn_ok(n, k) for n, k in l0)
             bufs, bufTs, dims = [], [], []
             for parts in (rows1, rows2):
                 d = parts[0].shape[1]
@@ -240,9 +242,16 @@ class DisentangledSSL(LightningModule):
             # exactly zero, so neither its backward pass nor autograd bookkeeping is needed: one grouped Gram
             # launch + one all-reduce for the four calls (rows of P are already normalised for the critic)
             with torch.no_grad(), ops._Prof("ortho"):
-                E1n, E2n = ops.row_normalize(E1), ops.row_normalize(E2)
+                bo = wb and ops.wgrad_mn_ok(D, D)     # bf16 Gram straight from row-major bf16 rows
+                E1n, E2n = ops.row_normalize(E1, want_bf16=bo), ops.row_normalize(E2, want_bf16=bo)
                 if self.usezsx:     # the critic normalised [z | e]; the ortho term needs normalize(z)
-                    P1n, P2n = ops.row_normalize(P1), ops.row_normalize(P2)
+                    P1n, P2n = ops.row_normalize(P1, want_bf16=bo), ops.row_normalize(P2, want_bf16=bo)
+                    if bo:
+                        P1n, P2n = P1n[1], P2n[1]
+                elif bo and wbs:
+                    P1n, P2n = P1b, P2b             # the bf16 copies written for the specific critic
+                if bo:
+                    E1n, E2n = E1n[1], E2n[1]
                 ov = ops.ortho_values_nograd([(P1n[:B], E1n[:B]), (P2n[:B], E2n[:B]), (P1n[B:], E1n[B:]), (P2n[B:], E2n[B:])],
                                              self.precision)
                 loss_ortho = 0.5 * (ov[0] + ov[1]) + 0.5 * (ov[2] + ov[3])

@@ -7,6 +7,8 @@ process group -- nothing else.  ``precision`` is 'fp32' (FFMA path, 1e-5 parity)
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -93,7 +95,18 @@ def gemm_tc(descs: Sequence[dict], epilogue: int) -> None:
         g.M, g.N, g.K = d["M"], d["N"], d["K"]
         g.out_bf16_t, g.ldo_t = ptr(d.get("out_t")), d.get("ldo_t", 0)
         g.split_k = d.get("split_k", 1)
+        g.mn_major = d.get("mn_major", 0)
     check(lib.dmf_grouped_gemm_bf16_tc(arr, len(descs), epilogue, stream()))
+
+
+def wgrad_mn_ok(n_out: int, k_in: int) -> bool:
+    """True when the wgrad of a Linear(k_in -> n_out) runs on the CTA-pair kernel with MN-major operands, i.e. reads the
+    row-major bf16 activations dY [batch, n_out] and X [batch, k_in] as they are: no transposed copies are written
+    anywhere.  (``DMF_WGRAD_T=1`` forces the older transposed-copy path, for A/B timing.)"""
+    return n_out >= 512 and k_in >= 128 and n_out % 8 == 0 and not _WGRAD_T
+
+
+_WGRAD_T = bool(os.environ.get("DMF_WGRAD_T"))
 
 
 def cast_bf16(src: Tensor, dst: Optional[Tensor] = None, ldd: Optional[int] = None) -> Tensor:
@@ -368,6 +381,8 @@ class _GroupedMLP(torch.autograd.Function):
             raise L.DmfError("bf16 grouped MLP: evidence epilogue is only built for the fp32 path")
         dev = xs[0].device
         need_t = torch.is_grad_enabled() and any(w.requires_grad for ws in Ws for w in ws)
+        # layers whose wgrad reads the row-major activations MN-major need no transposed copy of their input
+        mn = [all(wgrad_mn_ok(*Ws[g][l].shape) for g in range(G)) for l in range(NL)]
         xTs = opts.get("xTs") or [None] * G
         out_b = opts.get("out_bf16") or [None] * G
         out_bt = opts.get("out_bf16T") or [None] * G
@@ -394,7 +409,7 @@ class _GroupedMLP(torch.autograd.Function):
                 M, K = x.shape
                 Kp, Mp = (K + 7) // 8 * 8, (M + 7) // 8 * 8
                 buf = torch.empty(M, Kp, dtype=torch.bfloat16, device=dev)
-                bufT = torch.empty(K, Mp, dtype=torch.bfloat16, device=dev) if need_t else None
+                bufT = torch.empty(K, Mp, dtype=torch.bfloat16, device=dev) if (need_t and not mn[0]) else None
                 check(lib.dmf_cast_dual_bf16(ptr(x), x.stride(0), ptr(buf), Kp, ptr(bufT), Mp, 0, M, K, stream()))
                 a0.append(buf[:, :K] if Kp != K else buf)
                 a0T.append(bufT)
@@ -429,7 +444,7 @@ class _GroupedMLP(torch.autograd.Function):
                     o = torch.empty(M, Np, dtype=torch.bfloat16, device=dev)
                     d.update(out_bf16=o, ldo_bf16=Np)
                     acts[g].append(o[:, :N] if Np != N else o)
-                    if need_t:
+                    if need_t and not mn[l + 1]:
                         oT = torch.empty(N, Mp, dtype=torch.bfloat16, device=dev)
                         d.update(out_t=oT, ldo_t=Mp)
                         actTs[g].append(oT)
@@ -449,6 +464,7 @@ class _GroupedMLP(torch.autograd.Function):
         dbs = [[None] * NL for _ in range(G)]
         dxs = [None] * G
         dYb, dYT = [None] * G, [None] * G
+        mn = [all(wgrad_mn_ok(*Ws[g][l].shape) for g in range(G)) for l in range(NL)]
         for g in range(G):
             M = acts[g][0].shape[0]
             N = Ws[g][-1].shape[0]
@@ -460,7 +476,7 @@ class _GroupedMLP(torch.autograd.Function):
                 dy = dy * (ctx.saved["outs"][g] > 0)
             Np, Mp = (N + 7) // 8 * 8, (M + 7) // 8 * 8
             b = torch.empty(M, Np, dtype=torch.bfloat16, device=dev)
-            bT = torch.empty(N, Mp, dtype=torch.bfloat16, device=dev)
+            bT = None if mn[NL - 1] else torch.empty(N, Mp, dtype=torch.bfloat16, device=dev)
             slot = _grad_slot(ctx.bs[g][NL - 1])
             db = slot if slot is not None else torch.zeros(N, dtype=torch.float32, device=dev)
             check(lib.dmf_cast_dual_bf16(ptr(dy), dy.stride(0), ptr(b), Np, ptr(bT), Mp, ptr(db), M, N, stream()))
@@ -475,14 +491,18 @@ class _GroupedMLP(torch.autograd.Function):
                 M, K = X.shape
                 N = dYb[g].shape[1]
                 Mp = (M + 7) // 8 * 8
-                XT = actTs[g][l]
-                if XT is None:
-                    XT = transpose_bf16(X)          # [K, Mp]
                 slot = _grad_slot(Ws[g][l]) if (N >= 512 and K >= 128) else None     # pair kernel can accumulate
                 wdirect.append(slot is not None)
                 dW = slot if slot is not None else torch.zeros(N, K, dtype=torch.float32, device=dev)
-                wdescs.append(dict(A=dYT[g], lda=dYT[g].stride(0), B=XT, ldb=XT.stride(0), out_f32=dW, ldo_f32=K,
-                                   M=N, N=K, K=M, split_k=-1 if slot is not None else 0))
+                if mn[l]:       # dW[n, k] = sum_m dY[m, n] X[m, k] straight from the row-major activations
+                    wdescs.append(dict(A=dYb[g], lda=dYb[g].stride(0), B=X, ldb=X.stride(0), out_f32=dW, ldo_f32=K,
+                                       M=N, N=K, K=M, split_k=-1 if slot is not None else 0, mn_major=1))
+                else:
+                    XT = actTs[g][l]
+                    if XT is None:
+                        XT = transpose_bf16(X)          # [K, Mp]
+                    wdescs.append(dict(A=dYT[g], lda=dYT[g].stride(0), B=XT, ldb=XT.stride(0), out_f32=dW, ldo_f32=K,
+                                       M=N, N=K, K=M, split_k=-1 if slot is not None else 0))
                 dWs[g][l] = None if slot is not None else dW
                 if l == 0 and not ctx.in_needs_grad[g] and ctx.extra_needs_grad[g]:
                     De = ctx.extra_cols[g]
@@ -497,8 +517,10 @@ class _GroupedMLP(torch.autograd.Function):
                     if l > 0:
                         Kp = (K + 7) // 8 * 8
                         dXb = torch.empty(M, Kp, dtype=torch.bfloat16, device=dev)
-                        dXT = torch.empty(K, Mp, dtype=torch.bfloat16, device=dev)
-                        d.update(out_bf16=dXb, ldo_bf16=Kp, out_t=dXT, ldo_t=Mp, mask=X, ldmask=X.stride(0))
+                        dXT = None if mn[l - 1] else torch.empty(K, Mp, dtype=torch.bfloat16, device=dev)
+                        d.update(out_bf16=dXb, ldo_bf16=Kp, mask=X, ldmask=X.stride(0))
+                        if dXT is not None:
+                            d.update(out_t=dXT, ldo_t=Mp)
                         nextb[g] = dXb[:, :K] if Kp != K else dXb
                         nextT[g] = dXT
                     else:
@@ -926,7 +948,8 @@ class _OrthoLoss(torch.autograd.Function):
 
 @torch.no_grad()
 def ortho_values_nograd(pairs: Sequence[Tuple[Tensor, Tensor]], precision: str = "fp32") -> Tensor:
-    """Values of ``ortho_loss`` for several (z1, zs) pairs whose rows are ALREADY L2-normalised, without autograd:
+    """Values of ``ortho_loss`` for several (z1, zs) pairs whose rows are ALREADY L2-normalised (fp32, or the bf16
+    copies the head kernels wrote), without autograd:
     one grouped split-K Gram launch (bf16 path) for all pairs, one all-reduce, one reduction.  Used by
     DisentangledSSL when the ortho weight is exactly zero (the term is only logged)."""
     L.require_device()
@@ -937,7 +960,15 @@ def ortho_values_nograd(pairs: Sequence[Tuple[Tensor, Tensor]], precision: str =
     if precision == "bf16" and R >= 512 and D >= 128:
         Rp = (R + 7) // 8 * 8
         descs = []
+        mn = wgrad_mn_ok(D, D)      # the Gram reads row-major bf16 rows MN-major: no transposed copies
         for i, (a, b) in enumerate(pairs):
+            if mn:
+                ab = a if a.dtype == torch.bfloat16 else cast_bf16(_f32c(a))
+                bb = b if b.dtype == torch.bfloat16 else cast_bf16(_f32c(b))
+                descs.append(dict(A=ab, lda=ab.stride(0), B=bb, ldb=bb.stride(0), out_f32=grams[i], ldo_f32=D, M=D, N=D,
+                                  K=R, split_k=0, mn_major=1))
+                continue
+            a, b = a.float(), b.float()
             aT = torch.empty(D, Rp, dtype=torch.bfloat16, device=dev)
             bT = torch.empty(D, Rp, dtype=torch.bfloat16, device=dev)
             cast_dual_bf16(a, None, 0, aT, Rp)
@@ -946,7 +977,7 @@ def ortho_values_nograd(pairs: Sequence[Tuple[Tensor, Tensor]], precision: str =
         gemm_tc(descs, L.EPI_NONE)
     else:
         for i, (a, b) in enumerate(pairs):
-            a, b = _f32c(a), _f32c(b)
+            a, b = _f32c(a.float()), _f32c(b.float())
             chunks = max(1, min(64, R // 512))
             rows = (R + chunks - 1) // chunks
             chunks = (R + rows - 1) // rows

@@ -88,6 +88,10 @@ typedef struct {
                    out_f32 alone (wgrad: K = batch); partial tiles are accumulated with red.add, so for
                    split_k >= 0 the CALLER must zero out_f32 first.  Honoured by the CTA-pair kernel only
                    (M >= 512 and N >= 128 in every group) */
+  int mn_major; /* 1: BOTH operands are given MN-major -- A is [K, M] (lda = pitch of a k-row), B is [K, N]:
+                   C[m,n] = sum_k A[k,m] * B[k,n].  This is wgrad read straight from the row-major activations
+                   (dW[n_out, k_in] = sum_batch dY[batch, n_out] * X[batch, k_in]): no transposed copies.  M, N
+                   multiples of 8.  CTA-pair kernel only (M >= 512 and N >= 128), else the call fails.          */
 } dmf_tc_gemm_desc;
 int dmf_grouped_gemm_bf16_tc(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, dmf_stream_t s);
 

@@ -220,9 +220,9 @@ class DisentangledSSL(LightningModule):
         # ONE op for the four critic calls (the reference discards loss_x / loss_y of the two specific-critic calls:
         # their intra-view blocks are skipped); under data parallelism the four calls share one column-sum all-reduce
         # and one LSE all-gather
-        if normal or pr_spec != pr:
+        if normal or pr_spec != pr or Dc != D:
             # Gaussian samples are not unit vectors (the shared calls then take the exact online-max kernels), and the
-            # two groups may run at different precisions: one op per group
+            # two groups may run at different precisions or widths ([z | e] with usezsx): one op per group
             o_sh = self.critic.multi(pairs[:2], pres=pres[:2], unit_norm=not normal, reduce=not dp, diagnostics=[True, True])
             o_sp = self.critic.multi(pairs[2:], pres=pres[2:], unit_norm=True, reduce=not dp, diagnostics=[False, False],
                                      precision=pr_spec)

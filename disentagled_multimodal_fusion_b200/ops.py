@@ -640,6 +640,42 @@ class GatheredPair:
         self.works = []
 
 
+_SIDE = {}
+_FORK = os.environ.get("DMF_FORK", "1") != "0"
+
+
+class _Fork:
+    """Deal INDEPENDENT kernel launches round-robin over the current stream and one side stream: the tail wave and the
+    prologue of consecutive launches then overlap instead of serialising on stream order (each InfoNCE launch fills the
+    GPU with one CTA per SM, so nothing else is shared).  Inside a CUDA-graph capture the fork / join become graph edges.
+    Nothing may be allocated inside ``with fork.next():`` (the caching allocator is per stream)."""
+
+    def __init__(self, dev):
+        self.cur = torch.cuda.current_stream(dev)
+        self.side = None
+        if _FORK:
+            key = (dev.index if dev.index is not None else torch.cuda.current_device())
+            if key not in _SIDE:
+                _SIDE[key] = torch.cuda.Stream(device=dev)
+            self.side = _SIDE[key]
+            self.side.wait_stream(self.cur)
+        self.k = 0
+
+    def resync(self):
+        """the side stream must also see what the current stream has waited for since the fork (NCCL gathers)"""
+        if self.side is not None:
+            self.side.wait_stream(self.cur)
+
+    def next(self):
+        use_side = self.side is not None and (self.k & 1) == 1
+        self.k += 1
+        return torch.cuda.stream(self.side if use_side else self.cur)
+
+    def join(self):
+        if self.side is not None:
+            self.cur.wait_stream(self.side)
+
+
 class _InfoNCE(torch.autograd.Function):
     """forward(cfg, z0_0, z1_0, z0_1, z1_1, ...) -> out [ncalls, 3] = (loss, loss_x, loss_y) per critic call.
     cfg = (temperature, precision, bound, pres, reduce, diag_flags).  All calls of a step go through ONE invocation so
@@ -653,6 +689,8 @@ class _InfoNCE(torch.autograd.Function):
         nc = len(zs) // 2
         zs = [_f32c(z) for z in zs]
         Bl, D = zs[0].shape
+        if any(tuple(z.shape) != (Bl, D) for z in zs):
+            raise L.DmfError("infonce_multi: every critic input of one batched op must have the same [rows, width]")
         dev = zs[0].device
         world = dist.get_world_size() if _dist_on() else 1
         rank = dist.get_rank() if world > 1 else 0
@@ -682,13 +720,20 @@ class _InfoNCE(torch.autograd.Function):
                                                   off, ptr(rs[k]), ptr(cs[k]), off, ptr(dg[k]), stream()))
             for c in range(nc):
                 pres[c].wait()
-                a0, a1, g0, g1 = pres[c].a0, pres[c].a1, pres[c].g0, pres[c].g1
-                b = rbase[c]
-                with _Prof("rowlse_x4"):
-                    rowcol(a0, g1, b, 0)         # cross block: rows -> view-0 anchors, columns -> view-1 anchors
+            # the launches write disjoint rows of rs / cs / dg: dealt over two streams so that their tails overlap
+            fork = _Fork(dev)
+            with _Prof("rowlse_x4"):
+                for c in range(nc):
+                    a0, a1, g0, g1 = pres[c].a0, pres[c].a1, pres[c].g0, pres[c].g1
+                    b = rbase[c]
+                    with fork.next():
+                        rowcol(a0, g1, b, 0)         # cross block: rows -> view-0 anchors, columns -> view-1 anchors
                     if diag_flags[c]:
-                        rowcol(a0, g0, b + 1, 1)     # intra-view blocks: only the no-grad diagnostics loss_x / loss_y need them
-                        rowcol(a1, g1, b + 2, 1)     # (the reference's row max is the self-similarity 1/T = the fixed shift)
+                        with fork.next():
+                            rowcol(a0, g0, b + 1, 1)     # intra-view blocks: only the no-grad diagnostics loss_x / loss_y need them
+                        with fork.next():
+                            rowcol(a1, g1, b + 2, 1)     # (the reference's row max is the self-similarity 1/T = the fixed shift)
+                fork.join()
             if world > 1:
                 with _Prof("colsum_allreduce"):
                     dist.all_reduce(cs)              # ONE collective for the column sums of every call
@@ -752,6 +797,7 @@ class _InfoNCE(torch.autograd.Function):
         gout = gout.contiguous().float()
         coef = scale / (2.0 * Bg)
         grads = []
+        work = []
         for c in range(nc):
             a0, a1, g0, g1 = saved[4 * c: 4 * c + 4]
             gs = gout[c, 0:1]                           # only the loss has a gradient; diagnostics are no-grad
@@ -762,15 +808,18 @@ class _InfoNCE(torch.autograd.Function):
                     g0T, g1T = transpose_bf16(g0), transpose_bf16(g1)
             else:       # fp32 path, or the bf16 kernel that reads the column block MN-major (D = 256 / 512)
                 g0T = g1T = None
-            with _Prof("infonce_bwd"):
-                check(lib.dmf_infonce_bwd(ptr(a0), a0.stride(0), Bl, ptr(lse[c, 0]), ptr(g1), g1.stride(0), ptr(g1T),
-                                          g1T.stride(0) if g1T is not None else 0, Bg, ptr(lse_all[c, 1]), D, scale, coef, ptr(gs),
-                                          off, ptr(dz0), D, 0, dt, stream()))
-            with _Prof("infonce_bwd"):
-                check(lib.dmf_infonce_bwd(ptr(a1), a1.stride(0), Bl, ptr(lse[c, 1]), ptr(g0), g0.stride(0), ptr(g0T),
-                                          g0T.stride(0) if g0T is not None else 0, Bg, ptr(lse_all[c, 0]), D, scale, coef, ptr(gs),
-                                          off, ptr(dz1), D, 0, dt, stream()))
+            work.append((a0, lse[c, 0], g1, g1T, lse_all[c, 1], gs, dz0))
+            work.append((a1, lse[c, 1], g0, g0T, lse_all[c, 0], gs, dz1))
             grads += [dz0, dz1]
+        # 2 * nc independent launches (every one writes its own dz): dealt over two streams, tails overlap
+        fork = _Fork(dev)
+        with _Prof("infonce_bwd"):
+            for a, la, g, gT, lb, gs, dz in work:
+                with fork.next():
+                    check(lib.dmf_infonce_bwd(ptr(a), a.stride(0), Bl, ptr(la), ptr(g), g.stride(0), ptr(gT),
+                                              gT.stride(0) if gT is not None else 0, Bg, ptr(lb), D, scale, coef, ptr(gs),
+                                              off, ptr(dz), D, 0, dt, stream()))
+            fork.join()
         return (None, *grads)
 
 

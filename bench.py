@@ -440,6 +440,27 @@ def run_small_config(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def gpu_local_cpus(dev_index):
+    """CPUs NVML reports as local to this GPU (its NUMA node), restricted to the CPUs this process may use."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = getattr(torch.cuda.get_device_properties(dev_index), "uuid", None)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode()) if uuid is not None else None
+        except Exception:  # noqa: BLE001
+            h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(dev_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_gpu(args, rank, world, local_rank):
     import disentagled_multimodal_fusion_b200 as pkg
     from disentagled_multimodal_fusion_b200 import ops, _lib
@@ -480,7 +501,17 @@ def run_gpu(args, rank, world, local_rank):
             parts = [host_chunk(c, Bg // 8) for c in range(r * 8 // w, (r + 1) * 8 // w)]
             return {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
         return host_chunk(100 + r, Bg // w)
-    host = {k: v.pin_memory() for k, v in host_rows(rank, world).items()}
+    # One process per GPU: the pinned staging buffers are allocated while the process is bound to the CPUs of the GPU's
+    # own NUMA node (first touch), so the H2D DMA of every rank reads node-local memory instead of crossing the socket
+    # interconnect.  The binding is dropped again before the CPU baseline arm (which uses every host thread).
+    rows_h = host_rows(rank, world)
+    host_unbound = {k: v.pin_memory() for k, v in rows_h.items()} if args.e2e_diag else None
+    all_cpus = os.sched_getaffinity(0)
+    local_cpus = gpu_local_cpus(local_rank) if (world > 1 and not args.no_numa_bind) else None
+    if local_cpus:
+        os.sched_setaffinity(0, local_cpus)
+    host = {k: v.clone().pin_memory() for k, v in rows_h.items()}
+    del rows_h
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
     # The batch a user hands to training_step is (x1, x2[, y]); the augmented views v1, v2 are made ON THE DEVICE by
@@ -664,22 +695,46 @@ def run_gpu(args, rank, world, local_rank):
     bufs = [with_views({k: torch.empty_like(v, device=dev) for k, v in host.items()}) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     gsteps = [None, None]
+    # The H2D prefetch of the next batch is started from INSIDE the step: an external event recorded by a node of the
+    # graph at the start of the InfoNCE backward (long kernels; the launch-bound front of the step -- noise draws,
+    # casts, small GEMMs, the embedding all-gathers -- is over by then).  Started at the step boundary instead, the
+    # 67 MB / rank copy cost the 8-GPU step 1.6 ms (13.3 -> 14.9 ms) although it takes only 2.9 ms by itself.
+    mid_ev = [torch.cuda.Event(external=True), torch.cuda.Event(external=True)] if not args.h2d_at_step_start else [None, None]
     if gstep is not None:
         try:
             for i in range(2):
                 for k, v in host.items():
                     bufs[i][k].copy_(v)
                 augment_views(bufs[i])
-                gsteps[i] = GraphedStep(lambda i=i: step(bufs[i], capturable=True), warmup=1, pool=gstep.pool(),
-                                        stream=torch.cuda.current_stream())
+                fired = []
+
+                def marker(name, i=i, fired=fired):
+                    if name == "infonce_bwd" and not fired and mid_ev[i] is not None and torch.cuda.is_current_stream_capturing():
+                        mid_ev[i].record()
+                        fired.append(1)
+                ops.ON_PHASE = marker
+                try:
+                    gsteps[i] = GraphedStep(lambda i=i: step(bufs[i], capturable=True), warmup=1, pool=gstep.pool(),
+                                            stream=torch.cuda.current_stream())
+                finally:
+                    ops.ON_PHASE = None
+                if not fired:
+                    mid_ev[i] = None
         except Exception:  # noqa: BLE001
             gsteps = [None, None]
+            ops.ON_PHASE = None
             torch.cuda.synchronize()
+
+    copy_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    step_t0 = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    h2d_src = {"host": host}
 
     def prefetch(i):
         with torch.cuda.stream(copy_stream):
-            for k, v in host.items():
+            copy_ev[0].record(copy_stream)
+            for k, v in h2d_src["host"].items():
                 bufs[i][k].copy_(v, non_blocking=True)
+            copy_ev[1].record(copy_stream)
             ready[i].record(copy_stream)
     state = {"i": 0, "losses": []}
     d2h = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -692,13 +747,20 @@ def run_gpu(args, rank, world, local_rank):
         # previous step's loss (after its copy event) -- the usual one-step-lagged logging of a training loop,
         # so the host never idles the GPU while it waits for a scalar.
         i = state["i"]
+        late = copy and gsteps[i] is not None and mid_ev[i] is not None
         if copy:
             torch.cuda.current_stream().wait_event(ready[i])
-            copy_stream.wait_stream(torch.cuda.current_stream())   # next copy must not overwrite a buffer in use
-            prefetch(i ^ 1)
+            if not late:
+                copy_stream.wait_stream(torch.cuda.current_stream())   # next copy must not overwrite a buffer in use
+                prefetch(i ^ 1)
         model.draw_noise(Bl, dev, out=noise_bufs)
         augment_views(bufs[i])
+        step_t0[i].record()
         out = gsteps[i]() if gsteps[i] is not None else step(bufs[i])
+        if late:
+            # bufs[i ^ 1] was last read by step i-1, which precedes this step's marker in stream order
+            copy_stream.wait_event(mid_ev[i])
+            prefetch(i ^ 1)
         d2h[i].copy_(out.reshape(1), non_blocking=True)         # device->host read of the step's loss
         d2h_ev[i].record()
         d2h_pending[i] = True
@@ -720,6 +782,16 @@ def run_gpu(args, rank, world, local_rank):
     ms_e2e = timed(args.steps, e2e_step)
     e2e_drain()
     e2e_value = Bg * args.steps / (ms_e2e / 1e3)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+    h2d_copy_ms = max_over_ranks(copy_ev[0].elapsed_time(copy_ev[1]))     # the last in-loop copy, device-timed
+    # how far into its step the last prefetch started (the graph's marker event releases it)
+    h2d_start_ms = step_t0[state["i"] ^ 1].elapsed_time(copy_ev[0])
     e2e_diag = None
     if args.e2e_diag:
         # where does the end-to-end arm lose time against the device-resident one?  Same loop without the H2D copies,
@@ -729,8 +801,20 @@ def run_gpu(args, rank, world, local_rank):
         prefetch(state["i"])
         ms_nosync = timed(args.steps, lambda: e2e_step(sync=False))
         e2e_drain()
-        e2e_diag = {"ms_per_step_no_h2d": ms_nocopy / args.steps, "ms_per_step_no_host_read": ms_nosync / args.steps}
+        e2e_diag = {"ms_per_step_no_h2d": ms_nocopy / args.steps, "ms_per_step_no_host_read": ms_nosync / args.steps,
+                    "h2d_copy_ms_in_loop": h2d_copy_ms, "h2d_start_ms_into_step": h2d_start_ms,
+                    "numa_bound_cpus": len(local_cpus) if local_cpus else None}
+        if local_cpus:      # the same loop fed from pinned buffers allocated BEFORE the NUMA binding
+            h2d_src["host"] = host_unbound
+            prefetch(state["i"])
+            ms_unbound = timed(args.steps, e2e_step)
+            e2e_drain()
+            e2e_diag["ms_per_step_unbound_pinned"] = ms_unbound / args.steps
+            e2e_diag["h2d_copy_ms_unbound"] = max_over_ranks(copy_ev[0].elapsed_time(copy_ev[1]))
+            h2d_src["host"] = host
 
+    if local_cpus:
+        os.sched_setaffinity(0, all_cpus)       # the CPU baseline arm below uses every host thread
     if rank != 0:
         return
     pk = peaks()
@@ -805,7 +889,7 @@ def run_gpu(args, rank, world, local_rank):
         "step_frac_of_sustained_bf16": step_flops / (ms / args.steps * 1e-3) / 1e12 / (pk["tf_sust"] * world),
         "roofline": roof, "roofline_k1": roof_k1, "roofline_k3": roof_k3, "cpu_baseline": cpu,
         "loss_check": lcheck, "phase_ms": phases, "e2e_diag": e2e_diag,
-        "step_ms": {"value": step_marks[0], "e2e": step_marks[-1]},
+        "step_ms": {"value": step_marks[0], "e2e": step_marks[1]},
     }
     print(json.dumps(line), flush=True)
 
@@ -824,6 +908,12 @@ def main():
                     help="BASELINE.json config: c5 (default) = the headline workload; c1-c4 = the small launch-bound configs "
                          "(single GPU; samples/s + launches/step beside the CPU port at the same batch)")
     ap.add_argument("--e2e-diag", action="store_true", help="extra end-to-end loops without H2D / without the host read")
+    ap.add_argument("--nccl-priority", default="high", choices=["high", "normal"],
+                    help="priority of the NCCL stream (high: collective CTAs take the next free SM under the InfoNCE tiles)")
+    ap.add_argument("--h2d-at-step-start", action="store_true",
+                    help="start the H2D prefetch at the step boundary instead of at the graph's mid-step marker (A/B)")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="N > 1: do not bind each rank to the CPUs of its GPU's NUMA node while it allocates pinned memory")
     ap.add_argument("--no-kernel-rooflines", action="store_true", help="skip the live K1 / K3 roofline measurements")
     ap.add_argument("--no-loss-check", dest="loss_check", action="store_false",
                     help="skip the cross-N loss / gradient-norm check step")
@@ -845,7 +935,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from disentagled_multimodal_fusion_b200.dp import init_process_group_nccl
+        init_process_group_nccl(torch.device("cuda", local_rank), high_priority=args.nccl_priority == "high")
     try:
         # the whole run lives on one non-default stream (see dp.GraphedStep: CUDA-graph capture of the backward
         # pass needs every autograd leaf to have been touched on a capturable stream only)

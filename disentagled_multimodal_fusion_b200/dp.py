@@ -125,6 +125,24 @@ class FlatParams:
         self._lr_on_device = float(lr)
 
 
+def init_process_group_nccl(device, high_priority: bool = True) -> None:
+    """``dist.init_process_group("nccl")`` with the collectives on a HIGH-PRIORITY stream.  The InfoNCE kernels queue
+    several CTAs per SM (one resident at a time: they take the whole shared memory); at normal priority the CTAs of an
+    all-gather issued meanwhile only get an SM once that whole queue has been dispatched, so the gather the next
+    critic call waits for sits behind a full kernel.  At high priority the block scheduler hands the next free SM to
+    the collective, which then overlaps the tiles.  (Captured into the step's CUDA graph as the node's priority.)"""
+    opts = None
+    if high_priority:
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:  # noqa: BLE001
+            opts = None
+    if opts is not None:
+        dist.init_process_group("nccl", device_id=device, pg_options=opts)
+    else:
+        dist.init_process_group("nccl", device_id=device)
+
+
 class GraphedStep:
     """A whole training step (forward, backward, NCCL collectives, fused optimizer) captured ONCE into a CUDA graph
     and replayed: one graph launch per step instead of ~600 kernel launches, which is what keeps an 8-GPU strong-

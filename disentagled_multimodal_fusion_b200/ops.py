@@ -34,6 +34,8 @@ def _dist_on() -> bool:
 PROFILE_ON = False
 PROFILE_EXTERNAL = False     # events recorded as nodes of a CUDA graph under capture (timed on every replay)
 PROFILE: dict = {}
+ON_PHASE = None              # optional callback(name) at the start of every phase region (e.g. record a marker event
+                             # into the CUDA graph under capture: bench.py starts its H2D prefetch at such a marker)
 
 
 class _Prof:
@@ -41,6 +43,8 @@ class _Prof:
         self.name = name
 
     def __enter__(self):
+        if ON_PHASE is not None:
+            ON_PHASE(self.name)
         if PROFILE_ON:
             self.s = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
             self.e = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
@@ -633,10 +637,15 @@ class GatheredPair:
             else:
                 self.g0, self.g1 = self.a0, self.a1
 
-    def wait(self):
+    def wait(self, also: Optional["torch.cuda.Stream"] = None):
+        """make the current stream (and ``also``: the side stream of a ``_Fork``) wait for the gathers"""
         with _Prof("gather_wait"):
             for w in self.works:
                 w.wait()
+        if also is not None and self.works:
+            with torch.cuda.stream(also):
+                for w in self.works:
+                    w.wait()
         self.works = []
 
 
@@ -718,14 +727,15 @@ class _InfoNCE(torch.autograd.Function):
             def rowcol(A, Bm, k, sym):
                 check(lib.dmf_infonce_rowcol_sums(ptr(A), A.stride(0), Bl, ptr(Bm), Bm.stride(0), Bg, D, scale, shift, sym,
                                                   off, ptr(rs[k]), ptr(cs[k]), off, ptr(dg[k]), stream()))
-            for c in range(nc):
-                pres[c].wait()
-            # the launches write disjoint rows of rs / cs / dg: dealt over two streams so that their tails overlap
+            # the launches write disjoint rows of rs / cs / dg: dealt over two streams so that their tails overlap; the
+            # gathers of call c are awaited (by both streams) right before its launches, so later gathers stay in flight
+            # under the tiles of the earlier calls
             fork = _Fork(dev)
-            with _Prof("rowlse_x4"):
-                for c in range(nc):
-                    a0, a1, g0, g1 = pres[c].a0, pres[c].a1, pres[c].g0, pres[c].g1
-                    b = rbase[c]
+            for c in range(nc):
+                pres[c].wait(also=fork.side)
+                a0, a1, g0, g1 = pres[c].a0, pres[c].a1, pres[c].g0, pres[c].g1
+                b = rbase[c]
+                with _Prof("rowlse_x4"):
                     with fork.next():
                         rowcol(a0, g1, b, 0)         # cross block: rows -> view-0 anchors, columns -> view-1 anchors
                     if diag_flags[c]:
@@ -733,7 +743,8 @@ class _InfoNCE(torch.autograd.Function):
                             rowcol(a0, g0, b + 1, 1)     # intra-view blocks: only the no-grad diagnostics loss_x / loss_y need them
                         with fork.next():
                             rowcol(a1, g1, b + 2, 1)     # (the reference's row max is the self-similarity 1/T = the fixed shift)
-                fork.join()
+                    if c == nc - 1:
+                        fork.join()
             if world > 1:
                 with _Prof("colsum_allreduce"):
                     dist.all_reduce(cs)              # ONE collective for the column sums of every call

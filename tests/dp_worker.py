@@ -20,8 +20,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
     import disentagled_multimodal_fusion_b200 as pkg
+    from disentagled_multimodal_fusion_b200.dp import init_process_group_nccl
+    init_process_group_nccl(dev)
     from disentagled_multimodal_fusion_b200 import ops, dp as dpmod
     from disentagled_multimodal_fusion_b200.dp import FlatParams, shard_rows
 

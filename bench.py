@@ -832,7 +832,10 @@ def run_gpu(args, rank, world, local_rank):
             cap = {}
     same_shape = world == 1 and Bg == 65536 and prec == "bf16"
     if "infonce_bwd" in prof:
+        # one timed region per step brackets the 8 backward launches (4 critic calls x 2 sides), which are dealt over
+        # two streams so that consecutive launches overlap their tail / first wave: average = span / launches
         n, tot_ms = prof["infonce_bwd"]
+        n *= 8
         avg_ms = tot_ms / n
         flops = 2.0 * Bl * Bg * EMB
         ach = flops / (avg_ms * 1e-3) / 1e12
@@ -840,7 +843,8 @@ def run_gpu(args, rank, world, local_rank):
                 "frac": ach / pk["tf_sust"], "traffic": cap.get("dram_bytes") if same_shape else None, "launches": n,
                 "avg_ms": avg_ms, "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
                 "share_of_step": (tot_ms / prof_steps) / (ms / args.steps),
-                "timed_in": f"{prof_steps} eager steps after warm-up (CUDA events on the launching stream)",
+                "timed_in": f"{prof_steps} eager steps after warm-up (CUDA events on the launching stream around each step's 8 "
+                            "backward launches, fork to join of the two streams they are dealt over)",
                 "traffic_source": "bytes/launch, ncu --set full capture of this kernel at this shape (profiles/r02_traffic.json)" if same_shape and cap else None,
                 "executed_over_algorithmic_flops": cap.get("executed_over_algorithmic_flops"),
                 "tensor_pipe_active_pct_ncu": cap.get("tensor_pipe_active_pct") if same_shape else None,

@@ -220,7 +220,8 @@ extern "C" int dmf_grouped_gemm_bf16_tc(const dmf_tc_gemm_desc* groups, int n_gr
       g.epi.out_bf16 = d.out_bf16; g.epi.ldo_bf16 = d.ldo_bf16;
       g.epi.out_t = d.out_bf16_t; g.epi.ldo_t = d.ldo_t;
       g.epi.bias = d.bias; g.epi.mask = d.mask_bf16; g.epi.ldmask = d.ldmask;
-      g.epi.M = d.M; g.epi.N = d.N; g.K = d.K;
+      g.epi.M = d.M; g.epi.N = d.N;
+      g.epi.fast = tc_epi_fast_ok(g.epi); g.K = d.K;
       P.tile_start[P.n] = tiles;
       tiles += ((d.M + TC_BM - 1) / TC_BM) * ((d.N + TC_BN - 1) / TC_BN);
       ++P.n;

@@ -187,14 +187,23 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
       tc::mbar_wait(acc_full + buf, (n >> 1) & 1);
       tc::tc_fence_after_sync();
       if (it.kb1 > it.kb0) {
+        // the TMEM read of chunk c + 1 is in flight while chunk c goes through the staging tile
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * G2_BN + (uint32_t)(ch * 128);
+        const int nb0 = it.n0 + ch * 128;
+        uint32_t ra[32], rb[32];
+        auto emit = [&](const uint32_t (&r)[32], int c) {
+          if (g.atomic) tc_epilogue_chunk<EPI, true>(g.epi, r, row0, lane, nb0 + c * 32, it.ks == 0, my_stage);
+          else tc_epilogue_chunk<EPI, false>(g.epi, r, row0, lane, nb0 + c * 32, true, my_stage);
+        };
+        tc::tmem_ld_32x32(t0, ra);
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * G2_BN + (uint32_t)(ch * 128 + c * 32), r);
+        for (int c2 = 0; c2 < 2; ++c2) {
           tc::tmem_ld_wait();
-          const int nbase = it.n0 + ch * 128 + c * 32;
-          if (g.atomic) tc_epilogue_chunk<EPI, true>(g.epi, r, row0, lane, nbase, it.ks == 0, my_stage);
-          else tc_epilogue_chunk<EPI, false>(g.epi, r, row0, lane, nbase, true, my_stage);
+          tc::tmem_ld_32x32(t0 + (uint32_t)(c2 * 64 + 32), rb);
+          emit(ra, 2 * c2);
+          tc::tmem_ld_wait();
+          if (c2 == 0) tc::tmem_ld_32x32(t0 + 64, ra);
+          emit(rb, 2 * c2 + 1);
         }
       }
       tc::tc_fence_before_sync();
@@ -251,6 +260,7 @@ int launch_gemm_tc2(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, 
       g.epi.out_t = d.out_bf16_t; g.epi.ldo_t = d.ldo_t;
       g.epi.bias = d.bias; g.epi.mask = d.mask_bf16; g.epi.ldmask = d.ldmask;
       g.epi.M = d.M; g.epi.N = d.N;
+      g.epi.fast = tc_epi_fast_ok(g.epi);
       g.K = d.K;
       g.num_kb = (d.K + 63) / 64;
       g.tiles_n = (d.N + G2_BN - 1) / G2_BN;

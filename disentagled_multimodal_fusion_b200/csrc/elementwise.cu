@@ -800,7 +800,7 @@ cast_dual_kernel(const float* __restrict__ src, long long lds, uint16_t* __restr
 }
 
 // column sums of a bf16 matrix (bias gradient of a hidden layer from the bf16 dgrad output):
-// out[n] += sum_m X[m, n]; CTA = 64 columns x 256 rows, 4-byte loads (two columns per thread)
+// out[n] += sum_m X[m, n]; CTA = 64 columns x 256 rows, 4-byte loads (two columns per thread): ragged / unaligned shapes
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const uint16_t* __restrict__ X, long long ld, int M, int N, float* __restrict__ out) {
   __shared__ float red[8][64];
@@ -830,6 +830,46 @@ colsum_bf16_kernel(const uint16_t* __restrict__ X, long long ld, int M, int N, f
     const int cc = blockIdx.x * 64 + threadIdx.x;
     if (cc < N) atomicAdd(out + cc, s);
   }
+}
+
+// Aligned shapes (N % 256 == 0, 16-byte aligned rows): CTA = 256 columns x `rows_per_cta` rows; a warp reads one 512-byte
+// row segment per instruction (16 bytes = 8 columns per lane), four rows in flight per lane.
+__global__ void __launch_bounds__(256)
+colsum_bf16_wide_kernel(const uint16_t* __restrict__ X, long long ld, int M, int rows_per_cta, float* __restrict__ out) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(M, r0 + rows_per_cta);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  auto add8 = [&](const uint4 w) {
+    const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[2 * j] += __uint_as_float(u[j] << 16);
+      acc[2 * j + 1] += __uint_as_float(u[j] & 0xFFFF0000u);
+    }
+  };
+  const uint16_t* p = X + (long long)(r0 + rl) * ld + c;
+  const long long step = 8 * ld;
+  int r = r0 + rl;
+  for (; r + 24 < r1; r += 32, p += 4 * step) {
+    const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(p + step));
+    const uint4 w2 = __ldg(reinterpret_cast<const uint4*>(p + 2 * step));
+    const uint4 w3 = __ldg(reinterpret_cast<const uint4*>(p + 3 * step));
+    add8(w0); add8(w1); add8(w2); add8(w3);
+  }
+  for (; r < r1; r += 8, p += step) add8(__ldg(reinterpret_cast<const uint4*>(p)));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][lane * 8 + j] = acc[j];
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+  atomicAdd(out + blockIdx.x * 256 + threadIdx.x, s);
 }
 
 inline int grid_for(long long n, int threads = 256) {
@@ -1044,6 +1084,14 @@ extern "C" int dmf_cast_dual_bf16(const float* src, long long lds, uint16_t* dst
 extern "C" int dmf_colsum_bf16(const uint16_t* X, long long ld, int M, int N, float* out, dmf_stream_t s) {
   DMF_REQUIRE(X && out && M >= 0 && N >= 0, "dmf_colsum_bf16: bad arguments");
   if (M == 0 || N == 0) return 0;
+  if ((N & 255) == 0 && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    // enough CTAs to fill the GPU a few times over, at least 64 rows each
+    int rows = 512;
+    while (rows > 64 && (long long)(N / 256) * ((M + rows - 1) / rows) < 4 * kNumSMs) rows >>= 1;
+    dim3 gridw(N / 256, (M + rows - 1) / rows);
+    colsum_bf16_wide_kernel<<<gridw, 256, 0, (cudaStream_t)s>>>(X, ld, M, rows, out);
+    return launched("dmf_colsum_bf16");
+  }
   dim3 grid((N + 63) / 64, (M + 255) / 256);
   DMF_REQUIRE(grid.y <= 65535, "dmf_colsum_bf16: too many rows (%d)", M);
   colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(X, ld, M, N, out);

@@ -46,12 +46,12 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// Lean path of a full 32 x 32 chunk (no ragged edges, no atomics, no transposed copy; alignment checked on the host):
+// Lean path of a full 32 x 32 chunk (no ragged edges, no transposed copy; alignment checked on the host):
 // the same staging tile and lane mapping as the general path below, with every store a full-width vector store and the
 // destination pointers advanced by a constant -- ~125 instructions per chunk against ~540 for the general path, which
 // (ncu, K = 1024: 17 k warp instructions per 256 x 256 tile at 29 % issue utilisation) made every layer with K <= 1024
 // EPILOGUE-bound: ~14 k cycles per tile next to a 4-8 k cycle main loop.
-template <int EPI>
+template <int EPI, bool kAtomic>
 __device__ __forceinline__ void tc_epilogue_chunk_fast(const TcEpi& g, const uint32_t (&r)[32], int row0, int lane, int nbase,
                                                        bool add_bias, float* stage) {
   const int c = (lane & 7) * 4;
@@ -92,7 +92,8 @@ __device__ __forceinline__ void tc_epilogue_chunk_fast(const TcEpi& g, const uin
       if ((m2.y & 0x7FFF0000u) == 0u || (m2.y & 0x80000000u)) v.w = 0.f;
     }
     if (d32) {
-      *reinterpret_cast<float4*>(d32) = v;
+      if (kAtomic) red_add_v4(d32, v.x, v.y, v.z, v.w);       // split-K partial tile / accumulate-into-grad (wgrad)
+      else *reinterpret_cast<float4*>(d32) = v;
       d32 += s32;
     }
     if (d16) {
@@ -115,8 +116,8 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& g, const uint32_t
   if (row0 >= g.M || nbase >= g.N) return;          // warp-uniform
   const int nvalid = min(32, g.N - nbase);
   const int mvalid = min(32, g.M - row0);
-  if (!kAtomic && g.fast && nvalid == 32 && mvalid == 32) {
-    tc_epilogue_chunk_fast<EPI>(g, r, row0, lane, nbase, add_bias, stage);
+  if (g.fast && nvalid == 32 && mvalid == 32) {
+    tc_epilogue_chunk_fast<EPI, kAtomic>(g, r, row0, lane, nbase, add_bias, stage);
     return;
   }
   // ReLU-mask words of the whole chunk are fetched up front (8 independent 8-byte loads in flight) so the

@@ -422,7 +422,7 @@ def test_tc_gemm_mn_major_wgrad(dmf, Mb, Nout, Kin, split):
 def test_cast_dual_and_colsum_bf16(dmf):
     ops, Lb = dmf.ops, dmf._lib
     gen = torch.Generator().manual_seed(21)
-    for R, Cc in ((1000, 520), (64, 64), (333, 47)):
+    for R, Cc in ((1000, 520), (64, 64), (333, 47), (4096, 512), (1003, 256), (70000, 512)):    # last three: wide column-sum kernel
         x = torch.randn(R, Cc, generator=gen).to(DEV)
         Cp, Rp = (Cc + 7) // 8 * 8, (R + 7) // 8 * 8
         dst = torch.zeros(R, Cp, dtype=torch.bfloat16, device=DEV)

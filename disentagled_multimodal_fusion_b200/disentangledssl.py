@@ -30,6 +30,12 @@ class ProbabilisticEncoder(nn.Module):
         self.vmfkappa = vmfkappa
 
 
+class StackedNoise(list):
+    """The four (w, v) vMF noise draws as views into row-stacked buffers (``stacked`` = (w1, v1, w2, v2), each [2B, .]:
+    rows [0, B) = the draw for the original batch, rows [B, 2B) = the draw for the augmented batch of that modality)."""
+    stacked = None
+
+
 class DisentangledSSL(LightningModule):
     def __init__(self, feature_encoders=None, output_dim=[100, 100], dropout=0., a=1,
                  optimizer=torch.optim.Adam, hidden_dim=512, embed_dim=100,
@@ -149,8 +155,17 @@ class DisentangledSSL(LightningModule):
             return [torch.randn(B, D, device=device) for _ in range(4)]
         if self.noise_mode == "device":
             self.noise_seed += 1
-            return [ops.vmf_draw(B, D, self.vmfkappa, 0x5EED + self.noise_seed, i, device, out=None if out is None else out[i])
-                    for i in range(4)]
+            if out is None:
+                # draws 0 / 2 (modality 1: original, augmented rows) and 1 / 3 (modality 2) land in the two halves of ONE
+                # buffer each -- the row-stacked layout the vMF head consumes -- so forward() needs no torch.cat
+                ws = [torch.empty(2 * B, 1, dtype=torch.float32, device=device) for _ in range(2)]
+                vs = [torch.empty(2 * B, D - 1, dtype=torch.float32, device=device) for _ in range(2)]
+                out = StackedNoise([(ws[i & 1][(i >> 1) * B:(i >> 1) * B + B], vs[i & 1][(i >> 1) * B:(i >> 1) * B + B])
+                                    for i in range(4)])
+                out.stacked = (ws[0], vs[0], ws[1], vs[1])
+            for i in range(4):
+                ops.vmf_draw(B, D, self.vmfkappa, 0x5EED + self.noise_seed, i, device, out=out[i])
+            return out
         res = []
         for _ in range(4):
             w, v = draw_vmf_noise(B, D, float(self.vmfkappa))
@@ -183,10 +198,13 @@ class DisentangledSSL(LightningModule):
                 bf = [None, None]
             else:
                 # vMF reparameterised samples (noise rows follow the stacking: modality 1 <- draws 0,2; modality 2 <- 1,3)
-                w1 = torch.cat([noise[0][0], noise[2][0]], 0)
-                vv1 = torch.cat([noise[0][1], noise[2][1]], 0)
-                w2 = torch.cat([noise[1][0], noise[3][0]], 0)
-                vv2 = torch.cat([noise[1][1], noise[3][1]], 0)
+                if isinstance(noise, StackedNoise) and noise.stacked is not None and noise.stacked[0].shape[0] == 2 * B:
+                    w1, vv1, w2, vv2 = noise.stacked          # drawn in place into the row-stacked layout
+                else:
+                    w1 = torch.cat([noise[0][0], noise[2][0]], 0)
+                    vv1 = torch.cat([noise[0][1], noise[2][1]], 0)
+                    w2 = torch.cat([noise[1][0], noise[3][0]], 0)
+                    vv2 = torch.cat([noise[1][1], noise[3][1]], 0)
                 Z1, Z2 = ops.vmf_rsample(E1, w1, vv1, want_bf16=wb), ops.vmf_rsample(E2, w2, vv2, want_bf16=wb)
                 if wb:
                     (Z1, Z1b), (Z2, Z2b) = Z1, Z2
@@ -194,6 +212,7 @@ class DisentangledSSL(LightningModule):
                 else:
                     bf = [None, None]
             st["pairs"] = [(Z1[:B], Z2[:B]), (Z1[B:], Z2[B:])]
+            st["Z"] = (Z1, Z2)
             # the shared critic inputs exist now: launch their embedding all-gathers (asynchronous NCCL) BEFORE the
             # private encoders run, so that the gathers overlap those GEMMs
             st["pres"] = [ops.GatheredPair(a, b, pr, bf16=f) for (a, b), f in zip(st["pairs"], bf)]
@@ -228,7 +247,10 @@ class DisentangledSSL(LightningModule):
                                      precision=pr_spec)
             out = torch.cat([o_sh, o_sp], 0)
         else:
-            out = self.critic.multi(pairs, pres=pres, unit_norm=True, reduce=not dp, diagnostics=[True, True, False, False])
+            # the four calls read row blocks of the four row-stacked tensors (original rows on top of the augmented ones)
+            Z1, Z2 = st["Z"]
+            out = self.critic.multi_stacked([Z1, Z2, P1n, P2n], [(0, 0, 1, 0), (0, B, 1, B), (2, 0, 2, B), (3, 0, 3, B)], B,
+                                            pres=pres, unit_norm=True, reduce=not dp, diagnostics=[True, True, False, False])
         joint_loss = 0.5 * (out[0, 0] + out[1, 0])
         loss_x = 0.5 * (out[0, 1] + out[1, 1]).detach()
         loss_y = 0.5 * (out[0, 2] + out[1, 2]).detach()

@@ -49,6 +49,14 @@ class SupConLoss(nn.Module):
         return (self.temperature / self.base_temperature) * out
 
 
+    def multi_stacked(self, stacks, layout, rows, pres=None, unit_norm=False, reduce=True, diagnostics=None, precision=None):
+        """``multi`` on row-stacked inputs (ops.infonce_stacked): call c = rows [ra, ra+rows) of stacks[ia] vs rows
+        [rb, rb+rows) of stacks[ib] for layout[c] = (ia, ra, ib, rb)."""
+        out = ops.infonce_stacked(stacks, layout, rows, self.temperature, precision or self.precision, unit_norm=unit_norm,
+                                  pres=pres, reduce=reduce, diagnostics=diagnostics)
+        return (self.temperature / self.base_temperature) * out
+
+
 def ortho_loss(z1, zs, norm=True, temp=0.1):
     if not norm:
         raise NotImplementedError('Please set norm=True')

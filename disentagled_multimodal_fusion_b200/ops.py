@@ -694,9 +694,18 @@ class _InfoNCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, *zs):
         L.require_device()
-        temperature, precision, bound, pres, reduce, diag_flags = cfg
-        nc = len(zs) // 2
+        temperature, precision, bound, pres, reduce, diag_flags = cfg[:6]
+        layout = cfg[6] if len(cfg) > 6 else None
         zs = [_f32c(z) for z in zs]
+        ctx.layout = layout
+        if layout is not None:
+            # zs are ROW-STACKED tensors; call c contrasts rows [ra, ra + Bl) of stack ia with rows [rb, rb + Bl) of stack
+            # ib.  Slicing here, inside the Function, keeps autograd from embedding every half into a zero-filled
+            # full-size gradient and adding the halves up again (5 extra passes over each stacked tensor per step).
+            Bl = layout[0][4]
+            ctx.stack_shapes = [tuple(z.shape) for z in zs]
+            zs = [t for (ia, ra, ib, rb, _) in layout for t in (zs[ia][ra:ra + Bl], zs[ib][rb:rb + Bl])]
+        nc = len(zs) // 2
         Bl, D = zs[0].shape
         if any(tuple(z.shape) != (Bl, D) for z in zs):
             raise L.DmfError("infonce_multi: every critic input of one batched op must have the same [rows, width]")
@@ -809,11 +818,24 @@ class _InfoNCE(torch.autograd.Function):
         coef = scale / (2.0 * Bg)
         grads = []
         work = []
+        layout = ctx.layout
+        if layout is not None:
+            # gradients of the row-stacked inputs: every critic call writes its two row blocks in place
+            covered = [0] * len(ctx.stack_shapes)
+            for (ia, ra, ib, rb, bl) in layout:
+                covered[ia] += bl
+                covered[ib] += bl
+            sgr = [(torch.empty if covered[i] == shp[0] else torch.zeros)(shp, dtype=torch.float32, device=dev)
+                   for i, shp in enumerate(ctx.stack_shapes)]
         for c in range(nc):
             a0, a1, g0, g1 = saved[4 * c: 4 * c + 4]
             gs = gout[c, 0:1]                           # only the loss has a gradient; diagnostics are no-grad
-            dz0 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
-            dz1 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
+            if layout is not None:
+                ia, ra, ib, rb, _ = layout[c]
+                dz0, dz1 = sgr[ia][ra:ra + Bl], sgr[ib][rb:rb + Bl]
+            else:
+                dz0 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
+                dz1 = torch.empty(Bl, D, dtype=torch.float32, device=dev)
             if dt == 1 and lib.dmf_infonce_bwd_needs_transposed(D):
                 with _Prof("transpose_gathered"):
                     g0T, g1T = transpose_bf16(g0), transpose_bf16(g1)
@@ -831,6 +853,8 @@ class _InfoNCE(torch.autograd.Function):
                                               gT.stride(0) if gT is not None else 0, Bg, ptr(lb), D, scale, coef, ptr(gs),
                                               off, ptr(dz), D, 0, dt, stream()))
             fork.join()
+        if layout is not None:
+            return (None, *sgr)
         return (None, *grads)
 
 
@@ -844,6 +868,21 @@ def infonce_multi(pairs: Sequence[Tuple[Tensor, Tensor]], temperature: float = 0
     flags = tuple(bool(d) for d in (diagnostics if diagnostics is not None else [True] * len(pairs)))
     flat = [z for p in pairs for z in p]
     return _InfoNCE.apply((float(temperature), precision, bound, list(pres) if pres is not None else None, reduce, flags), *flat)
+
+
+def infonce_stacked(stacks: Sequence[Tensor], layout: Sequence[Tuple[int, int, int, int]], rows: int,
+                    temperature: float = 0.07, precision: str = "fp32", unit_norm: bool = False,
+                    pres: Optional[Sequence["GatheredPair"]] = None, reduce: bool = True,
+                    diagnostics: Optional[Sequence[bool]] = None) -> Tensor:
+    """``infonce_multi`` on ROW-STACKED inputs: critic call c contrasts rows [ra, ra + rows) of ``stacks[ia]`` with rows
+    [rb, rb + rows) of ``stacks[ib]`` for ``layout[c] = (ia, ra, ib, rb)``.  Same values and gradients as slicing the
+    stacks and calling ``infonce_multi`` -- but the row blocks never pass through autograd as separate tensors, so the
+    backward writes each block of d stack in place (no zero-filled embeddings, no adds)."""
+    bound = (1.0 / float(temperature)) if unit_norm else None
+    flags = tuple(bool(d) for d in (diagnostics if diagnostics is not None else [True] * len(layout)))
+    lay = tuple((int(ia), int(ra), int(ib), int(rb), int(rows)) for ia, ra, ib, rb in layout)
+    return _InfoNCE.apply((float(temperature), precision, bound, list(pres) if pres is not None else None, reduce, flags, lay),
+                          *stacks)
 
 
 def infonce(z0: Tensor, z1: Tensor, temperature: float = 0.07, precision: str = "fp32",

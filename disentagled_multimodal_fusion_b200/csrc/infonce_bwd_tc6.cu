@@ -145,8 +145,10 @@ infonce_bwd_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int c = 0; c < 2; ++c) {
             tc::mbar_wait(empty_bar + stage, phase ^ 1);
             if (tc::elect_one()) {
-              if (leader) tc::mbar_expect_tx(full_bar + stage, 2 * B6_STAGE);
-              if (CL == 2)
+              // DBG & 8 (timing only): skip the block this CTA already fetched as an S operand (j half == rank, own d set)
+              if (leader) tc::mbar_expect_tx(full_bar + stage, (DBG & 8) ? B6_STAGE : 2 * B6_STAGE);
+              if ((DBG & 8) && jh == (int)rank) {
+              } else if (CL == 2)
                 tc2::tma_load_2d_pair(ring + stage * B6_STAGE, &tmB, h * 256 + (int)rank * 128 + c * 64, j0 + jh * 128,
                                       full_bar + stage);
               else if ((uint32_t)(stage & 1) == pairi)
@@ -367,12 +369,14 @@ int dmf_infonce_bwd_bf16_tc6(const void* A, long long lda, int Ma, const float* 
     case 4: kern = CL == 4 ? infonce_bwd_tc6_kernel<4, 4> : infonce_bwd_tc6_kernel<4, 2>; break;
     case 6: kern = CL == 4 ? infonce_bwd_tc6_kernel<6, 4> : infonce_bwd_tc6_kernel<6, 2>; break;
     case 7: kern = CL == 4 ? infonce_bwd_tc6_kernel<7, 4> : infonce_bwd_tc6_kernel<7, 2>; break;
+    case 8: kern = infonce_bwd_tc6_kernel<8, 2>; break;      // CL = 2 only: duplicate PV operand blocks not fetched
+    case 15: kern = infonce_bwd_tc6_kernel<15, 2>; break;
     default: break;
   }
 #endif
   // resident clusters (set the attribute, then ask the occupancy API once per variant)
-  static int slots_tab[2][8] = {{0}};
-  int& slots = slots_tab[CL == 4][dbg & 7];
+  static int slots_tab[2][16] = {{0}};
+  int& slots = slots_tab[CL == 4][dbg & 15];
   if (!slots) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B6_SMEM);
     if (e != cudaSuccess) return fail((int)e, "dmf_infonce_bwd(bf16 m128): cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -81,6 +81,10 @@ _SIGS = {
     "dmf_rowlse": ([c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_f, c_p, c_p, c_ll, c_p, c_p, c_sz, c_i, c_p], c_i),
     "dmf_infonce_rowcol_sums": ([c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_f, c_f, c_i, c_i, c_p, c_p, c_ll, c_p, c_p], c_i),
     "dmf_rowlse_workspace_bytes": ([c_i, c_i], c_sz),
+    "dmf_infonce_rowcol_sums_store": ([c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_f, c_f, c_i, c_i, c_p, c_p, c_ll, c_p, c_p, c_p], c_i),
+    "dmf_infonce_e_bytes": ([c_i, c_i], c_sz),
+    "dmf_infonce_bwd_stored_work_floats": ([c_i, c_i], c_sz),
+    "dmf_infonce_bwd_stored": ([c_p, c_i, c_i, c_p, c_p, c_f, c_p, c_ll, c_i, c_i, c_f, c_p, c_ll, c_p, c_ll, c_i, c_p, c_p], c_i),
     "dmf_infonce_finalize": ([c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_f, c_i, c_p, c_p, c_p], c_i),
     "dmf_infonce_bwd": ([c_p, c_ll, c_i, c_p, c_p, c_ll, c_p, c_ll, c_i, c_p, c_i, c_f, c_f, c_p, c_ll, c_p, c_ll,
                          c_i, c_i, c_p], c_i),

@@ -167,6 +167,23 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, long long rows, long l
   return 0;
 }
 
+// [rows, 64] bf16 block-row view of the stored InfoNCE probabilities, box = 32 rows x 32 columns (64-byte rows in
+// shared memory, 64B swizzle): the store side of infonce_fwd_tc4.cu
+int make_tmap_bf16_2d_box32_sw64(CUtensorMap* out, const void* base, long long rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(-1, "TMA store target needs a 16B-aligned base");
+  cuuint64_t gdim[2] = {64u, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {128u};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled (store map) failed (CUresult %d) rows=%lld", (int)r, rows);
+  return 0;
+}
+
 }  // namespace dmf
 
 using namespace dmf;

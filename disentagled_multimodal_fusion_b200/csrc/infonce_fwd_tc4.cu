@@ -27,6 +27,9 @@ constexpr int F4_TILE = 128 * 64 * 2;   // 16 KB: [128 rows x 64 bf16]
 constexpr int F4_STAGES = 5;
 constexpr int F4_BN = 256;              // column tile of the pair
 constexpr float kLog2eF4 = 1.4426950408889634f;
+// anchors (8 slots) + ring + 2 KB (barriers, TMEM slot, merge buffer) + 8 x 2 KB E staging + 1 KB alignment slack
+constexpr size_t F4_SMEM_MAX = 1024 + (size_t)(8 + F4_STAGES) * F4_TILE + 2048 + 8 * 2048;
+static_assert(F4_SMEM_MAX <= 232448, "forward carve-up exceeds the opt-in shared-memory window");
 
 __device__ __forceinline__ float f4_exp2(float x) {
   float y;
@@ -95,10 +98,39 @@ struct F4Args {
   float* col_sum;     // [Nb]  += (caller zeroes); may be NULL when !sym (rows only)
   long long diag_offset;
   float* diag_out;    // [Ma] raw scaled similarity s_{i, diag_offset + i}
+  int store_e;        // sym = 0 only: keep e_ij as bf16 in [128 x 64] blocks, block (ib, jb) at (ib * njb + jb) * 16 KB,
+  int njb;            //   written through the tensor map tmE (the operand of the stored-probability backward, infonce_bwd_e.cu)
 };
 
+// 32 consecutive e values of one row -> bf16 -> this thread's 64-byte row of the warp's [32 x 64 B] staging tile (16-byte
+// chunk index XOR ((row >> 1) & 3): the 64B TMA swizzle, conflict-free for 16-byte stores of 8 consecutive rows)
+__device__ __forceinline__ void f4_stage_e(uint32_t stage_row, int lane, const float (&e)[32]) {
+  const uint32_t x = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[k]) : "f"(e[g * 8 + 2 * k + 1]), "f"(e[g * 8 + 2 * k]));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (((uint32_t)g ^ x) << 4)), "r"(w[0]), "r"(w[1]),
+                 "r"(w[2]), "r"(w[3])
+                 : "memory");
+  }
+}
+// [32 rows x 32 columns] box of the staging tile -> E block rows (c0 = column inside the 64-wide block, c1 = block row)
+__device__ __forceinline__ void f4_tma_store_2d(const CUtensorMap* d, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(d)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void f4_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void f4_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F4_THREADS, 1)
-rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const F4Args P) {
+rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmE, const F4Args P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smemA = smem;                                    // num_kb tiles: this CTA's 128 anchor rows
@@ -110,7 +142,8 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* s_full = empty_bar + F4_STAGES;   // per CTA [2]
   uint64_t* s_empty = s_full + 2;             // leader [2]: 16 softmax warps of the pair drained the buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
-  float* mrg = reinterpret_cast<float*>(tmem_slot + 4);   // [128] row-sum merge of the two column halves
+  float* mrg = reinterpret_cast<float*>(tmem_slot + 4);   // [3][128] row-sum / diag merge of the two column halves
+  uint8_t* estage = smem + (8 + F4_STAGES) * F4_TILE + 2048;   // 8 x 2 KB staging tiles of the E stores (store_e only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = tc2::cluster_ctarank();
@@ -212,6 +245,7 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     bool has_diag = false;
     const long long dj = (P.diag_offset >= 0 && rvalid) ? P.diag_offset + row : -1;
     const uint32_t s_empty_leader0 = tc2::mapa(tc::smem_u32(s_empty), 0);
+    const uint32_t my_stage = tc::smem_u32(estage) + (uint32_t)(sw * 2048);
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       int J = w0 + t_begin + t;
@@ -227,7 +261,23 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         tc::tmem_ld_wait();
         const int nbase = j0 + c * 32;
         const int nvalid = P.Nb - nbase;
-        if (nvalid <= 0) continue;                 // warp-uniform
+        // E: the warp's [32 rows x 32 columns] piece goes to block rows q*32.. of block (m0 / 128, nbase / 64), column
+        // (c & 1) * 32 inside the block
+        const int e_c0 = (c & 1) * 32, e_c1 = ((m0 >> 7) * P.njb + (nbase >> 6)) * 128 + q * 32;
+        if (nvalid <= 0) {                         // warp-uniform
+          if (P.store_e) {
+            float z[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) z[j] = 0.f;
+            if (lane == 0) f4_store_wait_read();   // the previous store of this warp has read the staging tile
+            __syncwarp();
+            f4_stage_e(my_stage + (uint32_t)(lane * 64), lane, z);
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) f4_tma_store_2d(&tmE, my_stage, e_c0, e_c1);
+          }
+          continue;
+        }
         if (dj >= nbase && dj < nbase + 32) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -245,6 +295,14 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 32; j += 4) { ps0 += e[j]; ps1 += e[j + 1]; ps2 += e[j + 2]; ps3 += e[j + 3]; }
         l += (ps0 + ps1) + (ps2 + ps3);
+        if (P.store_e) {
+          if (lane == 0) f4_store_wait_read();     // the previous store of this warp has read the staging tile
+          __syncwarp();
+          f4_stage_e(my_stage + (uint32_t)(lane * 64), lane, e);
+          tc::fence_proxy_async_smem();            // generic-proxy stores -> visible to the TMA engine (async proxy)
+          __syncwarp();
+          if (lane == 0) f4_tma_store_2d(&tmE, my_stage, e_c0, e_c1);
+        }
         if (want_cols) {
           const float cs = warp_colsum32(e, lane);
           if (lane < nvalid) atomicAdd(P.col_sum + nbase + lane, cs);
@@ -254,6 +312,7 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       __syncwarp();
       if (lane == 0) tc2::mbar_arrive_cluster(s_empty_leader0 + (uint32_t)(buf * 8));
     }
+    if (P.store_e && lane == 0) f4_store_wait_all();   // the E stores must have left shared memory before the CTA exits
     // merge the two column halves of each row, then one atomicAdd per row (column splits share rows)
     if (ch == 1) {
       mrg[rloc] = l;
@@ -288,7 +347,19 @@ using namespace dmf;
 extern "C" int dmf_infonce_rowcol_sums(const void* A, long long lda, int Ma, const void* Bm, long long ldb, int Nb, int D,
                                        float scale, float shift, int sym, int row0_global, float* row_sum, float* col_sum,
                                        long long diag_offset, float* diag_out, dmf_stream_t s) {
+  return dmf_infonce_rowcol_sums_store(A, lda, Ma, Bm, ldb, Nb, D, scale, shift, sym, row0_global, row_sum, col_sum,
+                                       diag_offset, diag_out, nullptr, s);
+}
+
+// The same pass; E != NULL (sym = 0 only) additionally keeps e_ij = exp(s_ij - shift) as bf16 in the blocked layout of
+// dmf_infonce_bwd_stored (dmf_infonce_e_bytes(Ma, Nb) bytes, every byte written: zeros outside [Ma x Nb]).
+extern "C" int dmf_infonce_rowcol_sums_store(const void* A, long long lda, int Ma, const void* Bm, long long ldb, int Nb,
+                                             int D, float scale, float shift, int sym, int row0_global, float* row_sum,
+                                             float* col_sum, long long diag_offset, float* diag_out, void* E,
+                                             dmf_stream_t s) {
   DMF_REQUIRE(A && Bm && row_sum, "dmf_infonce_rowcol_sums: null argument");
+  DMF_REQUIRE(!E || (!sym && (reinterpret_cast<uintptr_t>(E) & 15) == 0),
+              "dmf_infonce_rowcol_sums_store: E needs sym = 0 and a 16-byte aligned base");
   DMF_REQUIRE(Ma >= 0 && Nb >= 1, "dmf_infonce_rowcol_sums: bad shape Ma=%d Nb=%d", Ma, Nb);
   DMF_REQUIRE(D % 64 == 0 && D >= 64 && D <= 512, "dmf_infonce_rowcol_sums: D=%d must be a multiple of 64 in [64,512]", D);
   DMF_REQUIRE(!sym || (col_sum && (row0_global % 256) == 0 && row0_global + Ma <= Nb),
@@ -300,11 +371,13 @@ extern "C" int dmf_infonce_rowcol_sums(const void* A, long long lda, int Ma, con
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, Bm, Nb, D, ldb, 128);
   if (rc) return rc;
-  const size_t smem = 1024 + (size_t)(num_kb + F4_STAGES) * F4_TILE + 256 + 2048;
+  // carve-up: anchors, ring, barriers + merge buffer (2 KB); with E the ring sits after 8 anchor slots' worth of space
+  // so that the 8 x 2 KB staging tiles have a fixed, 1024-aligned offset
+  const size_t smem = E ? F4_SMEM_MAX : 1024 + (size_t)(num_kb + F4_STAGES) * F4_TILE + 256 + 2048;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(rowcol_sum_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(1024 + (size_t)(8 + F4_STAGES) * F4_TILE + 256 + 2048));
+                                         (int)F4_SMEM_MAX);
     if (e != cudaSuccess) return fail((int)e, "dmf_infonce_rowcol_sums: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr = true;
   }
@@ -318,6 +391,15 @@ extern "C" int dmf_infonce_rowcol_sums(const void* A, long long lda, int Ma, con
   P.total_tiles = (Nb + F4_BN - 1) / F4_BN;
   P.row_sum = row_sum; P.col_sum = col_sum;
   P.diag_offset = diag_offset; P.diag_out = diag_out;
+  P.store_e = E ? 1 : 0;
+  P.njb = 4 * P.total_tiles;
+  CUtensorMap tmE;
+  if (E) {
+    rc = make_tmap_bf16_2d_box32_sw64(&tmE, E, 2LL * ((Ma + 255) / 256) * P.njb * 128);
+    if (rc) return rc;
+  } else {
+    tmE = tmA;      // never dereferenced
+  }
   const int pairs = (Ma + 255) / 256;
   const int window = sym ? P.total_tiles / 2 + 1 : P.total_tiles;
   // split the tile window over blockIdx.y so that pairs * nsplit fills whole waves of the 74 clusters
@@ -334,6 +416,6 @@ extern "C" int dmf_infonce_rowcol_sums(const void* A, long long lda, int Ma, con
   }
   P.tiles_per_split = (window + nsplit - 1) / nsplit;
   dim3 grid(2 * pairs, nsplit);
-  rowcol_sum_tc4_kernel<<<grid, F4_THREADS, smem, (cudaStream_t)s>>>(tmA, tmB, P);
+  rowcol_sum_tc4_kernel<<<grid, F4_THREADS, smem, (cudaStream_t)s>>>(tmA, tmB, tmE, P);
   return launched("dmf_infonce_rowcol_sums");
 }

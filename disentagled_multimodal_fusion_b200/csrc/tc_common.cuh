@@ -180,5 +180,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, i
 // 2D bf16 row-major tensor [rows, cols] (leading dimension ld elements); box = box_rows x 64 cols,
 // 128B swizzle, OOB -> zero fill.  Returns 0 on success.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows);
+// [rows, 64] bf16, box = 32 rows x 32 cols, 64B swizzle (TMA store of the InfoNCE probability blocks)
+int make_tmap_bf16_2d_box32_sw64(CUtensorMap* out, const void* base, long long rows);
 
 }  // namespace dmf

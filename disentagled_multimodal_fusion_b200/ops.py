@@ -651,6 +651,11 @@ class GatheredPair:
 
 _SIDE = {}
 _FORK = os.environ.get("DMF_FORK", "1") != "0"
+# Keep exp(s - shift) of every cross block (bf16, B_local x B bytes x 2 per critic call) between forward and backward so
+# that the backward is one product per gradient instead of recompute + product (dmf_infonce_bwd_stored).  "0" restores the
+# recompute kernels; DMF_STORE_E_MAX_GB bounds the bytes one batched op may keep (beyond it the calls fall back one by one).
+_STORE_E = os.environ.get("DMF_STORE_E", "1") != "0"
+_STORE_E_MAX = float(os.environ.get("DMF_STORE_E_MAX_GB", "64")) * 2 ** 30
 
 
 class _Fork:
@@ -733,9 +738,17 @@ class _InfoNCE(torch.autograd.Function):
             cs = torch.zeros(sum(nrow), Bg, dtype=torch.float32, device=dev)
             dg = torch.empty(sum(nrow), Bl, dtype=torch.float32, device=dev)
 
-            def rowcol(A, Bm, k, sym):
-                check(lib.dmf_infonce_rowcol_sums(ptr(A), A.stride(0), Bl, ptr(Bm), Bm.stride(0), Bg, D, scale, shift, sym,
-                                                  off, ptr(rs[k]), ptr(cs[k]), off, ptr(dg[k]), stream()))
+            # stored probabilities (world == 1: both gradient directions; data parallel: the local-row direction)
+            ebytes = int(lib.dmf_infonce_e_bytes(Bl, Bg)) if (_STORE_E and D in (256, 512)
+                                                              and any(ctx.needs_input_grad[1:])) else 0
+            estore = [None] * nc
+            if ebytes:
+                for c in range(min(nc, int(_STORE_E_MAX // ebytes))):
+                    estore[c] = torch.empty(ebytes, dtype=torch.uint8, device=dev)
+
+            def rowcol(A, Bm, k, sym, E=None):
+                check(lib.dmf_infonce_rowcol_sums_store(ptr(A), A.stride(0), Bl, ptr(Bm), Bm.stride(0), Bg, D, scale, shift,
+                                                        sym, off, ptr(rs[k]), ptr(cs[k]), off, ptr(dg[k]), ptr(E), stream()))
             # the launches write disjoint rows of rs / cs / dg: dealt over two streams so that their tails overlap; the
             # gathers of call c are awaited (by both streams) right before its launches, so later gathers stay in flight
             # under the tiles of the earlier calls
@@ -746,7 +759,7 @@ class _InfoNCE(torch.autograd.Function):
                 b = rbase[c]
                 with _Prof("rowlse_x4"):
                     with fork.next():
-                        rowcol(a0, g1, b, 0)         # cross block: rows -> view-0 anchors, columns -> view-1 anchors
+                        rowcol(a0, g1, b, 0, estore[c])   # cross block: rows -> view-0 anchors, columns -> view-1 anchors
                     if diag_flags[c]:
                         with fork.next():
                             rowcol(a0, g0, b + 1, 1)     # intra-view blocks: only the no-grad diagnostics loss_x / loss_y need them
@@ -807,6 +820,10 @@ class _InfoNCE(torch.autograd.Function):
             saved += [pres[c].a0, pres[c].a1, pres[c].g0, pres[c].g1]
         ctx.save_for_backward(lse, lse_all, *saved)
         ctx.meta = (nc, Bl, Bg, D, scale, off, dt)
+        # not through save_for_backward: these are private byte buffers no hook / version counter needs to see
+        ctx.estore = estore if fused else [None] * nc
+        ctx.shift = float(bound) if fused else 0.0
+        ctx.world = world
         return out3
 
     @staticmethod
@@ -841,18 +858,36 @@ class _InfoNCE(torch.autograd.Function):
                     g0T, g1T = transpose_bf16(g0), transpose_bf16(g1)
             else:       # fp32 path, or the bf16 kernel that reads the column block MN-major (D = 256 / 512)
                 g0T = g1T = None
-            work.append((a0, lse[c, 0], g1, g1T, lse_all[c, 1], gs, dz0))
-            work.append((a1, lse[c, 1], g0, g0T, lse_all[c, 0], gs, dz1))
+            E = ctx.estore[c]
+            if E is not None:
+                # E holds exp(s - shift) of rows = this rank's view-0 anchors, columns = all view-1 rows
+                wk = torch.empty(int(lib.dmf_infonce_bwd_stored_work_floats(Bl, Bg)), dtype=torch.float32, device=dev)
+                work.append(("E", E, lse[c, 0], lse_all[c, 1], g1, 0, gs, dz0, wk))
+                if ctx.world == 1:
+                    wk1 = torch.empty_like(wk)
+                    work.append(("E", E, lse[c, 0], lse_all[c, 1], a0, 1, gs, dz1, wk1))
+                else:       # the columns of the other ranks' row blocks live on those ranks: recompute this direction
+                    work.append(("R", a1, lse[c, 1], g0, g0T, lse_all[c, 0], gs, dz1))
+            else:
+                work.append(("R", a0, lse[c, 0], g1, g1T, lse_all[c, 1], gs, dz0))
+                work.append(("R", a1, lse[c, 1], g0, g0T, lse_all[c, 0], gs, dz1))
             grads += [dz0, dz1]
         # 2 * nc independent launches (every one writes its own dz): dealt over two streams, tails overlap
         fork = _Fork(dev)
         with _Prof("infonce_bwd"):
-            for a, la, g, gT, lb, gs, dz in work:
+            for w in work:
                 with fork.next():
-                    check(lib.dmf_infonce_bwd(ptr(a), a.stride(0), Bl, ptr(la), ptr(g), g.stride(0), ptr(gT),
-                                              gT.stride(0) if gT is not None else 0, Bg, ptr(lb), D, scale, coef, ptr(gs),
-                                              off, ptr(dz), D, 0, dt, stream()))
+                    if w[0] == "E":
+                        _, E, la, lb, z, direction, gs, dz, wk = w
+                        check(lib.dmf_infonce_bwd_stored(ptr(E), Bl, Bg, ptr(la), ptr(lb), ctx.shift, ptr(z), z.stride(0), D,
+                                                         direction, coef, ptr(gs), off, ptr(dz), D, 0, ptr(wk), stream()))
+                    else:
+                        _, a, la, g, gT, lb, gs, dz = w
+                        check(lib.dmf_infonce_bwd(ptr(a), a.stride(0), Bl, ptr(la), ptr(g), g.stride(0), ptr(gT),
+                                                  gT.stride(0) if gT is not None else 0, Bg, ptr(lb), D, scale, coef, ptr(gs),
+                                                  off, ptr(dz), D, 0, dt, stream()))
             fork.join()
+        ctx.estore = None
         if layout is not None:
             return (None, *sgr)
         return (None, *grads)

@@ -138,6 +138,15 @@ int dmf_infonce_rowcol_sums(const void* A, long long lda, int Ma, const void* Bm
                             float scale, float shift, int sym, int row0_global, float* row_sum, float* col_sum,
                             long long diag_offset, float* diag_out, dmf_stream_t s);
 
+/* The same pass that additionally KEEPS the probabilities (sym = 0 only): E, dmf_infonce_e_bytes(Ma, Nb) bytes,
+ * receives e_ij = exp(s_ij - shift) as bf16 in blocks of [128 rows x 64 columns] (block (ib, jb) at byte offset
+ * (ib * 4*ceil(Nb/256) + jb) * 16384, row-major inside; zeros outside [Ma x Nb]) -- the operand of
+ * dmf_infonce_bwd_stored, which then needs no recomputation of S.  E = NULL: identical to the call above.   */
+size_t dmf_infonce_e_bytes(int Ma, int Nb);
+int dmf_infonce_rowcol_sums_store(const void* A, long long lda, int Ma, const void* Bm, long long ldb, int Nb, int D,
+                                  float scale, float shift, int sym, int row0_global, float* row_sum, float* col_sum,
+                                  long long diag_offset, float* diag_out, void* E, dmf_stream_t s);
+
 /* Per-anchor finalisation of one SupConLoss call (models/losses.py:68-99) for BOTH anchor sets:
  *   m_full = max(m_cross, m_intra); sum_c = l_cross*exp(m_cross-m_full);
  *   loss_i = -(pos - m_full - log(sum_c + 1e-12));  lse_eff_i = m_full + log(sum_c + 1e-12)
@@ -157,6 +166,17 @@ int dmf_infonce_bwd(const void* A, long long lda, int Ma, const float* lseA,
 /* BmT: the transposed column block [D, Nb] (dmf_transpose_bf16).  NULL for fp32, and for the bf16 path whenever
  * dmf_infonce_bwd_needs_transposed(D) returns 0 (D = 256 / 512: the kernel reads Bm as an MN-major operand). */
 int dmf_infonce_bwd_needs_transposed(int D);
+
+/* Backward of one gradient direction from the stored probabilities E of dmf_infonce_rowcol_sums_store (same Ma, Nb,
+ * shift), replacing the autograd chain of models/losses.py:64-99 like dmf_infonce_bwd but with ONE product:
+ *   dir 0: dOut[i,:] (+)= coef*g*( sum_j e_ij (fa_i + fb_j) Z[j,:] - 2 Z[i + diag_offset,:] ),  i < Ma, Z = columns [Nb, D]
+ *   dir 1: dOut[j,:] (+)= coef*g*( sum_i e_ij (fa_i + fb_j) Z[i,:] - 2 Z[j - diag_offset,:] ),  j < Nb, Z = anchors [Ma, D]
+ * fa_i = exp(shift - lseA[i]), fb_j = exp(shift - lseB[j]); Z bf16, D = 256 or 512; dOut fp32 (16-byte aligned, ldo % 4
+ * == 0); work = scratch of dmf_infonce_bwd_stored_work_floats(Ma, Nb) floats (16-byte aligned).              */
+size_t dmf_infonce_bwd_stored_work_floats(int Ma, int Nb);
+int dmf_infonce_bwd_stored(const void* E, int Ma, int Nb, const float* lseA, const float* lseB, float shift,
+                           const void* Z, long long ldz, int D, int dir, float coef, const float* gscale,
+                           long long diag_offset, float* dOut, long long ldo, int accumulate, float* work, dmf_stream_t s);
 
 /* ------------------------------------------------------------------ K4 ortho Gram pieces
  * ortho_loss (models/losses.py:104-110) = || normalize(z1)^T normalize(zs) ||_F.

@@ -300,6 +300,72 @@ def test_infonce_rowcol_sums_kernel(dmf, Bg, D, nrank):
     assert_close(dg[1], torch.diagonal(S00).float(), 1e-3, "self similarities")
 
 
+@pytest.mark.parametrize("Ma,Nb,D,off", [(256, 256, 256, 0), (700, 700, 256, 0), (1000, 1000, 512, 0), (1536, 8192, 256, 2048),
+                                         (4096, 4096, 512, 0), (300, 1100, 512, 512)])
+def test_infonce_stored_probabilities_backward(dmf, Ma, Nb, D, off):
+    """dmf_infonce_rowcol_sums_store + dmf_infonce_bwd_stored through the C-ABI: the stored e_ij blocks against a dense
+    fp64 exp(s - shift) (bf16 rounding, zero padding), and BOTH gradient directions against the dense formula of SURVEY
+    App. B (models/losses.py:64-99 under autograd) with arbitrary LSE vectors; ragged shapes, a row shard with offset."""
+    Lb = dmf._lib
+    lib = Lb.lib
+    gen = torch.Generator().manual_seed(Ma + Nb + D)
+    zc = torch.nn.functional.normalize(torch.randn(Nb, D, generator=gen), dim=-1)
+    za = torch.nn.functional.normalize(0.6 * zc[off:off + Ma] + 0.4 * torch.randn(Ma, D, generator=gen), dim=-1)
+    A, Bm = za.to(DEV).bfloat16().contiguous(), zc.to(DEV).bfloat16().contiguous()
+    scale = 1 / 0.07
+    shift = scale
+    S = (A.double() @ Bm.double().T) * scale
+    Eref = torch.exp(S - shift)
+    rs, cs, dg = torch.zeros(Ma, device=DEV), torch.zeros(Nb, device=DEV), torch.zeros(Ma, device=DEV)
+    nbytes = int(lib.dmf_infonce_e_bytes(Ma, Nb))
+    nib, njb = 2 * ((Ma + 255) // 256), 4 * ((Nb + 255) // 256)
+    assert nbytes == nib * njb * 16384
+    E = torch.full((nbytes // 2,), float("nan"), dtype=torch.bfloat16, device=DEV)
+    Lb.check(lib.dmf_infonce_rowcol_sums_store(A.data_ptr(), D, Ma, Bm.data_ptr(), D, Nb, D, scale, shift, 0, off,
+                                               rs.data_ptr(), cs.data_ptr(), off, dg.data_ptr(), E.data_ptr(), Lb.stream()))
+    assert_close(rs, Eref.sum(1).float(), 2e-3, "row sums (store variant)")
+    assert_close(cs, Eref.sum(0).float(), 2e-3, "column sums (store variant)")
+    dense = E.view(nib, njb, 128, 64).permute(0, 2, 1, 3).reshape(nib * 128, njb * 64).float()
+    assert torch.isfinite(dense).all(), "every byte of E must be written"
+    assert float(dense[Ma:].abs().max() if dense.shape[0] > Ma else 0.0) == 0.0 and \
+        float(dense[:, Nb:].abs().max() if dense.shape[1] > Nb else 0.0) == 0.0, "padding of E must be zero"
+    err = ((dense[:Ma, :Nb].double() - Eref).abs() / (Eref + 1e-30)).max()
+    assert float(err) < 1.2e-2, f"stored e_ij: rel err {float(err):.3e}"        # bf16 rounding of e + bf16-operand logits
+    # arbitrary (but realistic) LSE vectors: row LSEs of this block, column LSEs shifted by a per-column constant
+    lseA = torch.logsumexp(S, 1).float().contiguous()
+    lseB = (torch.logsumexp(S, 0) + 0.3 * torch.rand(Nb, generator=gen).to(DEV).double()).float().contiguous()
+    W = torch.exp(S - lseA.double()[:, None]) + torch.exp(S - lseB.double()[None, :])
+    coef = scale / (2 * Nb)
+    g = torch.full((1,), 0.7, device=DEV)
+    wk = torch.empty(int(lib.dmf_infonce_bwd_stored_work_floats(Ma, Nb)), device=DEV)
+    ref0 = W @ Bm.double() - 2.0 * Bm.double()[off:off + Ma]
+    ref1 = W.T @ A.double()
+    ref1[off:off + Ma] -= 2.0 * A.double()
+    for direction, Z, n_own, ref in ((0, Bm, Ma, ref0), (1, A, Nb, ref1)):
+        out = torch.full((n_own, D), float("nan"), device=DEV)
+        Lb.check(lib.dmf_infonce_bwd_stored(E.data_ptr(), Ma, Nb, lseA.data_ptr(), lseB.data_ptr(), shift, Z.data_ptr(), D, D,
+                                            direction, coef, g.data_ptr(), off, out.data_ptr(), D, 0, wk.data_ptr(), Lb.stream()))
+        assert_close(out, (ref * coef * 0.7).float(), 5e-3, f"stored backward dir {direction}")
+
+
+def test_infonce_stored_path_matches_recompute_path(dmf, monkeypatch):
+    """ops.infonce(unit_norm=True) with the stored-probability backward against the recompute kernels (DMF_STORE_E=0)."""
+    gen = torch.Generator().manual_seed(19)
+    B, D = 2048, 512
+    z0 = torch.nn.functional.normalize(torch.randn(B, D, generator=gen), dim=-1).to(DEV)
+    z1 = torch.nn.functional.normalize(0.5 * z0.cpu() + 0.5 * torch.randn(B, D, generator=gen), dim=-1).to(DEV)
+    outs = []
+    for store in (False, True):
+        monkeypatch.setattr(dmf.ops, "_STORE_E", store)
+        a, b = z0.clone().requires_grad_(), z1.clone().requires_grad_()
+        loss, lx, ly = dmf.ops.infonce(a, b, 0.07, "bf16", unit_norm=True)
+        loss.backward()
+        outs.append((loss.detach(), a.grad, b.grad))
+    assert_close(outs[1][0], outs[0][0], 1e-6, "loss (same forward kernel)")
+    assert_close(outs[1][1], outs[0][1], 5e-3, "dz0 stored vs recompute")
+    assert_close(outs[1][2], outs[0][2], 5e-3, "dz1 stored vs recompute")
+
+
 def test_infonce_unit_norm_path_matches_generic(dmf):
     """ops.infonce(unit_norm=True) (fixed shift, 3 launches) vs the generic online-max path on the same bf16 inputs."""
     gen = torch.Generator().manual_seed(9)

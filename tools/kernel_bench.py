@@ -64,6 +64,29 @@ def main():
                                               scale, scale / (2 * B), ptr(one), 0, ptr(dz), D, 0, 1, stream()))
         ms = timeit(g)
         print(f"infonce_bwd_tc B={B} D={D}: {ms:.3f} ms  algorithmic {2*B*B*D/ms/1e9:.1f} TFLOP/s, executed {(D//128)*(2*B*B*D + 2*B*B*128)/ms/1e9:.1f} TFLOP/s")
+    if a.what in ("all", "stored"):
+        # forward with / without keeping E, then both gradient directions from E
+        rs = torch.zeros(B, device=dev); cs = torch.zeros(B, device=dev); dg = torch.zeros(B, device=dev)
+        E = torch.empty(int(lib.dmf_infonce_e_bytes(B, B)), dtype=torch.uint8, device=dev)
+        for tag, e in (("no E", None), ("store E", E)):
+            f = lambda: check(lib.dmf_infonce_rowcol_sums_store(ptr(b0), D, B, ptr(b1), D, B, D, scale, scale, 0, 0, ptr(rs), ptr(cs),
+                                                                0, ptr(dg), ptr(e), stream()))
+            ms = timeit(f)
+            print(f"rowcol_sums[cross, {tag}] B={B} D={D}: {ms:.3f} ms  {2*B*B*D/ms/1e9:.1f} TFLOP/s"
+                  + (f", E write {E.numel()/ms/1e6:.0f} GB/s" if e is not None else ""))
+        rs.zero_(); cs.zero_()
+        check(lib.dmf_infonce_rowcol_sums_store(ptr(b0), D, B, ptr(b1), D, B, D, scale, scale, 0, 0, ptr(rs), ptr(cs), 0, ptr(dg),
+                                                ptr(E), stream()))
+        lseA, lseB = scale + torch.log(rs), scale + torch.log(cs)
+        wk = torch.empty(int(lib.dmf_infonce_bwd_stored_work_floats(B, B)), device=dev)
+        dz = torch.empty(B, D, device=dev)
+        one = torch.ones(1, device=dev)
+        for direction, z in ((0, b1), (1, b0)):
+            g = lambda: check(lib.dmf_infonce_bwd_stored(ptr(E), B, B, ptr(lseA), ptr(lseB), scale, ptr(z), D, D, direction,
+                                                         scale / (2 * B), ptr(one), 0, ptr(dz), D, 0, ptr(wk), stream()))
+            ms = timeit(g)
+            print(f"infonce_bwd_stored dir {direction} B={B} D={D}: {ms:.3f} ms  {2*B*B*D/ms/1e9:.1f} TFLOP/s (algorithmic = executed), "
+                  f"E read {E.numel()/ms/1e6:.0f} GB/s")
     if a.what in ("all", "aug"):
         x = torch.randn(B, 1024, device=dev)
         y = torch.empty_like(x)

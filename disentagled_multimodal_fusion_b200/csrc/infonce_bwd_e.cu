@@ -140,6 +140,7 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
     // TMA producer: whole warp, uniform control flow; one elected lane issues
     int stage = 0;
     uint32_t phase = 0;
+    const uint64_t e_policy = tc::l2_policy_evict_first();      // E is read exactly once: keep the Z block in L2 instead
     for (int k = k0; k < k1; ++k) {
       tc::mbar_wait(empty_bar + stage, phase ^ 1);
       if (tc::elect_one()) {
@@ -149,14 +150,14 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
         if (DIR == 0) {
           // block (ib = m0 / 128, jb = k): rows 0-63 and 64-127 are adjacent in shared memory = one [128 x 64] K-major tile
           const int row = ((m0 >> 7) * P.njb + k) * 128;
-          tc::tma_load_2d(sb, &tmE, 0, row, e_full + stage);
-          tc::tma_load_2d(sb + 8192, &tmE, 0, row + 64, e_full + stage);
+          tc::tma_load_2d_hint(sb, &tmE, 0, row, e_full + stage, e_policy);
+          tc::tma_load_2d_hint(sb + 8192, &tmE, 0, row + 64, e_full + stage, e_policy);
         } else {
           // rows i = 64 k .. +63 of the two blocks that hold this CTA's 128 columns j: two MN-major 64-j chunks
           const int ib = k >> 1, hh = k & 1, jb0 = m0 >> 6;
 #pragma unroll
           for (int c = 0; c < 2; ++c)
-            tc::tma_load_2d(sb + c * 8192, &tmE, 0, (ib * P.njb + jb0 + c) * 128 + hh * 64, e_full + stage);
+            tc::tma_load_2d_hint(sb + c * 8192, &tmE, 0, (ib * P.njb + jb0 + c) * 128 + hh * 64, e_full + stage, e_policy);
         }
         be_bulk_load(fsm + stage * 64, P.f_str + (size_t)k * 64, BE_FBYTES, e_full + stage);
         for (int h = 0; h < P.nh; ++h)

@@ -16,6 +16,7 @@
 // CTA pair, cta_group::2, M = 256 anchor rows resident in smem, 256-column tiles through a 5-stage TMA ring,
 // S tiles double-buffered in TMEM (2 x 256 columns), 8 softmax warps per CTA -- same skeleton as
 // infonce_fwd_tc2.cu (which remains the exact online-max path for arbitrary inputs).
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_pair.cuh"
@@ -24,11 +25,11 @@ namespace dmf {
 
 constexpr int F4_THREADS = 320;
 constexpr int F4_TILE = 128 * 64 * 2;   // 16 KB: [128 rows x 64 bf16]
-constexpr int F4_STAGES = 5;
+constexpr int F4_STAGES = 5;          // ring depth (4 when E is kept with double-buffered staging tiles)
 constexpr int F4_BN = 256;              // column tile of the pair
 constexpr float kLog2eF4 = 1.4426950408889634f;
 // anchors (8 slots) + ring + 2 KB (barriers, TMEM slot, merge buffer) + 8 x 2 KB E staging + 1 KB alignment slack
-constexpr size_t F4_SMEM_MAX = 1024 + (size_t)(8 + F4_STAGES) * F4_TILE + 2048 + 8 * 2048;
+constexpr size_t F4_SMEM_MAX = 1024 + (size_t)(8 + F4_STAGES) * F4_TILE + 2048 + 8 * 2048;   // = (8 + 4) tiles + 2048 + 16 * 2048
 static_assert(F4_SMEM_MAX <= 232448, "forward carve-up exceeds the opt-in shared-memory window");
 
 __device__ __forceinline__ float f4_exp2(float x) {
@@ -100,32 +101,43 @@ struct F4Args {
   float* diag_out;    // [Ma] raw scaled similarity s_{i, diag_offset + i}
   int store_e;        // sym = 0 only: keep e_ij as bf16 in [128 x 64] blocks, block (ib, jb) at (ib * njb + jb) * 16 KB,
   int njb;            //   written through the tensor map tmE (the operand of the stored-probability backward, infonce_bwd_e.cu)
+  int stages;         // ring depth: F4_STAGES, or F4_STAGES - 1 with two staging tiles per warp (estage_bufs = 2)
+  int estage_bufs;
 };
 
 // 32 consecutive e values of one row -> bf16 -> this thread's 64-byte row of the warp's [32 x 64 B] staging tile (16-byte
 // chunk index XOR ((row >> 1) & 3): the 64B TMA swizzle, conflict-free for 16-byte stores of 8 consecutive rows)
+#ifndef DMF_F4_VAR
+#define DMF_F4_VAR 0      // timing variants, tools builds only: 1 = stage only (no TMA store), 2 = truncating pack, 3 = no column sums
+#endif
 __device__ __forceinline__ void f4_stage_e(uint32_t stage_row, int lane, const float (&e)[32]) {
   const uint32_t x = (uint32_t)((lane >> 1) & 3);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     uint32_t w[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 4; ++k) {
+#if DMF_F4_VAR == 2
+      w[k] = __byte_perm(__float_as_uint(e[g * 8 + 2 * k]), __float_as_uint(e[g * 8 + 2 * k + 1]), 0x7632);
+#else
       asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[k]) : "f"(e[g * 8 + 2 * k + 1]), "f"(e[g * 8 + 2 * k]));
+#endif
+    }
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (((uint32_t)g ^ x) << 4)), "r"(w[0]), "r"(w[1]),
                  "r"(w[2]), "r"(w[3])
                  : "memory");
   }
 }
 // [32 rows x 32 columns] box of the staging tile -> E block rows (c0 = column inside the 64-wide block, c1 = block row)
-__device__ __forceinline__ void f4_tma_store_2d(const CUtensorMap* d, uint32_t smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+__device__ __forceinline__ void f4_tma_store_2d(const CUtensorMap* d, uint32_t smem_src, int c0, int c1, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
                    reinterpret_cast<uint64_t>(d)),
-               "r"(smem_src), "r"(c0), "r"(c1)
+               "r"(smem_src), "r"(c0), "r"(c1), "l"(policy)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void f4_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void f4_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void f4_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F4_THREADS, 1)
@@ -135,7 +147,7 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smemA = smem;                                    // num_kb tiles: this CTA's 128 anchor rows
   uint8_t* smemB = smem + P.num_kb * F4_TILE;               // F4_STAGES tiles: this CTA's half of the column tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + F4_STAGES * F4_TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + P.stages * F4_TILE);
   uint64_t* a_full = bars;
   uint64_t* full_bar = bars + 1;
   uint64_t* empty_bar = full_bar + F4_STAGES;
@@ -143,7 +155,7 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* s_empty = s_full + 2;             // leader [2]: 16 softmax warps of the pair drained the buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
   float* mrg = reinterpret_cast<float*>(tmem_slot + 4);   // [3][128] row-sum / diag merge of the two column halves
-  uint8_t* estage = smem + (8 + F4_STAGES) * F4_TILE + 2048;   // 8 x 2 KB staging tiles of the E stores (store_e only)
+  uint8_t* estage = smem + (8 + P.stages) * F4_TILE + 2048;    // 8 x estage_bufs x 2 KB staging tiles of the E stores
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = tc2::cluster_ctarank();
@@ -166,7 +178,7 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
     tc::mbar_init(a_full, 1);
-    for (int s = 0; s < F4_STAGES; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < P.stages; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
     for (int b = 0; b < 2; ++b) { tc::mbar_init(s_full + b, 1); tc::mbar_init(s_empty + b, 16); }
     tc::fence_barrier_init();
   }
@@ -197,7 +209,7 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tc2::tma_load_2d_pair(smemB + stage * F4_TILE, &tmB, kb * 64, j0, full_bar + stage);
           }
           __syncwarp();
-          if (++stage == F4_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -226,7 +238,7 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tc2::umma_commit2(empty_bar + stage);
           }
           __syncwarp();
-          if (++stage == F4_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
         if (tc::elect_one()) tc2::umma_commit2(s_full + buf);
         __syncwarp();
@@ -245,7 +257,9 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     bool has_diag = false;
     const long long dj = (P.diag_offset >= 0 && rvalid) ? P.diag_offset + row : -1;
     const uint32_t s_empty_leader0 = tc2::mapa(tc::smem_u32(s_empty), 0);
-    const uint32_t my_stage = tc::smem_u32(estage) + (uint32_t)(sw * 2048);
+    const uint32_t my_stage0 = tc::smem_u32(estage) + (uint32_t)(sw * 2048 * P.estage_bufs);
+    uint32_t ebuf = 0;                                          // staging tile of the next E store
+    const uint64_t e_policy = tc::l2_policy_evict_first();      // E is written once and read much later
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       int J = w0 + t_begin + t;
@@ -269,12 +283,16 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             float z[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) z[j] = 0.f;
-            if (lane == 0) f4_store_wait_read();   // the previous store of this warp has read the staging tile
+            const uint32_t my_stage = my_stage0 + ebuf * 2048;
+            if (lane == 0) {                       // the last store from this staging tile has read it
+              if (P.estage_bufs == 2) f4_store_wait_read1(); else f4_store_wait_read();
+            }
             __syncwarp();
             f4_stage_e(my_stage + (uint32_t)(lane * 64), lane, z);
             tc::fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) f4_tma_store_2d(&tmE, my_stage, e_c0, e_c1);
+            if (lane == 0) f4_tma_store_2d(&tmE, my_stage, e_c0, e_c1, e_policy);
+            if (P.estage_bufs == 2) ebuf ^= 1;
           }
           continue;
         }
@@ -296,14 +314,22 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int j = 0; j < 32; j += 4) { ps0 += e[j]; ps1 += e[j + 1]; ps2 += e[j + 2]; ps3 += e[j + 3]; }
         l += (ps0 + ps1) + (ps2 + ps3);
         if (P.store_e) {
-          if (lane == 0) f4_store_wait_read();     // the previous store of this warp has read the staging tile
+          const uint32_t my_stage = my_stage0 + ebuf * 2048;
+#if DMF_F4_VAR == 1
+          f4_stage_e(my_stage + (uint32_t)(lane * 64), lane, e);
+#else
+          if (lane == 0) {                         // the last store from this staging tile has read it
+            if (P.estage_bufs == 2) f4_store_wait_read1(); else f4_store_wait_read();
+          }
           __syncwarp();
           f4_stage_e(my_stage + (uint32_t)(lane * 64), lane, e);
           tc::fence_proxy_async_smem();            // generic-proxy stores -> visible to the TMA engine (async proxy)
           __syncwarp();
-          if (lane == 0) f4_tma_store_2d(&tmE, my_stage, e_c0, e_c1);
+          if (lane == 0) f4_tma_store_2d(&tmE, my_stage, e_c0, e_c1, e_policy);
+#endif
+          if (P.estage_bufs == 2) ebuf ^= 1;
         }
-        if (want_cols) {
+        if (want_cols && DMF_F4_VAR != 3) {
           const float cs = warp_colsum32(e, lane);
           if (lane < nvalid) atomicAdd(P.col_sum + nbase + lane, cs);
         }
@@ -373,6 +399,10 @@ extern "C" int dmf_infonce_rowcol_sums_store(const void* A, long long lda, int M
   if (rc) return rc;
   // carve-up: anchors, ring, barriers + merge buffer (2 KB); with E the ring sits after 8 anchor slots' worth of space
   // so that the 8 x 2 KB staging tiles have a fixed, 1024-aligned offset
+  // with E: variant 2 (default) = 4-stage ring + two staging tiles per softmax warp (a store may still be reading one
+  // tile while the next chunk is staged), variant 1 = 5-stage ring + one staging tile (DMF_F4_ESTAGE=1)
+  static int ebufs = 0;
+  if (!ebufs) { const char* ev = getenv("DMF_F4_ESTAGE"); ebufs = (ev && atoi(ev) == 1) ? 1 : 2; }
   const size_t smem = E ? F4_SMEM_MAX : 1024 + (size_t)(num_kb + F4_STAGES) * F4_TILE + 256 + 2048;
   static bool attr = false;
   if (!attr) {
@@ -382,6 +412,8 @@ extern "C" int dmf_infonce_rowcol_sums_store(const void* A, long long lda, int M
     attr = true;
   }
   F4Args P;
+  P.estage_bufs = E ? ebufs : 1;
+  P.stages = (E && ebufs == 2) ? F4_STAGES - 1 : F4_STAGES;
   P.Ma = Ma; P.Nb = Nb; P.num_kb = num_kb;
   P.scale = scale;
   P.sl2 = scale * kLog2eF4;

@@ -84,6 +84,27 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* d
       : "memory");
 }
 
+// L2 cache policies for streamed-once data (the stored InfoNCE probabilities: 8.6 GB per critic call must not push the
+// 64 MB column block that every CTA re-reads out of the 126 MB L2) and for the re-read operands
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* d, int c0, int c1, uint64_t* bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(d)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {

@@ -8,7 +8,11 @@ from disentagled_multimodal_fusion_b200 import ops, _lib as L
 from disentagled_multimodal_fusion_b200._lib import lib, check, ptr, stream
 
 
-def timeit(fn, iters=5, warm=2):
+ITERS = 5
+
+
+def timeit(fn, iters=None, warm=2):
+    iters = iters or ITERS
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -26,7 +30,10 @@ def main():
     ap.add_argument("--B", type=int, default=16384)
     ap.add_argument("--D", type=int, default=512)
     ap.add_argument("--what", default="all")
+    ap.add_argument("--iters", type=int, default=5, help="timed launches per kernel (large values reach the power-capped steady state)")
     a = ap.parse_args()
+    global ITERS
+    ITERS = a.iters
     L.require_device()
     dev = "cuda"
     B, D = a.B, a.D
@@ -64,6 +71,14 @@ def main():
                                               scale, scale / (2 * B), ptr(one), 0, ptr(dz), D, 0, 1, stream()))
         ms = timeit(g)
         print(f"infonce_bwd_tc B={B} D={D}: {ms:.3f} ms  algorithmic {2*B*B*D/ms/1e9:.1f} TFLOP/s, executed {(D//128)*(2*B*B*D + 2*B*B*128)/ms/1e9:.1f} TFLOP/s")
+    if a.what == "fwdstore":
+        rs = torch.zeros(B, device=dev); cs = torch.zeros(B, device=dev); dg = torch.zeros(B, device=dev)
+        E = torch.empty(int(lib.dmf_infonce_e_bytes(B, B)), dtype=torch.uint8, device=dev)
+        for tag, e in (("no E", None), ("store E", E)):
+            f = lambda: check(lib.dmf_infonce_rowcol_sums_store(ptr(b0), D, B, ptr(b1), D, B, D, scale, scale, 0, 0, ptr(rs), ptr(cs),
+                                                                0, ptr(dg), ptr(e), stream()))
+            ms = timeit(f)
+            print(f"rowcol_sums[cross, {tag}] B={B} D={D}: {ms:.3f} ms  {2*B*B*D/ms/1e9:.1f} TFLOP/s")
     if a.what in ("all", "stored"):
         # forward with / without keeping E, then both gradient directions from E
         rs = torch.zeros(B, device=dev); cs = torch.zeros(B, device=dev); dg = torch.zeros(B, device=dev)

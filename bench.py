@@ -818,37 +818,56 @@ def run_gpu(args, rank, world, local_rank):
     if rank != 0:
         return
     pk = peaks()
-    # roofline of the dominant kernel (InfoNCE backward): algorithmic FLOPs per launch = 2*Ma*Nb*D (the
-    # recompute of S is not counted).  DRAM traffic, tensor-pipe activity and executed/algorithmic FLOPs come from the
+    # rooflines of the two K2 kernels that carry ~80 % of the step, measured live (CUDA events on the launching stream
+    # around each step's launches of the phase, which are dealt over two streams: fork to join):
+    #   forward  rowcol_sum_tc4_kernel: 8 launches per step = 4 cross blocks (2 Bl Bg D FLOP each, row + column sums,
+    #            the exp(s - shift) blocks written to HBM for the backward) + 4 symmetric half-window blocks of the two
+    #            critic calls whose no-grad diagnostics the reference logs (Bl Bg D each)
+    #   backward infonce_bwd_e_kernel: 8 launches per step (4 critic calls x 2 gradient directions), 2 Bl Bg D FLOP each,
+    #            ONE product from the stored probabilities (executed = algorithmic FLOPs)
+    # `roofline` is the one with the larger share of the step.  DRAM traffic and tensor-pipe activity come from the
     # committed ncu capture of the same kernel at this shape (profiles/r02_traffic.json), never from literals here.
-    roof = None
-    kname = "infonce_bwd_tc6_kernel"
-    cap = {}
     tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    caps = {}
     if os.path.isfile(tpath):
         try:
-            cap = json.load(open(tpath)).get(kname, {})
+            caps = json.load(open(tpath))
         except Exception:  # noqa: BLE001
-            cap = {}
+            caps = {}
     same_shape = world == 1 and Bg == 65536 and prec == "bf16"
-    if "infonce_bwd" in prof:
-        # one timed region per step brackets the 8 backward launches (4 critic calls x 2 sides), which are dealt over
-        # two streams so that consecutive launches overlap their tail / first wave: average = span / launches
-        n, tot_ms = prof["infonce_bwd"]
-        n *= 8
-        avg_ms = tot_ms / n
-        flops = 2.0 * Bl * Bg * EMB
-        ach = flops / (avg_ms * 1e-3) / 1e12
-        roof = {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+
+    def k2_roof(phase, kname, launches_per_step, flops_per_step, what):
+        if phase not in prof:
+            return None
+        _, tot_ms = prof[phase]                  # total over the profiled steps (a phase may be several timed regions)
+        n = prof_steps * launches_per_step
+        ach = flops_per_step * prof_steps / (tot_ms * 1e-3) / 1e12
+        cap = caps.get(kname, {})
+        return {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": ach / pk["tf_sust"], "traffic": cap.get("dram_bytes") if same_shape else None, "launches": n,
-                "avg_ms": avg_ms, "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
+                "avg_ms": tot_ms / n, "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
                 "share_of_step": (tot_ms / prof_steps) / (ms / args.steps),
-                "timed_in": f"{prof_steps} eager steps after warm-up (CUDA events on the launching stream around each step's 8 "
-                            "backward launches, fork to join of the two streams they are dealt over)",
-                "traffic_source": "bytes/launch, ncu --set full capture of this kernel at this shape (profiles/r02_traffic.json)" if same_shape and cap else None,
+                "algorithmic_flops_per_step": flops_per_step, "what": what,
+                "timed_in": f"{prof_steps} eager steps after warm-up (CUDA events on the launching stream around each step's "
+                            f"{launches_per_step} launches, fork to join of the two streams they are dealt over)",
+                "traffic_source": ("bytes/launch, ncu --set full capture of this kernel at this shape "
+                                   "(profiles/r02_traffic.json)") if same_shape and cap else None,
                 "executed_over_algorithmic_flops": cap.get("executed_over_algorithmic_flops"),
-                "tensor_pipe_active_pct_ncu": cap.get("tensor_pipe_active_pct") if same_shape else None,
-                "other_kernels_ms_per_step": {k: v[1] / prof_steps for k, v in prof.items()}}
+                "tensor_pipe_active_pct_ncu": cap.get("tensor_pipe_active_pct") if same_shape else None}
+    stored_e = bool(ops._STORE_E) and prec == "bf16" and EMB in (256, 512)
+    bwd_kernel = ("infonce_bwd_e_kernel" if world == 1 else "infonce_bwd_e_kernel (local rows) + infonce_bwd_tc6_kernel "
+                  "(gathered columns)") if stored_e else "infonce_bwd_tc6_kernel"
+    roof_fwd = k2_roof("rowlse_x4", "rowcol_sum_tc4_kernel", 8, 12.0 * Bl * Bg * EMB,
+                       "4 cross blocks (row + column sums" + (", exp(s - shift) kept in HBM as bf16" if stored_e else "") +
+                       ") + 4 symmetric half-window blocks per step")
+    roof_bwd = k2_roof("infonce_bwd", bwd_kernel, 8, 16.0 * Bl * Bg * EMB,
+                       "4 critic calls x 2 gradient directions per step" +
+                       (", one product each from the stored probabilities" if stored_e else ", S recomputed per launch"))
+    roof = None
+    cands = [r for r in (roof_fwd, roof_bwd) if r]
+    if cands:
+        roof = dict(max(cands, key=lambda r: r["share_of_step"]))
+        roof["other_kernels_ms_per_step"] = {k: v[1] / prof_steps for k, v in prof.items()}
     # rooflines of the other two kernel families, measured live (CUDA events, kernels timed alone -> burst peak):
     #   K1 grouped MLP GEMM at the C5 layer shapes (2 groups, M = 2 x per-GPU batch), K3 evidence fusion + EDL loss in
     #   the mode training uses (gradient + conflict term) at the C4 shape B = 2^22, V = 4, C = 42
@@ -883,6 +902,9 @@ def run_gpu(args, rank, world, local_rank):
         "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": "C5 DisentangledSSL 2x1024-d, hidden 512, embed 512, T=0.07 + 3-head evidential probe (C=10)",
                    "global_batch": Bg, "per_gpu_batch": Bl, "parallelism": f"dp{world}",
+                   "infonce_backward": ("one product per gradient from exp(s - shift) kept in HBM by the forward "
+                                        f"({4 * 2 * ((Bl + 255) // 256) * 4 * ((Bg + 255) // 256) * 16384 / 2 ** 30:.1f} GiB/step/GPU)"
+                                        if stored_e else "S recomputed"),
                    "l2": "inputs (1 GiB/step/GPU at dp1) and embeddings are larger than the 126 MB L2",
                    "noise": "vMF noise and the augmented views v1, v2 drawn on device every step (dmf_vmf_draw, dmf_augment)", "launch": launch_mode},
         "clocks": sampler.summary(),
@@ -891,7 +913,7 @@ def run_gpu(args, rank, world, local_rank):
         "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
         "step_tflops_algorithmic": step_flops / 1e12,
         "step_frac_of_sustained_bf16": step_flops / (ms / args.steps * 1e-3) / 1e12 / (pk["tf_sust"] * world),
-        "roofline": roof, "roofline_k1": roof_k1, "roofline_k3": roof_k3, "cpu_baseline": cpu,
+        "roofline": roof, "roofline_k2_fwd": roof_fwd, "roofline_k2_bwd": roof_bwd, "roofline_k1": roof_k1, "roofline_k3": roof_k3, "cpu_baseline": cpu,
         "loss_check": lcheck, "phase_ms": phases, "e2e_diag": e2e_diag,
         "step_ms": {"value": step_marks[0], "e2e": step_marks[1]},
     }

@@ -23,13 +23,18 @@
 
 namespace dmf {
 
-constexpr int F4_THREADS = 320;
+#ifndef DMF_F4_SW
+#define DMF_F4_SW 16
+#endif
+constexpr int F4_SW = DMF_F4_SW;                      // softmax warps per CTA (8 or 16): 4 lane quarters x F4_SW / 4 column groups
+constexpr int F4_THREADS = 64 + 32 * F4_SW;
+constexpr int F4_WCOLS = 256 / (F4_SW / 4);           // columns of every 256-wide tile handled by one softmax warp
 constexpr int F4_TILE = 128 * 64 * 2;   // 16 KB: [128 rows x 64 bf16]
 constexpr int F4_STAGES = 5;          // ring depth (4 when E is kept with double-buffered staging tiles)
 constexpr int F4_BN = 256;              // column tile of the pair
 constexpr float kLog2eF4 = 1.4426950408889634f;
 // anchors (8 slots) + ring + 2 KB (barriers, TMEM slot, merge buffer) + 8 x 2 KB E staging + 1 KB alignment slack
-constexpr size_t F4_SMEM_MAX = 1024 + (size_t)(8 + F4_STAGES) * F4_TILE + 2048 + 8 * 2048;   // = (8 + 4) tiles + 2048 + 16 * 2048
+constexpr size_t F4_SMEM_MAX = 1024 + (size_t)(8 + F4_STAGES - 1) * F4_TILE + 2048 + 16 * 2048;   // E: 4-stage ring + 16 staging tiles
 static_assert(F4_SMEM_MAX <= 232448, "forward carve-up exceeds the opt-in shared-memory window");
 
 __device__ __forceinline__ float f4_exp2(float x) {
@@ -154,7 +159,6 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* s_full = empty_bar + F4_STAGES;   // per CTA [2]
   uint64_t* s_empty = s_full + 2;             // leader [2]: 16 softmax warps of the pair drained the buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
-  float* mrg = reinterpret_cast<float*>(tmem_slot + 4);   // [3][128] row-sum / diag merge of the two column halves
   uint8_t* estage = smem + (8 + P.stages) * F4_TILE + 2048;    // 8 x estage_bufs x 2 KB staging tiles of the E stores
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -179,7 +183,7 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tc::tma_prefetch_desc(&tmB);
     tc::mbar_init(a_full, 1);
     for (int s = 0; s < P.stages; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(s_full + b, 1); tc::mbar_init(s_empty + b, 16); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(s_full + b, 1); tc::mbar_init(s_empty + b, 2 * F4_SW); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc2::tmem_alloc2<512>(tmem_slot);
@@ -247,7 +251,7 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else {
     const int sw = warp - 2;
     const int q = warp & 3;
-    const int ch = sw >> 2;                      // column half (128 columns) of every 256-wide tile
+    const int ch = sw >> 2;                      // column group (F4_WCOLS columns) of every 256-wide tile
     const int rloc = q * 32 + lane;
     const int row = m0 + rloc;
     const bool rvalid = row < P.Ma;
@@ -267,11 +271,11 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const bool want_cols = P.col_sum != nullptr && !(P.sym && J == Ig);
       tc::mbar_wait(s_full + buf, ((uint32_t)t >> 1) & 1);
       tc::tc_fence_after_sync();
-      const int j0 = J * F4_BN + ch * 128;
+      const int j0 = J * F4_BN + ch * F4_WCOLS;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < F4_WCOLS / 32; ++c) {
         uint32_t r[32];
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * F4_BN + ch * 128 + c * 32), r);
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * F4_BN + ch * F4_WCOLS + c * 32), r);
         tc::tmem_ld_wait();
         const int nbase = j0 + c * 32;
         const int nvalid = P.Nb - nbase;
@@ -284,22 +288,27 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j) z[j] = 0.f;
             const uint32_t my_stage = my_stage0 + ebuf * 2048;
-            if (lane == 0) {                       // the last store from this staging tile has read it
+            if (tc::elect_one()) {                 // the last store from this staging tile has read it (same lane issues)
               if (P.estage_bufs == 2) f4_store_wait_read1(); else f4_store_wait_read();
             }
             __syncwarp();
             f4_stage_e(my_stage + (uint32_t)(lane * 64), lane, z);
             tc::fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) f4_tma_store_2d(&tmE, my_stage, e_c0, e_c1, e_policy);
+            if (tc::elect_one()) f4_tma_store_2d(&tmE, my_stage, e_c0, e_c1, e_policy);
             if (P.estage_bufs == 2) ebuf ^= 1;
           }
           continue;
         }
-        if (dj >= nbase && dj < nbase + 32) {
+        // positive / self term of this row, if it lies in this chunk: compare against CONSTANT indices (a loop over
+        // nbase + j == dj made ptxas carry 32 induction variables through the chunk loop: 38 VIADD per chunk, 10 % of
+        // all warp instructions of the kernel in the ncu source view)
+        const long long jd = dj - nbase;
+        if (jd >= 0 && jd < 32) {
+          const int jdi = (int)jd;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (nbase + j == dj) { diag = __uint_as_float(r[j]) * P.scale; has_diag = true; }
+            if (j == jdi) { diag = __uint_as_float(r[j]) * P.scale; has_diag = true; }
         }
         float e[32];
         if (nvalid >= 32) {
@@ -318,14 +327,14 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #if DMF_F4_VAR == 1
           f4_stage_e(my_stage + (uint32_t)(lane * 64), lane, e);
 #else
-          if (lane == 0) {                         // the last store from this staging tile has read it
+          if (tc::elect_one()) {                   // the last store from this staging tile has read it (same lane issues)
             if (P.estage_bufs == 2) f4_store_wait_read1(); else f4_store_wait_read();
           }
           __syncwarp();
           f4_stage_e(my_stage + (uint32_t)(lane * 64), lane, e);
           tc::fence_proxy_async_smem();            // generic-proxy stores -> visible to the TMA engine (async proxy)
           __syncwarp();
-          if (lane == 0) f4_tma_store_2d(&tmE, my_stage, e_c0, e_c1, e_policy);
+          if (tc::elect_one()) f4_tma_store_2d(&tmE, my_stage, e_c0, e_c1, e_policy);
 #endif
           if (P.estage_bufs == 2) ebuf ^= 1;
         }
@@ -338,20 +347,11 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       __syncwarp();
       if (lane == 0) tc2::mbar_arrive_cluster(s_empty_leader0 + (uint32_t)(buf * 8));
     }
-    if (P.store_e && lane == 0) f4_store_wait_all();   // the E stores must have left shared memory before the CTA exits
-    // merge the two column halves of each row, then one atomicAdd per row (column splits share rows)
-    if (ch == 1) {
-      mrg[rloc] = l;
-      mrg[128 + rloc] = diag;
-      mrg[256 + rloc] = has_diag ? 1.f : 0.f;
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (ch == 0 && rvalid && ntiles > 0) {
-      atomicAdd(P.row_sum + row, l + mrg[rloc]);
-      if (P.diag_out) {
-        if (has_diag) P.diag_out[row] = diag;
-        else if (mrg[256 + rloc] != 0.f) P.diag_out[row] = mrg[128 + rloc];
-      }
+    if (P.store_e && tc::elect_one()) f4_store_wait_all();   // the E stores must have left shared memory before the CTA exits
+    // one atomicAdd per row and softmax warp (once per CTA: column groups and column splits share rows)
+    if (rvalid && ntiles > 0) {
+      atomicAdd(P.row_sum + row, l);
+      if (P.diag_out && has_diag) P.diag_out[row] = diag;
     }
   }
   __syncwarp();
@@ -399,10 +399,8 @@ extern "C" int dmf_infonce_rowcol_sums_store(const void* A, long long lda, int M
   if (rc) return rc;
   // carve-up: anchors, ring, barriers + merge buffer (2 KB); with E the ring sits after 8 anchor slots' worth of space
   // so that the 8 x 2 KB staging tiles have a fixed, 1024-aligned offset
-  // with E: variant 2 (default) = 4-stage ring + two staging tiles per softmax warp (a store may still be reading one
-  // tile while the next chunk is staged), variant 1 = 5-stage ring + one staging tile (DMF_F4_ESTAGE=1)
-  static int ebufs = 0;
-  if (!ebufs) { const char* ev = getenv("DMF_F4_ESTAGE"); ebufs = (ev && atoi(ev) == 1) ? 1 : 2; }
+  // with E: 4-stage ring + one 2 KB staging tile per softmax warp (F4_SW = 16); F4_SW = 8 keeps two tiles per warp
+  const int ebufs = 16 / F4_SW;
   const size_t smem = E ? F4_SMEM_MAX : 1024 + (size_t)(num_kb + F4_STAGES) * F4_TILE + 256 + 2048;
   static bool attr = false;
   if (!attr) {
@@ -413,7 +411,7 @@ extern "C" int dmf_infonce_rowcol_sums_store(const void* A, long long lda, int M
   }
   F4Args P;
   P.estage_bufs = E ? ebufs : 1;
-  P.stages = (E && ebufs == 2) ? F4_STAGES - 1 : F4_STAGES;
+  P.stages = E ? F4_STAGES - 1 : F4_STAGES;
   P.Ma = Ma; P.Nb = Nb; P.num_kb = num_kb;
   P.scale = scale;
   P.sl2 = scale * kLog2eF4;

@@ -656,6 +656,9 @@ _FORK = os.environ.get("DMF_FORK", "1") != "0"
 # recompute kernels; DMF_STORE_E_MAX_GB bounds the bytes one batched op may keep (beyond it the calls fall back one by one).
 _STORE_E = os.environ.get("DMF_STORE_E", "1") != "0"
 _STORE_E_MAX = float(os.environ.get("DMF_STORE_E_MAX_GB", "64")) * 2 ** 30
+# data parallel, stored probabilities: gradient of the view-1 rows as partial sums over this rank's E rows + one NCCL
+# reduce-scatter per critic call ("0": recompute that direction from the gathered anchors with the M = 128 pair kernel)
+_DP_RS = os.environ.get("DMF_DP_RS", "1") != "0"
 
 
 class _Fork:
@@ -862,11 +865,17 @@ class _InfoNCE(torch.autograd.Function):
             if E is not None:
                 # E holds exp(s - shift) of rows = this rank's view-0 anchors, columns = all view-1 rows
                 wk = torch.empty(int(lib.dmf_infonce_bwd_stored_work_floats(Bl, Bg)), dtype=torch.float32, device=dev)
-                work.append(("E", E, lse[c, 0], lse_all[c, 1], g1, 0, gs, dz0, wk))
+                work.append(("E", E, lse[c, 0], lse_all[c, 1], g1, 0, gs, dz0, wk, None))
+                wk1 = torch.empty_like(wk)
                 if ctx.world == 1:
-                    wk1 = torch.empty_like(wk)
-                    work.append(("E", E, lse[c, 0], lse_all[c, 1], a0, 1, gs, dz1, wk1))
-                else:       # the columns of the other ranks' row blocks live on those ranks: recompute this direction
+                    work.append(("E", E, lse[c, 0], lse_all[c, 1], a0, 1, gs, dz1, wk1, None))
+                elif _DP_RS:
+                    # data parallel: this rank's rows of E give a PARTIAL gradient for every column j (all ranks' view-1
+                    # rows); one reduce-scatter per call sums the partials and leaves each rank its own rows.  The
+                    # positive term -2 z0[j] is added by the rank that owns row j (diag_offset = its row offset).
+                    full = torch.empty(Bg, D, dtype=torch.float32, device=dev)
+                    work.append(("E", E, lse[c, 0], lse_all[c, 1], a0, 1, gs, full, wk1, dz1))
+                else:       # DMF_DP_RS=0: recompute this direction from the gathered anchors instead
                     work.append(("R", a1, lse[c, 1], g0, g0T, lse_all[c, 0], gs, dz1))
             else:
                 work.append(("R", a0, lse[c, 0], g1, g1T, lse_all[c, 1], gs, dz0))
@@ -874,19 +883,26 @@ class _InfoNCE(torch.autograd.Function):
             grads += [dz0, dz1]
         # 2 * nc independent launches (every one writes its own dz): dealt over two streams, tails overlap
         fork = _Fork(dev)
+        pending = []
         with _Prof("infonce_bwd"):
             for w in work:
                 with fork.next():
                     if w[0] == "E":
-                        _, E, la, lb, z, direction, gs, dz, wk = w
+                        _, E, la, lb, z, direction, gs, dz, wk, scatter_to = w
                         check(lib.dmf_infonce_bwd_stored(ptr(E), Bl, Bg, ptr(la), ptr(lb), ctx.shift, ptr(z), z.stride(0), D,
                                                          direction, coef, ptr(gs), off, ptr(dz), D, 0, ptr(wk), stream()))
+                        if scatter_to is not None:      # NCCL's stream picks up after this launch; later launches overlap it
+                            pending.append(dist.reduce_scatter_tensor(scatter_to, dz, async_op=True))
                     else:
                         _, a, la, g, gT, lb, gs, dz = w
                         check(lib.dmf_infonce_bwd(ptr(a), a.stride(0), Bl, ptr(la), ptr(g), g.stride(0), ptr(gT),
                                                   gT.stride(0) if gT is not None else 0, Bg, ptr(lb), D, scale, coef, ptr(gs),
                                                   off, ptr(dz), D, 0, dt, stream()))
             fork.join()
+        if pending:
+            with _Prof("grad_reduce_scatter"):
+                for h in pending:
+                    h.wait()
         ctx.estore = None
         if layout is not None:
             return (None, *sgr)

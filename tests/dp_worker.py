@@ -43,11 +43,13 @@ def main():
             ops._dist_on, dpmod.world = saved_ops, saved_dp
 
     ok = True
-    if case in ("dssl", "dssl_small"):
+    if case in ("dssl", "dssl_small", "dssl_e256"):
         # dssl: per-rank shard 512 rows (fused row+column kernel); dssl_small: 128 rows per rank, where the fused
         # kernel is not eligible -- every rank must then take the generic path (rank-invariant choice)
-        dims, h, e = [256, 192], 128, 128
-        Bg = 1024 if case == "dssl" else 128 * world
+        # dssl_e256: embed width 256 -> the stored-probability backward (local-row direction from this rank's E rows,
+        # the other direction as partial sums + NCCL reduce-scatter)
+        dims, h, e = [256, 192], 128, (256 if case == "dssl_e256" else 128)
+        Bg = 128 * world if case == "dssl_small" else 1024
         torch.manual_seed(0)
         model = pkg.DisentangledSSL(output_dim=dims, hidden_dim=h, embed_dim=e, precision=prec).to(dev)
         gen = torch.Generator().manual_seed(1)

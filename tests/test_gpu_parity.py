@@ -929,7 +929,7 @@ def test_direct_grad_accumulation_matches_autograd(dmf):
 
 
 # ------------------------------------------------------------------------------------- multi-GPU (NCCL)
-@pytest.mark.parametrize("prec,case", [("bf16", "dssl"), ("fp32", "dssl"), ("bf16", "dssl_small"), ("fp32", "probe"),
+@pytest.mark.parametrize("prec,case", [("bf16", "dssl"), ("bf16", "dssl_e256"), ("fp32", "dssl"), ("bf16", "dssl_small"), ("fp32", "probe"),
                                        ("fp32", "dmvae")])
 def test_data_parallel_matches_single_gpu(dmf, prec, case):
     """2-rank NCCL run of one step vs the same step on the full batch in one process: DSSL (global negatives via

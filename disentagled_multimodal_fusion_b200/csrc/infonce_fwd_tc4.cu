@@ -113,7 +113,7 @@ struct F4Args {
 // 32 consecutive e values of one row -> bf16 -> this thread's 64-byte row of the warp's [32 x 64 B] staging tile (16-byte
 // chunk index XOR ((row >> 1) & 3): the 64B TMA swizzle, conflict-free for 16-byte stores of 8 consecutive rows)
 #ifndef DMF_F4_VAR
-#define DMF_F4_VAR 0      // timing variants, tools builds only: 1 = stage only (no TMA store), 2 = truncating pack, 3 = no column sums
+#define DMF_F4_VAR 0      // timing variants, tools builds only: 1 = stage only (no TMA store), 2 = truncating pack, 3 = no column sums, 4 = no bulk-group wait, 5 = no proxy fence, 6 = neither (4-6: WRONG results)
 #endif
 __device__ __forceinline__ void f4_stage_e(uint32_t stage_row, int lane, const float (&e)[32]) {
   const uint32_t x = (uint32_t)((lane >> 1) & 3);
@@ -327,12 +327,16 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #if DMF_F4_VAR == 1
           f4_stage_e(my_stage + (uint32_t)(lane * 64), lane, e);
 #else
+#if DMF_F4_VAR != 4 && DMF_F4_VAR != 6
           if (tc::elect_one()) {                   // the last store from this staging tile has read it (same lane issues)
             if (P.estage_bufs == 2) f4_store_wait_read1(); else f4_store_wait_read();
           }
+#endif
           __syncwarp();
           f4_stage_e(my_stage + (uint32_t)(lane * 64), lane, e);
+#if DMF_F4_VAR != 5 && DMF_F4_VAR != 6
           tc::fence_proxy_async_smem();            // generic-proxy stores -> visible to the TMA engine (async proxy)
+#endif
           __syncwarp();
           if (tc::elect_one()) f4_tma_store_2d(&tmE, my_stage, e_c0, e_c1, e_policy);
 #endif

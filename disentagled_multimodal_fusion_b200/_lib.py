@@ -62,6 +62,14 @@ class EdlParams(C.Structure):
                 ("coef", c_f), ("dc_weight", c_f), ("inv_B_global", c_f)]
 
 
+class HeadGemmDesc(C.Structure):
+    _fields_ = [("A", c_p), ("lda", c_ll), ("W", c_p), ("ldw", c_ll), ("bias", c_p),
+                ("pre_f32", c_p), ("ld_pre_f32", c_ll), ("pre_bf16", c_p), ("ld_pre_bf16", c_ll),
+                ("out_f32", c_p), ("ld_out_f32", c_ll), ("out_bf16", c_p), ("ld_out_bf16", c_ll),
+                ("inv_norm", c_p), ("noise_w", c_p), ("noise_v", c_p),
+                ("eps", c_f), ("M", c_i), ("N", c_i), ("K", c_i)]
+
+
 EPI_NONE, EPI_BIAS, EPI_BIAS_RELU, EPI_RELU_MASK, EPI_BIAS_EVIDENCE = range(5)
 AGG = {"cml": 0, "avg": 1, "joint": 2, "disentangled": 3, "dbf": 4}
 
@@ -72,6 +80,7 @@ _SIGS = {
     "dmf_launch_count": ([], c_ll),
     "dmf_grouped_gemm_f32": ([C.POINTER(GemmDesc), c_i, c_i, c_p], c_i),
     "dmf_grouped_gemm_bf16_tc": ([C.POINTER(TcGemmDesc), c_i, c_i, c_p], c_i),
+    "dmf_head_gemm_bf16": ([C.POINTER(HeadGemmDesc), c_i, c_i, c_p], c_i),
     "dmf_colsum_f32": ([c_p, c_ll, c_i, c_i, c_p, c_i, c_p], c_i),
     "dmf_cast_f32_to_bf16": ([c_p, c_ll, c_p, c_ll, c_i, c_i, c_p], c_i),
     "dmf_cast_transpose_f32_to_bf16": ([c_p, c_ll, c_p, c_ll, c_i, c_i, c_p], c_i),

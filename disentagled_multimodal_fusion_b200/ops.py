@@ -103,6 +103,24 @@ def gemm_tc(descs: Sequence[dict], epilogue: int) -> None:
     check(lib.dmf_grouped_gemm_bf16_tc(arr, len(descs), epilogue, stream()))
 
 
+def head_gemm(descs: Sequence[dict], head: int) -> None:
+    """Last encoder layer with the row head in its epilogue (dmf_head_gemm_bf16): head 0 = row-normalise, 1 = vMF sample.
+    Each dict: A, W (bf16, row-major), bias, M, N, K and any of pre_f32 / pre_bf16 / out_f32 / out_bf16 / inv_norm /
+    noise_w / noise_v / eps (tensors; leading dimensions are taken from their strides)."""
+    arr = (L.HeadGemmDesc * len(descs))()
+    for i, d in enumerate(descs):
+        g = arr[i]
+        g.A, g.lda, g.W, g.ldw, g.bias = ptr(d["A"]), d["A"].stride(0), ptr(d["W"]), d["W"].stride(0), ptr(d["bias"])
+        for k in ("pre_f32", "pre_bf16", "out_f32", "out_bf16"):
+            t = d.get(k)
+            setattr(g, k, ptr(t))
+            setattr(g, "ld_" + k, t.stride(0) if t is not None else 0)
+        g.inv_norm, g.noise_w, g.noise_v = ptr(d.get("inv_norm")), ptr(d.get("noise_w")), ptr(d.get("noise_v"))
+        g.eps = float(d.get("eps", 1e-12))
+        g.M, g.N, g.K = int(d["M"]), int(d["N"]), int(d["K"])
+    check(lib.dmf_head_gemm_bf16(arr, len(descs), int(head), stream()))
+
+
 def wgrad_mn_ok(n_out: int, k_in: int) -> bool:
     """True when the wgrad of a Linear(k_in -> n_out) runs on the CTA-pair kernel with MN-major operands, i.e. reads the
     row-major bf16 activations dY [batch, n_out] and X [batch, k_in] as they are: no transposed copies are written

@@ -95,6 +95,29 @@ typedef struct {
 } dmf_tc_gemm_desc;
 int dmf_grouped_gemm_bf16_tc(const dmf_tc_gemm_desc* groups, int n_groups, int epilogue, dmf_stream_t s);
 
+/* The LAST encoder layer with its per-row head fused into the epilogue (bf16 operands, fp32 accumulate; one CTA pair
+ * owns whole output rows, so N must be 256 or 512):  X = A W^T + b, then
+ *   head 0: out = X / max(|X|_2, eps)               F.normalize, models/disentangledssl.py:139-140
+ *   head 1: out = vMF reparameterised sample         models/classifiers.py:433-437 (Householder reflection of
+ *           x = [w, sqrt(1 - w^2) v] from e1 onto X / |X|), noise (w [M], v [M, N-1]) from dmf_vmf_draw
+ * Optional extra outputs: X itself (pre_f32 / pre_bf16: the vMF backward, the ortho term and the conditioning columns of
+ * the private encoders need it) and inv_norm[M] = 1 / max(|X|, eps) (head 0; dmf_row_normalize_bwd takes it).      */
+typedef struct {
+  const void* A; long long lda;           /* [M, K] bf16 */
+  const void* W; long long ldw;           /* [N, K] bf16 (nn.Linear layout) */
+  const float* bias;                      /* [N] */
+  float* pre_f32; long long ld_pre_f32;   /* X, may be NULL */
+  uint16_t* pre_bf16; long long ld_pre_bf16;
+  float* out_f32; long long ld_out_f32;   /* head output (at least one of out_f32 / out_bf16) */
+  uint16_t* out_bf16; long long ld_out_bf16;
+  float* inv_norm;                        /* [M], head 0, may be NULL */
+  const float* noise_w;                   /* [M], head 1 */
+  const float* noise_v;                   /* [M, N-1], head 1 */
+  float eps;                              /* head 0 */
+  int M, N, K;                            /* K % 8 == 0 */
+} dmf_head_gemm_desc;
+int dmf_head_gemm_bf16(const dmf_head_gemm_desc* groups, int n_groups, int head, dmf_stream_t s);
+
 /* column sums  out[n] (+)= sum_m X[m*ld + n]   (bias gradients)  */
 int dmf_colsum_f32(const float* X, long long ld, int M, int N, float* out, int accumulate, dmf_stream_t s);
 

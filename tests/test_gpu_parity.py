@@ -406,6 +406,49 @@ def test_tc_gemm(dmf, M, N, K):
     assert_close(outb[:, :N].float(), ref, 1e-2, "tc gemm bf16 out")
 
 
+@pytest.mark.parametrize("head", [0, 1])
+@pytest.mark.parametrize("shapes", [[(1000, 512, 512)], [(300, 256, 192), (777, 256, 192)], [(4096, 512, 1536), (4096, 512, 1536)]])
+def test_head_gemm_fused_epilogue(dmf, head, shapes):
+    """dmf_head_gemm_bf16: last encoder layer with the row head in its epilogue (head 0: F.normalize,
+    models/disentangledssl.py:139-140; head 1: the vMF Householder sample, models/classifiers.py:433-437) against
+    fp32 torch on the same bf16 operands followed by the separate head kernels' formulas; ragged row counts, two
+    groups of different height, N = 256 and 512."""
+    ops = dmf.ops
+    descs, refs = [], []
+    for gi, (M, N, K) in enumerate(shapes):
+        gen = torch.Generator().manual_seed(M + N + K + gi)
+        A = torch.randn(M, K, generator=gen).to(DEV).bfloat16()
+        W = (torch.randn(N, K, generator=gen) / K ** 0.5).to(DEV).bfloat16()
+        b = (0.1 * torch.randn(N, generator=gen)).to(DEV)
+        X = A.float() @ W.float().T + b
+        d = dict(A=A, W=W, bias=b, M=M, N=N, K=K,
+                 pre_f32=torch.full((M, N), float("nan"), device=DEV),
+                 pre_bf16=torch.zeros(M, N + 64, dtype=torch.bfloat16, device=DEV)[:, 64:],     # a strided view (concat buffer)
+                 out_f32=torch.full((M, N), float("nan"), device=DEV),
+                 out_bf16=torch.zeros(M, N, dtype=torch.bfloat16, device=DEV))
+        if head == 0:
+            d.update(inv_norm=torch.full((M,), float("nan"), device=DEV), eps=1e-12)
+            nrm = X.norm(dim=1, keepdim=True).clamp_min(1e-12)
+            refs.append((X, X / nrm, 1.0 / nrm[:, 0]))
+        else:
+            w = (2 * torch.rand(M, generator=gen) - 1).to(DEV)
+            v = torch.nn.functional.normalize(torch.randn(M, N - 1, generator=gen), dim=-1).to(DEV)
+            d.update(noise_w=w, noise_v=v)
+            Zk = torch.empty(M, N, device=DEV)
+            dmf._lib.check(dmf._lib.lib.dmf_vmf_fwd(X.contiguous().data_ptr(), N, w.data_ptr(), v.data_ptr(), M, N, Zk.data_ptr(), N,
+                                                    0, 0, dmf._lib.stream()))
+            refs.append((X, Zk, None))
+        descs.append(d)
+    ops.head_gemm(descs, head)
+    for d, (X, out, inv) in zip(descs, refs):
+        assert_close(d["pre_f32"], X, 2e-5, "pre-activation fp32")
+        assert_close(d["pre_bf16"].float(), X, 1e-2, "pre-activation bf16 (strided)")
+        assert_close(d["out_f32"], out, 5e-5, f"head {head} output fp32")
+        assert_close(d["out_bf16"].float(), out, 1e-2, f"head {head} output bf16")
+        if inv is not None:
+            assert_close(d["inv_norm"], inv, 1e-5, "inv_norm")
+
+
 @pytest.mark.parametrize("M,N,K,epi", [(1024, 512, 512, "bias_relu"), (1000, 384, 200, "bias_relu"), (777, 136, 1096, "bias"),
                                        (5000, 512, 1536, "mask")])
 def test_tc_gemm_pair_kernel(dmf, M, N, K, epi):

@@ -83,13 +83,18 @@ class DisentangledSSL(LightningModule):
         self.shared_embedding_dim = 2 * embed_dim   # width of get_embedding()[0]
 
     # ---------- models/disentangledssl.py:67-80
-    def _encode(self, rows1, rows2, after_shared=None):
+    def _encode(self, rows1, rows2, after_shared=None, head_noise=None):
         """shared + private encoders on row-stacked inputs of the two modalities (one grouped launch
         per layer): returns (E1, E2, P1, P2).  bf16 path: inputs are cast once into the
         [rows, d + D] concat buffers that feed both the shared (K = d) and the private (K = d + D) MLP.
         ``after_shared(E1, E2)`` runs between the two encoder stacks (the forward pass launches the vMF heads and the
-        all-gathers of the shared critic calls there, so that they overlap the private encoders)."""
+        all-gathers of the shared critic calls there, so that they overlap the private encoders).
+        ``head_noise`` = [(w1, v1), (w2, v2)] (row-stacked vMF noise of the two modalities): the bf16 path then runs the
+        vMF sample in the epilogue of the shared encoders' last GEMM and F.normalize in the private encoders' one
+        (dmf_head_gemm_bf16) whenever ops.head_fusable allows; the fifth return value carries those head outputs
+        (Z1, Z2, Z1b, Z2b, P1n, P2n, P1b, P2b) or is None."""
         D = self.embed_dim
+        fused = None
         if self.precision == "bf16":
             # transposed copies of the inputs feed the layer-0 wgrad only where it cannot read them MN-major
             l0 = [m.weights()[0].shape for m in (self.encoder_x1s, self.encoder_x2s, self.encoder_x1, self.encoder_x2)]
@@ -115,15 +120,31 @@ class DisentangledSSL(LightningModule):
             o1 = dict(xTs=[bufTs[0][:dims[0]], bufTs[1][:dims[1]]] if need_t else None,
                       out_bf16=[bufs[0][:, dims[0]:], bufs[1][:, dims[1]:]],
                       out_bf16T=[bufTs[0][dims[0]:], bufTs[1][dims[1]:]] if need_t else None)
-            E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="bf16", opts=o1)
-            if after_shared is not None:
-                after_shared(E1, E2)
+            encs = (self.encoder_x1s, self.encoder_x2s, self.encoder_x1, self.encoder_x2)
+            fuse = head_noise is not None and not need_t and \
+                ops.head_fusable([m.weights()[-1].shape for m in encs]) and all(m.final == "none" for m in encs)
+            if fuse:
+                o1["head"] = dict(kind=1, noise=list(head_noise))
+                E1, E2, Z1, Z2, Z1b, Z2b = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="bf16", opts=o1)
+                if after_shared is not None:
+                    after_shared(E1, E2, (Z1, Z2, Z1b, Z2b))
+            else:
+                E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="bf16", opts=o1)
+                if after_shared is not None:
+                    after_shared(E1, E2)
             if self.condzs:
                 o2 = dict(xTs=list(bufTs) if need_t else None, extras_prefilled=True)
-                P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], bufs, extras=[E1, E2], precision="bf16", opts=o2)
+                pin, pex = bufs, [E1, E2]
             else:       # unconditioned private encoders read the same bf16 input columns as the shared ones
                 o2 = dict(xTs=[bufTs[0][:dims[0]], bufTs[1][:dims[1]]] if need_t else None)
-                P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], ins, precision="bf16", opts=o2)
+                pin, pex = ins, None
+            if fuse:
+                o2["head"] = dict(kind=0, eps=1e-12)
+                P1, P2, P1n, P2n, P1b, P2b = grouped_forward([self.encoder_x1, self.encoder_x2], pin, extras=pex,
+                                                             precision="bf16", opts=o2)
+                fused = (Z1, Z2, Z1b, Z2b, P1n, P2n, P1b, P2b)
+            else:
+                P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], pin, extras=pex, precision="bf16", opts=o2)
         else:
             ins = [torch.cat(rows1, 0) if len(rows1) > 1 else rows1[0], torch.cat(rows2, 0) if len(rows2) > 1 else rows2[0]]
             E1, E2 = grouped_forward([self.encoder_x1s, self.encoder_x2s], ins, precision="fp32")
@@ -131,14 +152,14 @@ class DisentangledSSL(LightningModule):
                 after_shared(E1, E2)
             P1, P2 = grouped_forward([self.encoder_x1, self.encoder_x2], ins, extras=[E1, E2] if self.condzs else None,
                                      precision="fp32")
-        return E1, E2, P1, P2
+        return E1, E2, P1, P2, fused
 
     @torch.no_grad()
     def get_embedding(self, x):
         require_device()
         x1 = self.feature_encoders[0](x[0].float())
         x2 = self.feature_encoders[1](x[1].float())
-        zsx1, zsx2, z1x1, z2x2 = self._encode([x1], [x2])
+        zsx1, zsx2, z1x1, z2x2, _ = self._encode([x1], [x2])
         return torch.cat([zsx1, zsx2], dim=1), [z1x1, z2x2]
 
     def draw_noise(self, B, device, out=None):
@@ -190,21 +211,28 @@ class DisentangledSSL(LightningModule):
 
         normal = self.distribution == "normal"
 
-        def heads_shared(E1, E2):
-            if normal:
+        # row-stacked vMF noise of the two modalities (modality 1 <- draws 0, 2; modality 2 <- draws 1, 3)
+        stacked_noise = None
+        if not normal:
+            if isinstance(noise, StackedNoise) and noise.stacked is not None and noise.stacked[0].shape[0] == 2 * B:
+                stacked_noise = noise.stacked             # drawn in place into the row-stacked layout
+            else:
+                stacked_noise = (torch.cat([noise[0][0], noise[2][0]], 0), torch.cat([noise[0][1], noise[2][1]], 0),
+                                 torch.cat([noise[1][0], noise[3][0]], 0), torch.cat([noise[1][1], noise[3][1]], 0))
+
+        def heads_shared(E1, E2, fused_heads=None):
+            if fused_heads is not None:
+                # the vMF samples (and their bf16 copies) came out of the shared encoders' last GEMM epilogue
+                Z1, Z2, Z1b, Z2b = fused_heads
+                bf = [(Z1b[:B], Z2b[:B]), (Z1b[B:], Z2b[B:])]
+            elif normal:
                 # unit-variance Gaussian head: z = e + eps (noise rows follow the stacking: modality 1 <- draws 0,2)
                 Z1 = E1 + torch.cat([noise[0], noise[2]], 0)
                 Z2 = E2 + torch.cat([noise[1], noise[3]], 0)
                 bf = [None, None]
             else:
-                # vMF reparameterised samples (noise rows follow the stacking: modality 1 <- draws 0,2; modality 2 <- 1,3)
-                if isinstance(noise, StackedNoise) and noise.stacked is not None and noise.stacked[0].shape[0] == 2 * B:
-                    w1, vv1, w2, vv2 = noise.stacked          # drawn in place into the row-stacked layout
-                else:
-                    w1 = torch.cat([noise[0][0], noise[2][0]], 0)
-                    vv1 = torch.cat([noise[0][1], noise[2][1]], 0)
-                    w2 = torch.cat([noise[1][0], noise[3][0]], 0)
-                    vv2 = torch.cat([noise[1][1], noise[3][1]], 0)
+                # vMF reparameterised samples
+                w1, vv1, w2, vv2 = stacked_noise
                 Z1, Z2 = ops.vmf_rsample(E1, w1, vv1, want_bf16=wb), ops.vmf_rsample(E2, w2, vv2, want_bf16=wb)
                 if wb:
                     (Z1, Z1b), (Z2, Z2b) = Z1, Z2
@@ -216,7 +244,10 @@ class DisentangledSSL(LightningModule):
             # the shared critic inputs exist now: launch their embedding all-gathers (asynchronous NCCL) BEFORE the
             # private encoders run, so that the gathers overlap those GEMMs
             st["pres"] = [ops.GatheredPair(a, b, pr, bf16=f) for (a, b), f in zip(st["pairs"], bf)]
-        E1, E2, P1, P2 = self._encode([x1, v1], [x2, v2], after_shared=heads_shared)                       # [2B, D] each
+        hn = None
+        if wb and not normal and not self.usezsx:
+            hn = [(stacked_noise[0], stacked_noise[1]), (stacked_noise[2], stacked_noise[3])]
+        E1, E2, P1, P2, fused = self._encode([x1, v1], [x2, v2], after_shared=heads_shared, head_noise=hn)   # [2B, D] each
         # specific critic inputs: normalize(z) or, with usezsx, normalize([z | e]) (models/disentangledssl.py:128-140)
         C1, C2 = (torch.cat([P1, E1], 1), torch.cat([P2, E2], 1)) if self.usezsx else (P1, P2)
         # the tensor-core InfoNCE tiles cover widths that are multiples of 64 up to 512; a wider [z | e] critic input
@@ -224,12 +255,16 @@ class DisentangledSSL(LightningModule):
         Dc = C1.shape[1]
         pr_spec = pr if (pr != "bf16" or (Dc % 64 == 0 and Dc <= 512)) else "fp32"
         wbs = pr_spec == "bf16"
-        P1n, P2n = ops.row_normalize(C1, want_bf16=wbs), ops.row_normalize(C2, want_bf16=wbs)
-        if wbs:
-            (P1n, P1b), (P2n, P2b) = P1n, P2n
+        if fused is not None:        # F.normalize ran in the private encoders' last GEMM epilogue
+            P1n, P2n, P1b, P2b = fused[4:]
             bf = [(P1b[:B], P1b[B:]), (P2b[:B], P2b[B:])]
         else:
-            bf = [None, None]
+            P1n, P2n = ops.row_normalize(C1, want_bf16=wbs), ops.row_normalize(C2, want_bf16=wbs)
+            if wbs:
+                (P1n, P1b), (P2n, P2b) = P1n, P2n
+                bf = [(P1b[:B], P1b[B:]), (P2b[:B], P2b[B:])]
+            else:
+                bf = [None, None]
         pairs23 = [(P1n[:B], P1n[B:]), (P2n[:B], P2n[B:])]
         pairs = st["pairs"] + pairs23
         pres = st["pres"] + [ops.GatheredPair(a, b, pr_spec, bf16=f) for (a, b), f in zip(pairs23, bf)]

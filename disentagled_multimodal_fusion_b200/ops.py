@@ -121,6 +121,20 @@ def head_gemm(descs: Sequence[dict], head: int) -> None:
     check(lib.dmf_head_gemm_bf16(arr, len(descs), int(head), stream()))
 
 
+def head_fusable(last_shapes, out_bt=None) -> bool:
+    """Can the row head (row-normalise / vMF sample) run in the epilogue of the last layer?  ``last_shapes`` = [out, in]
+    of every group's last Linear.  One CTA pair must own whole rows: widths 256 / 512 only."""
+    # Opt-in (DMF_FUSE_HEADS=1).  Measured at C5 (profiles/r02_bench_v9_fused_heads.log): parity green, but the step is
+    # 64.7 ms against 60.2 ms with the separate head kernels -- a whole 512-wide row fills the 512 TMEM columns of its CTA,
+    # so the two-pass epilogue (1 MB of stores per 128-row tile) cannot overlap the next tile's main loop the way the
+    # double-buffered 256-column pair GEMM does, and what the fusion saves is one re-read of X (0.04 ms per group).
+    if os.environ.get("DMF_FUSE_HEADS", "0") != "1":
+        return False
+    if out_bt is not None and any(t is not None for t in out_bt):
+        return False
+    return all(int(n) in (256, 512) for n, k in last_shapes)
+
+
 def wgrad_mn_ok(n_out: int, k_in: int) -> bool:
     """True when the wgrad of a Linear(k_in -> n_out) runs on the CTA-pair kernel with MN-major operands, i.e. reads the
     row-major bf16 activations dY [batch, n_out] and X [batch, k_in] as they are: no transposed copies are written
@@ -270,6 +284,8 @@ class _GroupedMLP(torch.autograd.Function):
                 outs, saved = _GroupedMLP._fwd_f32(xs, Ws, bs, G, NL, final, masks)
         ctx.saved = saved
         ctx.Ws, ctx.bs = Ws, bs
+        if precision == "bf16" and saved.get("head") is not None:
+            ctx.mark_non_differentiable(*outs[2 * G:])          # the bf16 copies of the head values
         return tuple(outs)
 
     # ---------------- fp32 (FFMA) path
@@ -439,6 +455,11 @@ class _GroupedMLP(torch.autograd.Function):
         actTs = [[t] for t in a0T]
         Wb = [[None] * NL for _ in range(G)]
         outs = []
+        head = opts.get("head")
+        if head is not None and not head_fusable([Ws[g][-1].shape for g in range(G)], out_bt):
+            raise L.DmfError("grouped MLP: the fused row head needs an output width of 256 or 512 and no "
+                             "transposed output copy (check ops.head_fusable first)")
+        head_saved, head_out, head_outb = [], [], []
         for l in range(NL):
             last = l == NL - 1
             descs = []
@@ -453,6 +474,26 @@ class _GroupedMLP(torch.autograd.Function):
                 M = A.shape[0]
                 Mp = (M + 7) // 8 * 8
                 d = dict(A=A, lda=A.stride(0), B=wb, ldb=Kp, bias=bs[g][l], M=M, N=N, K=K)
+                if last and head is not None:
+                    # the row head runs in this layer's epilogue (dmf_head_gemm_bf16): X itself (fp32: ortho term, head
+                    # backward; bf16: conditioning columns of the private encoders), the head value fp32 + bf16
+                    o = torch.empty(M, N, dtype=torch.float32, device=dev)
+                    y = torch.empty(M, N, dtype=torch.float32, device=dev)
+                    yb = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+                    hd = dict(A=A, W=wb, bias=bs[g][l], M=M, N=N, K=K, pre_f32=o, pre_bf16=out_b[g], out_f32=y, out_bf16=yb)
+                    if head["kind"] == 0:
+                        inv = torch.empty(M, dtype=torch.float32, device=dev)
+                        hd.update(inv_norm=inv, eps=head.get("eps", 1e-12))
+                        head_saved.append((y, inv))
+                    else:
+                        w_, v_ = head["noise"][g]
+                        hd.update(noise_w=_f32c(w_), noise_v=_f32c(v_))
+                        head_saved.append((o, hd["noise_w"], hd["noise_v"]))
+                    outs.append(o)
+                    head_out.append(y)
+                    head_outb.append(yb)
+                    descs.append(hd)
+                    continue
                 if last:
                     o = torch.empty(M, N, dtype=torch.float32, device=dev)
                     d.update(out_f32=o, ldo_f32=N)
@@ -473,8 +514,14 @@ class _GroupedMLP(torch.autograd.Function):
                     else:
                         actTs[g].append(None)
                 descs.append(d)
-            gemm_tc(descs, L.EPI_BIAS if (last and final != "relu") else L.EPI_BIAS_RELU)
-        return outs, dict(acts=acts, actTs=actTs, Wb=Wb, outs=outs if final == "relu" else None)
+            if last and head is not None:
+                head_gemm(descs, head["kind"])
+            else:
+                gemm_tc(descs, L.EPI_BIAS if (last and final != "relu") else L.EPI_BIAS_RELU)
+        if head is not None:
+            outs = outs + head_out + head_outb
+        return outs, dict(acts=acts, actTs=actTs, Wb=Wb, outs=outs if final == "relu" else None,
+                          head=(head["kind"], head_saved) if head is not None else None)
 
     @staticmethod
     def _bwd_bf16(ctx, grads):
@@ -575,6 +622,28 @@ class _GroupedMLP(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         G, NL, final, precision, masks, opts = ctx.cfg
+        if precision == "bf16" and ctx.saved.get("head") is not None:
+            # outputs were (X_g ..., head_g ..., bf16 copies): fold the head's backward into the gradient of X
+            kind, hs = ctx.saved["head"]
+            gx = []
+            with _Prof("head_bwd"):
+                for g in range(G):
+                    gpre, gout = grads[g], grads[G + g]
+                    if gout is None:
+                        gx.append(gpre)
+                        continue
+                    gout = _f32c(gout)
+                    R, D = gout.shape
+                    dx = _f32c(gpre).clone() if gpre is not None else torch.empty(R, D, dtype=torch.float32, device=gout.device)
+                    acc = 1 if gpre is not None else 0
+                    if kind == 0:
+                        y, inv = hs[g]
+                        check(lib.dmf_row_normalize_bwd(ptr(y), D, ptr(inv), ptr(gout), D, R, D, ptr(dx), D, acc, stream()))
+                    else:
+                        e, w_, v_ = hs[g]
+                        check(lib.dmf_vmf_bwd(ptr(e), D, ptr(w_), ptr(v_), ptr(gout), D, R, D, ptr(dx), D, acc, stream()))
+                    gx.append(dx)
+            grads = gx
         with _Prof("mlp_bwd"):
             if precision == "bf16":
                 dxs, dWs, dbs = _GroupedMLP._bwd_bf16(ctx, grads)

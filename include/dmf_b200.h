@@ -114,7 +114,7 @@ typedef struct {
   const float* noise_w;                   /* [M], head 1 */
   const float* noise_v;                   /* [M, N-1], head 1 */
   float eps;                              /* head 0 */
-  int M, N, K;                            /* K % 8 == 0 */
+  int M, N, K;                            /* lda, ldw multiples of 8 elements; columns >= K read as zero */
 } dmf_head_gemm_desc;
 int dmf_head_gemm_bf16(const dmf_head_gemm_desc* groups, int n_groups, int head, dmf_stream_t s);
 

@@ -592,6 +592,41 @@ def test_dssl_bf16_pair_kernel_path(dmf):
 
 
 
+@pytest.mark.parametrize("lmd,condzs", [(0.0, True), (0.3, True), (0.0, False)])
+def test_dssl_fused_head_epilogues(dmf, monkeypatch, lmd, condzs):
+    """DSSL bf16 step at embed width 256: vMF sample / F.normalize in the epilogue of the last encoder GEMMs
+    (dmf_head_gemm_bf16, head backward folded into the MLP op; opt-in: DMF_FUSE_HEADS=1) against the same step with the
+    separate head kernels: same bf16 operands, so loss, logs and every gradient agree to fp32 rounding of the epilogues.
+    lmd > 0 makes the ortho term differentiable (gradient into the PRE-head outputs of both encoder stacks)."""
+    torch.manual_seed(0)
+    dims, h, e, B = [256, 192], 512, 256, 512        # hidden 512: every wgrad reads MN-major (no transposed copies)
+    kw = dict(output_dim=dims, hidden_dim=h, embed_dim=e, precision="bf16", condzs=condzs,
+              lmd_start_value=lmd, lmd_end_value=lmd)
+    ma = dmf.DisentangledSSL(**kw).to(DEV)
+    mb = dmf.DisentangledSSL(**kw).to(DEV)
+    mb.load_state_dict(ma.state_dict())
+    gen = torch.Generator().manual_seed(1)
+    x1, x2 = torch.randn(B, dims[0], generator=gen).to(DEV), torch.randn(B, dims[1], generator=gen).to(DEV)
+    v1, v2 = x1 + 0.01 * torch.randn_like(x1), x2 + 0.01 * torch.randn_like(x2)
+    torch.manual_seed(7)
+    noise = ma.draw_noise(B, DEV)
+    monkeypatch.setenv("DMF_FUSE_HEADS", "1")
+    n0 = dmf._lib.launch_count()
+    la, logsa = ma(x1, x2, v1, v2, noise=noise)
+    la.backward()
+    fused_launches = dmf._lib.launch_count() - n0
+    monkeypatch.setenv("DMF_FUSE_HEADS", "0")
+    n0 = dmf._lib.launch_count()
+    lb, logsb = mb(x1, x2, v1, v2, noise=noise)
+    lb.backward()
+    assert dmf._lib.launch_count() - n0 > fused_launches, "the fused path must launch fewer kernels"
+    assert_close(la, lb, 2e-4, "loss")
+    for k in ("shared", "specific", "ortho", "loss_x", "loss_y"):
+        assert_close(logsa[k], logsb[k], 2e-3, k, atol=1e-5)
+    for (k, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert_close(p.grad, q.grad, 5e-3, "grad " + k)
+
+
 @pytest.mark.parametrize("prec,tol", [("fp32", FP32), ("bf16", 2e-2)])
 def test_grouped_mlp_vs_torch(dmf, prec, tol):
     """Ragged groups (HandWritten-like widths), fwd + dgrad + wgrad + bias grad vs plain torch fp32."""

@@ -211,7 +211,12 @@ extern "C" int dmf_grouped_gemm_bf16_tc(const dmf_tc_gemm_desc* groups, int n_gr
     if (d.M == 0 || d.N == 0) continue;
     DMF_REQUIRE(d.A && d.B && (d.out_f32 || d.out_bf16 || d.out_bf16_t), "dmf_grouped_gemm_bf16_tc: null pointer in group %d", i);
     DMF_REQUIRE(epilogue != DMF_EPI_RELU_MASK || d.mask_bf16, "dmf_grouped_gemm_bf16_tc: RELU_MASK needs mask (group %d)", i);
-    if (d.M < 512 || d.N < 128) pair_ok = false;
+    // skinny wgrad shapes (tiny output, K = batch: the probe heads' [128, 512] weight gradients at K = 65536 ran for
+    // 0.3 ms on 16 single-CTA tiles) also go to the pair kernel: it splits K over the 74 clusters, and the unused
+    // second 128 rows of a tile are TMA zero fill
+    const bool skinny = epilogue == DMF_EPI_NONE && d.out_f32 && !d.out_bf16 && !d.out_bf16_t && d.split_k != 1 &&
+                        d.K >= 4096 && d.M >= 128 && d.N >= 128;
+    if ((d.M < 512 || d.N < 128) && !skinny) pair_ok = false;
     any_mn = any_mn || d.mn_major != 0;
     DMF_REQUIRE(!d.mn_major || ((d.lda & 7) == 0 && (d.ldb & 7) == 0), "dmf_grouped_gemm_bf16_tc: mn_major needs row pitches that are multiples of 8 (group %d)", i);
   }

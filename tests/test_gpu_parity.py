@@ -487,6 +487,23 @@ def test_tc_gemm_pair_kernel(dmf, M, N, K, epi):
         assert_close(outT[:, :M].float().T, ref, 1e-2, "pair gemm transposed bf16 out")
 
 
+def test_tc_gemm_skinny_wgrad_takes_the_pair_kernel(dmf):
+    """[128, 512] output with K = 16 384 (the probe heads' weight gradients): routed to the CTA-pair kernel with automatic
+    split-K (three groups per launch, zeroed outputs); the second 128 rows of every tile are TMA zero fill."""
+    ops, Lb = dmf.ops, dmf._lib
+    gen = torch.Generator().manual_seed(5)
+    M, N, K = 128, 512, 16384
+    descs, refs = [], []
+    for g in range(3):
+        A = (torch.randn(M, K, generator=gen) / 8).to(DEV).bfloat16()
+        Bm = (torch.randn(N, K, generator=gen) / 8).to(DEV).bfloat16()
+        refs.append(A.float().cpu() @ Bm.float().cpu().T)
+        descs.append(dict(A=A, lda=K, B=Bm, ldb=K, out_f32=torch.zeros(M, N, device=DEV), ldo_f32=N, M=M, N=N, K=K, split_k=0))
+    ops.gemm_tc(descs, Lb.EPI_NONE)
+    for d, ref in zip(descs, refs):
+        assert_close(d["out_f32"], ref, 1e-4, "skinny wgrad")
+
+
 @pytest.mark.parametrize("split", [0, 1, 7])
 def test_tc_gemm_split_k(dmf, split):
     """wgrad shape: tiny output, K = batch; split-K partial tiles accumulate with red.add into a zeroed output."""

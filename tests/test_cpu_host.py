@@ -1,6 +1,7 @@
 """CPU-side tests (no GPU): the C-ABI library loads and exports every symbol the header declares,
 the module mirrors reproduce the reference's parameter layout / init stream / noise stream, and the
 data-parallel host logic works under gloo with world_size 2."""
+import ctypes as C
 import os
 import re
 import subprocess
@@ -24,6 +25,30 @@ def test_library_exports_every_header_symbol():
         assert hasattr(L.lib, n), f"{n} declared in include/dmf_b200.h but not exported by libdmf_b200.so"
     assert set(L.EXPORTS) == names, set(L.EXPORTS) ^ names
     assert L.lib.dmf_version() == 100
+
+
+def test_stored_probability_buffer_sizes():
+    """Host-side size helpers of the stored-probability InfoNCE path (no compute): E is made of [128 x 64] bf16 blocks
+    covering the row count padded to 256 and the column count padded to 256; the scratch holds both padded factor arrays."""
+    import disentagled_multimodal_fusion_b200._lib as L
+    for Ma, Nb in ((65536, 65536), (8192, 65536), (300, 1100), (1, 1), (256, 257)):
+        nib, njb = 2 * ((Ma + 255) // 256), 4 * ((Nb + 255) // 256)
+        assert int(L.lib.dmf_infonce_e_bytes(Ma, Nb)) == nib * njb * 128 * 64 * 2
+        assert int(L.lib.dmf_infonce_bwd_stored_work_floats(Ma, Nb)) == 128 * nib + 64 * njb
+    assert int(L.lib.dmf_infonce_e_bytes(65536, 65536)) == 2 * 65536 * 65536           # 8.6 GB per critic call at C5
+    assert int(L.lib.dmf_infonce_e_bytes(0, 5)) == 0
+
+
+def test_stored_probability_calls_reject_bad_arguments():
+    """Argument errors of the new entry points surface as status < 0 + a message, before anything is launched."""
+    import disentagled_multimodal_fusion_b200._lib as L
+    rc = L.lib.dmf_infonce_bwd_stored(None, 4, 4, None, None, 1.0, None, 0, 512, 0, 1.0, None, 0, None, 0, 0, None, None)
+    assert rc < 0
+    buf = C.create_string_buffer(512)
+    L.lib.dmf_last_error(buf, 512)
+    assert b"dmf_infonce_bwd_stored" in buf.value
+    rc = L.lib.dmf_head_gemm_bf16(None, 0, 0, None)
+    assert rc < 0
 
 
 def test_no_cpu_fallback():

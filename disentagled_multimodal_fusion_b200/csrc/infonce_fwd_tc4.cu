@@ -43,47 +43,68 @@ __device__ __forceinline__ float f4_exp2(float x) {
   return y;
 }
 
-// Sum over the 32 lanes of e[j] for every j; lane L returns the total of column L.
+// packed fp32x2 (FFMA2 / FADD2: one issue slot for two elements; the softmax warps are issue / latency bound)
+__device__ __forceinline__ unsigned long long f4_pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f4_unpk2(unsigned long long a, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+}
+__device__ __forceinline__ unsigned long long f4_add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f4_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// Sum over the 32 lanes of e[j] for every j; lane L returns the total of column L.  The additions of each butterfly level
+// run two columns per instruction.
 __device__ __forceinline__ float warp_colsum32(float (&e)[32], int lane) {
   float t16[16];
   {
     const bool up = lane & 16;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float send = up ? e[k] : e[k + 16];
-      const float keep = up ? e[k + 16] : e[k];
-      t16[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    for (int k = 0; k < 16; k += 2) {
+      const float s0 = up ? e[k] : e[k + 16], s1 = up ? e[k + 1] : e[k + 17];
+      const float k0 = up ? e[k + 16] : e[k], k1 = up ? e[k + 17] : e[k + 1];
+      f4_unpk2(f4_add2(f4_pk2(k0, k1), f4_pk2(__shfl_xor_sync(0xffffffffu, s0, 16), __shfl_xor_sync(0xffffffffu, s1, 16))),
+               t16[k], t16[k + 1]);
     }
   }
   float t8[8];
   {
     const bool up = lane & 8;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float send = up ? t16[k] : t16[k + 8];
-      const float keep = up ? t16[k + 8] : t16[k];
-      t8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    for (int k = 0; k < 8; k += 2) {
+      const float s0 = up ? t16[k] : t16[k + 8], s1 = up ? t16[k + 1] : t16[k + 9];
+      const float k0 = up ? t16[k + 8] : t16[k], k1 = up ? t16[k + 9] : t16[k + 1];
+      f4_unpk2(f4_add2(f4_pk2(k0, k1), f4_pk2(__shfl_xor_sync(0xffffffffu, s0, 8), __shfl_xor_sync(0xffffffffu, s1, 8))),
+               t8[k], t8[k + 1]);
     }
   }
   float t4[4];
   {
     const bool up = lane & 4;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float send = up ? t8[k] : t8[k + 4];
-      const float keep = up ? t8[k + 4] : t8[k];
-      t4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    for (int k = 0; k < 4; k += 2) {
+      const float s0 = up ? t8[k] : t8[k + 4], s1 = up ? t8[k + 1] : t8[k + 5];
+      const float k0 = up ? t8[k + 4] : t8[k], k1 = up ? t8[k + 5] : t8[k + 1];
+      f4_unpk2(f4_add2(f4_pk2(k0, k1), f4_pk2(__shfl_xor_sync(0xffffffffu, s0, 4), __shfl_xor_sync(0xffffffffu, s1, 4))),
+               t4[k], t4[k + 1]);
     }
   }
   float t2[2];
   {
     const bool up = lane & 2;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const float send = up ? t4[k] : t4[k + 2];
-      const float keep = up ? t4[k + 2] : t4[k];
-      t2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
+    const float s0 = up ? t4[0] : t4[2], s1 = up ? t4[1] : t4[3];
+    const float k0 = up ? t4[2] : t4[0], k1 = up ? t4[3] : t4[1];
+    f4_unpk2(f4_add2(f4_pk2(k0, k1), f4_pk2(__shfl_xor_sync(0xffffffffu, s0, 2), __shfl_xor_sync(0xffffffffu, s1, 2))), t2[0], t2[1]);
   }
   const bool up = lane & 1;
   const float send = up ? t2[0] : t2[1];
@@ -312,16 +333,29 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
         float e[32];
         if (nvalid >= 32) {
+          const unsigned long long sl2p = f4_pk2(P.sl2, P.sl2), shp = f4_pk2(-my_shift, -my_shift);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) e[j] = f4_exp2(fmaf(__uint_as_float(r[j]), P.sl2, -my_shift));
+          for (int j = 0; j < 32; j += 2) {
+            float a0, a1;
+            f4_unpk2(f4_fma2(f4_pk2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sl2p, shp), a0, a1);
+            e[j] = f4_exp2(a0);
+            e[j + 1] = f4_exp2(a1);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) e[j] = j < nvalid ? f4_exp2(fmaf(__uint_as_float(r[j]), P.sl2, -my_shift)) : 0.f;
         }
-        float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+        {
+          unsigned long long pa = f4_pk2(e[0], e[1]), pb = f4_pk2(e[2], e[3]);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) { ps0 += e[j]; ps1 += e[j + 1]; ps2 += e[j + 2]; ps3 += e[j + 3]; }
-        l += (ps0 + ps1) + (ps2 + ps3);
+          for (int j = 4; j < 32; j += 4) {
+            pa = f4_add2(pa, f4_pk2(e[j], e[j + 1]));
+            pb = f4_add2(pb, f4_pk2(e[j + 2], e[j + 3]));
+          }
+          float q0, q1;
+          f4_unpk2(f4_add2(pa, pb), q0, q1);
+          l += q0 + q1;
+        }
         if (P.store_e) {
           const uint32_t my_stage = my_stage0 + ebuf * 2048;
 #if DMF_F4_VAR == 1

@@ -133,6 +133,13 @@ struct F4Args {
 
 // 32 consecutive e values of one row -> bf16 -> this thread's 64-byte row of the warp's [32 x 64 B] staging tile (16-byte
 // chunk index XOR ((row >> 1) & 3): the 64B TMA swizzle, conflict-free for 16-byte stores of 8 consecutive rows)
+#ifndef DMF_F4_COLSUM_MMA
+// 1: column sums as a ones x E product on the tensor core (ldmatrix.trans + mma.sync m16n8k16 from the staged bf16 tile:
+// 4 LDSM + 8 HMMA per chunk instead of 31 SHFL + 62 FSEL + 16 FADD2).  Parity green, but SLOWER on B200: cross block
+// 3.80 ms against 2.90 ms (with the E store 4.60 against 3.86 ms) -- the legacy mma.sync path shares the tensor pipe with
+// the tcgen05 stream that bounds the kernel.  Kept for the record; the fp32 warp butterfly (0) is the product path.
+#define DMF_F4_COLSUM_MMA 0
+#endif
 #ifndef DMF_F4_VAR
 #define DMF_F4_VAR 0      // timing variants, tools builds only: 1 = stage only (no TMA store), 2 = truncating pack, 3 = no column sums, 4 = no bulk-group wait, 5 = no proxy fence, 6 = neither (4-6: WRONG results)
 #endif
@@ -356,6 +363,52 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           f4_unpk2(f4_add2(pa, pb), q0, q1);
           l += q0 + q1;
         }
+#if DMF_F4_COLSUM_MMA
+        // The staged bf16 tile serves BOTH consumers: the TMA store of E (when kept) and the column sums, which are a
+        // ones x E product on the tensor core (ldmatrix.trans + mma.sync m16n8k16 from the staging tile) instead of a
+        // 32-lane butterfly: 4 LDSM + 8 HMMA + 1 red.v2 against 31 SHFL + 62 FSEL + 16 FADD2 per chunk.
+        if (P.store_e || want_cols) {
+          const uint32_t my_stage = my_stage0;
+          if (P.store_e && tc::elect_one()) f4_store_wait_read();     // the last store has read the staging tile
+          __syncwarp();
+          f4_stage_e(my_stage + (uint32_t)(lane * 64), lane, e);
+          if (P.store_e) tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the TMA engine (async proxy)
+          __syncwarp();
+          if (P.store_e && tc::elect_one()) f4_tma_store_2d(&tmE, my_stage, e_c0, e_c1, e_policy);
+          if (want_cols) {
+            float c0 = 0.f, c1 = 0.f;
+            const int g = lane >> 2;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              // lane L supplies row L of the 8-column group b: matrices = rows 0-7, 8-15, 16-23, 24-31
+              uint32_t m0r, m1r, m2r, m3r;
+              asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(m0r), "=r"(m1r), "=r"(m2r), "=r"(m3r)
+                           : "r"(my_stage + (uint32_t)(lane * 64) + (((uint32_t)b ^ (uint32_t)((lane >> 1) & 3)) << 4)));
+              float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+              const uint32_t ones = 0x3F803F80u;           // bf16 (1, 1)
+              asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, "
+                           "{%0, %1, %2, %3};"
+                           : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
+                           : "r"(ones), "r"(m0r), "r"(m1r));
+              asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, "
+                           "{%0, %1, %2, %3};"
+                           : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
+                           : "r"(ones), "r"(m2r), "r"(m3r));
+              // every row of D holds the column sums of columns 8 b + 2 (lane % 4) + {0, 1}; lane group g == b keeps them
+              if (g == b) { c0 = d0; c1 = d1; }
+            }
+            if (lane < 16) {
+              const int col = 8 * g + 2 * (lane & 3);
+              float* dst = P.col_sum + nbase + col;
+              if (col + 1 < nvalid)
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(c0), "f"(c1) : "memory");
+              else if (col < nvalid)
+                atomicAdd(dst, c0);
+            }
+          }
+        }
+#else
         if (P.store_e) {
           const uint32_t my_stage = my_stage0 + ebuf * 2048;
 #if DMF_F4_VAR == 1
@@ -380,6 +433,7 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const float cs = warp_colsum32(e, lane);
           if (lane < nvalid) atomicAdd(P.col_sum + nbase + lane, cs);
         }
+#endif
       }
       tc::tc_fence_before_sync();
       __syncwarp();
@@ -439,7 +493,11 @@ extern "C" int dmf_infonce_rowcol_sums_store(const void* A, long long lda, int M
   // so that the 8 x 2 KB staging tiles have a fixed, 1024-aligned offset
   // with E: 4-stage ring + one 2 KB staging tile per softmax warp (F4_SW = 16); F4_SW = 8 keeps two tiles per warp
   const int ebufs = 16 / F4_SW;
+#if DMF_F4_COLSUM_MMA
+  const size_t smem = F4_SMEM_MAX;       // the staging tiles also feed the column sums
+#else
   const size_t smem = E ? F4_SMEM_MAX : 1024 + (size_t)(num_kb + F4_STAGES) * F4_TILE + 256 + 2048;
+#endif
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(rowcol_sum_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -449,7 +507,7 @@ extern "C" int dmf_infonce_rowcol_sums_store(const void* A, long long lda, int M
   }
   F4Args P;
   P.estage_bufs = E ? ebufs : 1;
-  P.stages = E ? F4_STAGES - 1 : F4_STAGES;
+  P.stages = (E || DMF_F4_COLSUM_MMA) ? F4_STAGES - 1 : F4_STAGES;
   P.Ma = Ma; P.Nb = Nb; P.num_kb = num_kb;
   P.scale = scale;
   P.sl2 = scale * kLog2eF4;

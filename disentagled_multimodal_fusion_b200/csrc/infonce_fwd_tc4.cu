@@ -140,6 +140,14 @@ struct F4Args {
 // the tcgen05 stream that bounds the kernel.  Kept for the record; the fp32 warp butterfly (0) is the product path.
 #define DMF_F4_COLSUM_MMA 0
 #endif
+// 1: the two softmax warps that hold the two 32-column halves of the same [32 rows x 64 columns] piece of an E block share
+// one 4 KB staging tile and ONE TMA store of full 128-byte rows (two 64-thread named barriers per chunk).  Tried because
+// the per-warp variant (0) stores 64-byte row segments (134 M store requests per launch next to 131 M operand-tile
+// requests); parity green, NOT faster: 4.05 ms against 3.86-3.90 ms -- halving the request count buys nothing, the pair
+// barriers cost a little.  Kept for the record.
+#ifndef DMF_F4_PAIR_STORE
+#define DMF_F4_PAIR_STORE 0
+#endif
 #ifndef DMF_F4_VAR
 #define DMF_F4_VAR 0      // timing variants, tools builds only: 1 = stage only (no TMA store), 2 = truncating pack, 3 = no column sums, 4 = no bulk-group wait, 5 = no proxy fence, 6 = neither (4-6: WRONG results)
 #endif
@@ -168,6 +176,31 @@ __device__ __forceinline__ void f4_tma_store_2d(const CUtensorMap* d, uint32_t s
                "r"(smem_src), "r"(c0), "r"(c1), "l"(policy)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void f4_pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+// Pair variant: warp `hf` (0 / 1) of the pair writes its 64-byte half of every row of the pair's [32 x 128 B] tile (128B TMA
+// swizzle: 16-byte chunk k of row r sits at chunk k ^ (r & 7): conflict-free), warp 0 issues the store of the whole tile.
+__device__ __forceinline__ void f4_store_wait_read();
+__device__ __forceinline__ void f4_tma_store_2d(const CUtensorMap* d, uint32_t smem_src, int c0, int c1, uint64_t policy);
+__device__ __forceinline__ void f4_store_chunk_pair(const CUtensorMap* tmE, uint32_t tile, int bar_id, int hf, int lane,
+                                                    const float (&e)[32], int e_c1, uint64_t policy) {
+  if (hf == 0 && tc::elect_one()) f4_store_wait_read();      // the last store has read the tile (the same lane issues)
+  f4_pair_bar(bar_id);
+  const uint32_t rowp = tile + (uint32_t)(lane * 128);
+  const uint32_t x = (uint32_t)(lane & 7);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[k]) : "f"(e[g * 8 + 2 * k + 1]), "f"(e[g * 8 + 2 * k]));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + ((((uint32_t)(hf * 4 + g)) ^ x) << 4)), "r"(w[0]),
+                 "r"(w[1]), "r"(w[2]), "r"(w[3])
+                 : "memory");
+  }
+  tc::fence_proxy_async_smem();            // generic-proxy stores -> visible to the TMA engine (async proxy)
+  f4_pair_bar(bar_id);
+  if (hf == 0 && tc::elect_one()) f4_tma_store_2d(tmE, tile, 0, e_c1, policy);
 }
 __device__ __forceinline__ void f4_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void f4_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -290,6 +323,16 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const long long dj = (P.diag_offset >= 0 && rvalid) ? P.diag_offset + row : -1;
     const uint32_t s_empty_leader0 = tc2::mapa(tc::smem_u32(s_empty), 0);
     const uint32_t my_stage0 = tc::smem_u32(estage) + (uint32_t)(sw * 2048 * P.estage_bufs);
+#if DMF_F4_PAIR_STORE
+    // chunk c of warp (q, ch) = columns (ch / 2) * 128 + c * 64 + (ch & 1) * 32: warps ch and ch ^ 1 hold the two halves of
+    // the same 64-column E block at the same time
+    static_assert(F4_SW == 16, "the pair store maps 4 column groups onto 2 pairs");
+    const int cofs = (ch >> 1) * 128 + (ch & 1) * 32, cstep = 64;
+    const int hf = ch & 1, pair_bar = 1 + q * 2 + (ch >> 1);
+    const uint32_t pair_tile = tc::smem_u32(estage) + (uint32_t)((q * 2 + (ch >> 1)) * 4096);
+#else
+    const int cofs = ch * F4_WCOLS, cstep = 32;
+#endif
     uint32_t ebuf = 0;                                          // staging tile of the next E store
     const uint64_t e_policy = tc::l2_policy_evict_first();      // E is written once and read much later
     for (int t = 0; t < ntiles; ++t) {
@@ -299,18 +342,27 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const bool want_cols = P.col_sum != nullptr && !(P.sym && J == Ig);
       tc::mbar_wait(s_full + buf, ((uint32_t)t >> 1) & 1);
       tc::tc_fence_after_sync();
-      const int j0 = J * F4_BN + ch * F4_WCOLS;
+      const int j0 = J * F4_BN + cofs;
 #pragma unroll 1
       for (int c = 0; c < F4_WCOLS / 32; ++c) {
         uint32_t r[32];
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * F4_BN + ch * F4_WCOLS + c * 32), r);
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * F4_BN + cofs + c * cstep), r);
         tc::tmem_ld_wait();
-        const int nbase = j0 + c * 32;
+        const int nbase = j0 + c * cstep;
         const int nvalid = P.Nb - nbase;
         // E: the warp's [32 rows x 32 columns] piece goes to block rows q*32.. of block (m0 / 128, nbase / 64), column
         // (c & 1) * 32 inside the block
         const int e_c0 = (c & 1) * 32, e_c1 = ((m0 >> 7) * P.njb + (nbase >> 6)) * 128 + q * 32;
         if (nvalid <= 0) {                         // warp-uniform
+#if DMF_F4_PAIR_STORE
+          if (P.store_e) {
+            float z[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) z[j] = 0.f;
+            f4_store_chunk_pair(&tmE, pair_tile, pair_bar, hf, lane, z, e_c1, e_policy);
+          }
+          continue;
+#endif
           if (P.store_e) {
             float z[32];
 #pragma unroll
@@ -409,7 +461,12 @@ rowcol_sum_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
         }
 #else
+#if DMF_F4_PAIR_STORE
+        if (P.store_e) f4_store_chunk_pair(&tmE, pair_tile, pair_bar, hf, lane, e, e_c1, e_policy);
+        if (false) {
+#else
         if (P.store_e) {
+#endif
           const uint32_t my_stage = my_stage0 + ebuf * 2048;
 #if DMF_F4_VAR == 1
           f4_stage_e(my_stage + (uint32_t)(lane * 64), lane, e);
@@ -521,7 +578,11 @@ extern "C" int dmf_infonce_rowcol_sums_store(const void* A, long long lda, int M
   P.njb = 4 * P.total_tiles;
   CUtensorMap tmE;
   if (E) {
+#if DMF_F4_PAIR_STORE
+    rc = make_tmap_bf16_2d(&tmE, E, 2LL * ((Ma + 255) / 256) * P.njb * 128, 64, 64, 32);    // [32 rows x 64 cols] boxes, 128B swizzle
+#else
     rc = make_tmap_bf16_2d_box32_sw64(&tmE, E, 2LL * ((Ma + 255) / 256) * P.njb * 128);
+#endif
     if (rc) return rc;
   } else {
     tmE = tmA;      // never dereferenced

@@ -178,6 +178,22 @@ dz1 = coef * (W1 @ g0 - 2 * g0[lo:hi])
 assert abs(float(part) - float(ref)) < 1e-5 * abs(float(ref)), (float(part), float(ref))
 assert (dz0 - ra[lo:hi]).abs().max() < 1e-5 * ra.abs().max()
 assert (dz1 - rb[lo:hi]).abs().max() < 1e-5 * rb.abs().max()
+# stored-probability decomposition (ops._InfoNCE with E kept by the forward): with the fixed shift 1/T,
+#   e = exp(s01 - 1/T),  fa = exp(1/T - lse0) (local rows),  fb = exp(1/T - lse1_all) (all columns),
+# dir 0 gives the local view-0 rows; dir 1 gives a PARTIAL view-1 gradient for EVERY global column from this rank's E rows
+# (the positive term only for the columns this rank owns), summed over ranks by a reduce-scatter
+shift = 1.0 / T
+e = torch.exp(s01 - shift)
+fa, fb = torch.exp(shift - lse0), torch.exp(shift - lse1_all)
+Wst = e * (fa[:, None] + fb[None, :])
+dz0_st = coef * (Wst @ g1 - 2 * g1[lo:hi])
+part1 = Wst.T @ l0
+part1[lo:hi] -= 2 * l0
+part1 = coef * part1
+dist.all_reduce(part1)                       # gloo: all-reduce + own slice == NCCL reduce-scatter
+dz1_st = part1[lo:hi]
+assert (dz0_st - ra[lo:hi]).abs().max() < 1e-5 * ra.abs().max()
+assert (dz1_st - rb[lo:hi]).abs().max() < 1e-5 * rb.abs().max()
 # flat gradient all-reduce = SUM over ranks of per-shard grads of globally-normalised losses
 w = torch.nn.Parameter(torch.ones(D))
 (( (l0 * w).sum() ) / B).backward()

@@ -197,6 +197,40 @@ def supcon(z0: Tensor, z1: Tensor, T: float = 0.07) -> Tuple[Tensor, Tensor, Ten
     return loss, lx, ly
 
 
+def supcon_stored_probabilities(z0: Tensor, z1: Tensor, T: float = 0.07):
+    """The quantities of the stored-probability form of SupConLoss's backward for L2-NORMALISED views (what
+    models/disentangledssl.py:134-140 feeds; models/losses.py:64-99 under autograd):
+        e_ij = exp(s_ij - 1/T),  lseA_i = log sum_j exp(s_ij),  lseB_j = log sum_i exp(s_ij)   (cross block only: the
+        reference masks the intra-view logits out of the denominator),
+        exp(s_ij - lseA_i) + exp(s_ij - lseB_j) = e_ij (fa_i + fb_j),  fa = exp(1/T - lseA),  fb = exp(1/T - lseB),
+        dz0 = (W z1 - 2 z1) / (2 B T),  dz1 = (W^T z0 - 2 z0) / (2 B T)  with  W = e (fa + fb).
+    Returns (e, fa, fb, dz0, dz1)."""
+    B = z0.shape[0]
+    s = z0 @ z1.T / T
+    e = torch.exp(s - 1.0 / T)
+    fa, fb = 1.0 / e.sum(1), 1.0 / e.sum(0)
+    W = e * (fa[:, None] + fb[None, :])
+    coef = 1.0 / (2 * B * T)
+    return e, fa, fb, coef * (W @ z1 - 2 * z1), coef * (W.T @ z0 - 2 * z0)
+
+
+def infonce_e_blocks(e: Tensor) -> Tensor:
+    """Dense [Ma, Nb] probabilities -> the blocked HBM layout of dmf_infonce_rowcol_sums_store / dmf_infonce_bwd_stored
+    (include/dmf_b200.h): blocks of [128 rows x 64 columns], block (ib, jb) at index ib * njb + jb, rows padded to a
+    multiple of 256 and columns to a multiple of 256 with zeros.  Returns [nib * njb, 128, 64]."""
+    Ma, Nb = e.shape
+    nib, njb = 2 * ((Ma + 255) // 256), 4 * ((Nb + 255) // 256)
+    pad = torch.zeros(nib * 128, njb * 64, dtype=e.dtype)
+    pad[:Ma, :Nb] = e
+    return pad.view(nib, 128, njb, 64).permute(0, 2, 1, 3).reshape(nib * njb, 128, 64).contiguous()
+
+
+def infonce_e_unblock(blocks: Tensor, Ma: int, Nb: int) -> Tensor:
+    """inverse of ``infonce_e_blocks``"""
+    nib, njb = 2 * ((Ma + 255) // 256), 4 * ((Nb + 255) // 256)
+    return blocks.view(nib, njb, 128, 64).permute(0, 2, 1, 3).reshape(nib * 128, njb * 64)[:Ma, :Nb]
+
+
 def ortho_loss(z1: Tensor, zs: Tensor) -> Tensor:
     """models/losses.py:104-110."""
     return torch.norm(torch.matmul(F.normalize(z1, dim=-1).T, F.normalize(zs, dim=-1)))

@@ -4,6 +4,8 @@ properties pin its STRUCTURE on random inputs: closed forms, symmetries and limi
 (utils.py:46-116, models/losses.py:17-248, models/classifiers.py:314-437) imply.  float64 so the assertions are sharp."""
 import math
 
+import pytest
+
 import torch
 from hypothesis import given, settings, strategies as st
 
@@ -155,3 +157,24 @@ def test_uncertainty_summaries_limits():
     conf[0, 4] = 1e6
     u2, ale2, arg2 = port.uncertainty_summaries(conf)
     assert float(u2) < 1e-4 and int(arg2) == 4 and float(ale2) < float(ale[0])
+
+
+def test_stored_probability_form_of_the_supcon_backward():
+    """e (fa + fb) reproduces the autograd gradient of the reference formula for unit-norm views (the identity the
+    stored-probability kernels rely on), and the blocked E layout round-trips with zero padding."""
+    gen = torch.Generator().manual_seed(21)
+    B, D = 70, 24
+    z0 = torch.nn.functional.normalize(torch.randn(B, D, generator=gen, dtype=torch.float64), dim=-1)
+    z1 = torch.nn.functional.normalize(0.5 * z0 + 0.5 * torch.randn(B, D, generator=gen, dtype=torch.float64), dim=-1)
+    a, b = z0.clone().requires_grad_(), z1.clone().requires_grad_()
+    loss, _, _ = port.supcon(a, b)
+    ga, gb = torch.autograd.grad(loss, (a, b))
+    e, fa, fb, dz0, dz1 = port.supcon_stored_probabilities(z0, z1)
+    assert float((dz0 - ga).abs().max()) < 1e-9 * float(ga.abs().max()) + 1e-15
+    assert float((dz1 - gb).abs().max()) < 1e-9 * float(gb.abs().max()) + 1e-15
+    assert float(e.max()) <= 1.0 + 1e-12          # |s| <= 1/T: the fixed shift is the row maximum bound
+    blocks = port.infonce_e_blocks(e)
+    assert blocks.shape == (2 * 4, 128, 64)
+    assert torch.equal(port.infonce_e_unblock(blocks, B, B), e)
+    assert float(blocks.sum()) == pytest.approx(float(e.sum()), rel=1e-12)      # padding is zero
+    assert torch.equal(blocks[0, :B, :64], e[:, :64]) and float(blocks[1, :, 6:].abs().max()) == 0.0

@@ -855,14 +855,19 @@ def run_gpu(args, rank, world, local_rank):
                 "executed_over_algorithmic_flops": cap.get("executed_over_algorithmic_flops"),
                 "tensor_pipe_active_pct_ncu": cap.get("tensor_pipe_active_pct") if same_shape else None}
     stored_e = bool(ops._STORE_E) and prec == "bf16" and EMB in (256, 512)
-    bwd_kernel = ("infonce_bwd_e_kernel" if world == 1 else "infonce_bwd_e_kernel (local rows) + infonce_bwd_tc6_kernel "
-                  "(gathered columns)") if stored_e else "infonce_bwd_tc6_kernel"
+    bwd_kernel = "infonce_bwd_tc6_kernel"
+    if stored_e:
+        bwd_kernel = "infonce_bwd_e_kernel"
+        if world > 1 and not ops._DP_RS:
+            bwd_kernel = "infonce_bwd_e_kernel (local rows) + infonce_bwd_tc6_kernel (gathered columns)"
     roof_fwd = k2_roof("rowlse_x4", "rowcol_sum_tc4_kernel", 8, 12.0 * Bl * Bg * EMB,
                        "4 cross blocks (row + column sums" + (", exp(s - shift) kept in HBM as bf16" if stored_e else "") +
                        ") + 4 symmetric half-window blocks per step")
     roof_bwd = k2_roof("infonce_bwd", bwd_kernel, 8, 16.0 * Bl * Bg * EMB,
                        "4 critic calls x 2 gradient directions per step" +
-                       (", one product each from the stored probabilities" if stored_e else ", S recomputed per launch"))
+                       (", one product each from the stored probabilities" if stored_e else ", S recomputed per launch") +
+                       ("; the view-1 partial gradients of the ranks are summed by one NCCL reduce-scatter per call"
+                        if stored_e and world > 1 and ops._DP_RS else ""))
     roof = None
     cands = [r for r in (roof_fwd, roof_bwd) if r]
     if cands:

@@ -990,7 +990,7 @@ class _InfoNCE(torch.autograd.Function):
             with _Prof("grad_reduce_scatter"):
                 for h in pending:
                     h.wait()
-        ctx.estore = None
+        ctx.estore = [None] * nc        # free the probabilities now; a second backward (retain_graph) recomputes instead
         if layout is not None:
             return (None, *sgr)
         return (None, *grads)

@@ -13,7 +13,7 @@
 //   warp 1     (leader only) MMA issuer: 4 x tcgen05.mma 256x256x16 per stage, commit -> empty barrier of
 //              both CTAs; accumulators DOUBLE-BUFFERED in TMEM (2 x 256 columns) so the epilogue of item i
 //              overlaps the main loop of item i+1
-//   warps 2-9  epilogue: tcgen05.ld (lane quarter x column half), bias / ReLU / ReLU-mask, fp32 / bf16 /
+//   warps 2-9  epilogue (G2_EW = 8): tcgen05.ld (lane quarter x column half), bias / ReLU / ReLU-mask, fp32 / bf16 /
 //              transposed-bf16 stores; split-K items accumulate with red.global.add.v4.f32
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -22,12 +22,19 @@
 
 namespace dmf {
 
-constexpr int G2_THREADS = 320;
+// 16 epilogue warps (tried: 96 registers with small spills, 4-stage ring): K = 512 layers 934 -> 999 TFLOP/s, but K = 1024 / 1536
+// 1 223 -> 1 183 / 1 278 -> 1 259 and the MLP phases of the step unchanged within noise (6.97 vs 7.1 ms): 8 stays the default.
+#ifndef DMF_G2_EW
+#define DMF_G2_EW 8
+#endif
+constexpr int G2_EW = DMF_G2_EW;                      // epilogue warps per CTA (8 or 16): 4 lane quarters x G2_EW / 4 column groups
+constexpr int G2_THREADS = 64 + 32 * G2_EW;
+constexpr int G2_WCOLS = 256 / (G2_EW / 4);           // columns of the 256-wide tile per epilogue warp
 constexpr int G2_TILE = 128 * 64 * 2;   // 16 KB
-constexpr int G2_STAGES = 5;
+constexpr int G2_STAGES = G2_EW == 16 ? 4 : 5;        // 16 staging tiles (74 KB) leave room for a 4-stage ring
 constexpr int G2_BN = 256;
 constexpr int kMaxG2Groups = 8;
-constexpr size_t G2_SMEM_BYTES = 1024 + (size_t)G2_STAGES * 2 * G2_TILE + 8 * kEpiStageFloats * 4 + 512;
+constexpr size_t G2_SMEM_BYTES = 1024 + (size_t)G2_STAGES * 2 * G2_TILE + G2_EW * kEpiStageFloats * 4 + 512;
 
 struct G2Group {
   TcEpi epi;
@@ -76,8 +83,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + G2_STAGES * G2_TILE;
-  float* epi_stage = reinterpret_cast<float*>(smem + 2 * G2_STAGES * G2_TILE);      // [8 warps][32 x 36]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + 8 * kEpiStageFloats);
+  float* epi_stage = reinterpret_cast<float*>(smem + 2 * G2_STAGES * G2_TILE);      // [G2_EW warps][32 x 36]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + G2_EW * kEpiStageFloats);
   uint64_t* empty_bar = full_bar + G2_STAGES;
   uint64_t* acc_full = empty_bar + G2_STAGES;   // [2] per CTA (multicast commit)
   uint64_t* acc_empty = acc_full + 2;           // [2] leader: 16 epilogue warps of the pair drained the buffer
@@ -94,7 +101,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
       tc::tma_prefetch_desc(&P.tmB[i]);
     }
     for (int s = 0; s < G2_STAGES; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(acc_full + b, 1); tc::mbar_init(acc_empty + b, 16); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(acc_full + b, 1); tc::mbar_init(acc_empty + b, 2 * G2_EW); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc2::tmem_alloc2<512>(tmem_slot);
@@ -175,7 +182,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
     }
   } else {
     const int q = warp & 3;                  // TMEM lane quarter
-    const int ch = (warp - 2) >> 2;          // column half (128 columns) of the 256-wide tile
+    const int ch = (warp - 2) >> 2;          // column group (G2_WCOLS columns) of the 256-wide tile
     const uint32_t acc_empty_leader = tc2::mapa(tc::smem_u32(acc_empty), 0);
     float* my_stage = epi_stage + (warp - 2) * kEpiStageFloats;
     uint32_t n = 0;
@@ -188,8 +195,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
       tc::tc_fence_after_sync();
       if (it.kb1 > it.kb0) {
         // the TMEM read of chunk c + 1 is in flight while chunk c goes through the staging tile
-        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * G2_BN + (uint32_t)(ch * 128);
-        const int nb0 = it.n0 + ch * 128;
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * G2_BN + (uint32_t)(ch * G2_WCOLS);
+        const int nb0 = it.n0 + ch * G2_WCOLS;
         uint32_t ra[32], rb[32];
         auto emit = [&](const uint32_t (&r)[32], int c) {
           if (g.atomic) tc_epilogue_chunk<EPI, true>(g.epi, r, row0, lane, nb0 + c * 32, it.ks == 0, my_stage);
@@ -197,12 +204,12 @@ gemm_bf16_tc2_kernel(const __grid_constant__ G2Params P) {
         };
         tc::tmem_ld_32x32(t0, ra);
 #pragma unroll 1
-        for (int c2 = 0; c2 < 2; ++c2) {
+        for (int c2 = 0; c2 < G2_WCOLS / 64; ++c2) {
           tc::tmem_ld_wait();
           tc::tmem_ld_32x32(t0 + (uint32_t)(c2 * 64 + 32), rb);
           emit(ra, 2 * c2);
           tc::tmem_ld_wait();
-          if (c2 == 0) tc::tmem_ld_32x32(t0 + 64, ra);
+          if (c2 + 1 < G2_WCOLS / 64) tc::tmem_ld_32x32(t0 + (uint32_t)((c2 + 1) * 64), ra);
           emit(rb, 2 * c2 + 1);
         }
       }
